@@ -1,0 +1,211 @@
+// Shared helpers for libb200rl (sm_100a only): error convention, PTX wrappers for
+// mbarrier / TMA / tcgen05 / TMEM, small math utilities.
+//
+// Error convention (SURVEY.md §8b "C-ABI the replacement must export"): every entry point
+// returns 0 on success or a negative code; b200rl_last_error() returns a thread-local message.
+#pragma once
+#include <cuda.h>          // CUtensorMap types only; the driver symbol is resolved at run time
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace b200rl {
+
+enum : int {
+  B200RL_OK = 0,
+  B200RL_ERR_ARG = -1,       // bad argument (shape / alignment / null pointer)
+  B200RL_ERR_CUDA = -2,      // a CUDA runtime / driver call failed
+  B200RL_ERR_UNSUPPORTED = -3,
+  B200RL_ERR_STATE = -4,
+};
+
+int set_error(int code, const char* fmt, ...);
+
+#define B200RL_CUDA_OK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return ::b200rl::set_error(::b200rl::B200RL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);             \
+  } while (0)
+
+#define B200RL_REQUIRE(cond, ...)                                                         \
+  do {                                                                                    \
+    if (!(cond)) return ::b200rl::set_error(::b200rl::B200RL_ERR_ARG, __VA_ARGS__);       \
+  } while (0)
+
+#define B200RL_LAUNCH_OK()                                                                \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess)                                                                \
+      return ::b200rl::set_error(::b200rl::B200RL_ERR_CUDA, "kernel launch failed: %s (%s:%d)", \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);             \
+  } while (0)
+
+int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------------------
+// device helpers
+// ----------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 8 x bf16 <-> float[8] through one 16-byte vector
+struct __align__(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& in, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(in.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return o;
+}
+
+// ---- mbarrier ----------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must become a trap (reported as a CUDA error by the next
+// runtime call), never a hang of the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+      printf("b200rl: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+// ---- TMA -----------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+// ---- tcgen05 / TMEM ------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; one thread issues for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// tcgen05.commit: arrive on an mbarrier when all previously issued MMAs have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread i of the warp receives row (lane base + i).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b200rl

@@ -1,0 +1,474 @@
+// G1: persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+// Replaces the cuBLAS / bitsandbytes / Unsloth-Triton matmuls that the reference reaches through
+// `policy(...)` and `loss.backward()` (reference distributed_actor.py:241-243, :385, :483;
+// SURVEY.md §2.1 rows K1, K6).
+//
+//   C[M,N] = alpha * ( A1[M,K1] . B1[N,K1]^T  +  A2[M,K2] . B2[N,K2]^T ) (+ bias[N]) (+ R[M,N])
+//
+// * Operands are bf16, accumulation fp32 in TMEM, output bf16 or fp32.
+// * The second (A2,B2) segment is the LoRA side path: A2 = s*(X.A^T) (the rank-r intermediate),
+//   B2 = LoRA B, so "base GEMM + LoRA" is one mainloop over K1+K2 with no extra pass over C.
+// * Two layouts: TN (both operands K-major: activations x weights) and the "dW" form where both
+//   operands are MN-major (C[N_out, r] = Y^T . U, reduction over tokens), with optional split-K
+//   into fp32 partial slabs (deterministic: the slabs are summed in fixed order by the caller).
+//
+// Structure (one CTA per SM, 256 threads):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1   : MMA issuer     (one thread: tcgen05.mma kind::f16, M=128, N=BN, K=16 per instr)
+//   warp 2   : TMEM allocator (2 accumulator stages so the epilogue overlaps the next mainloop)
+//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> registers -> alpha/bias/residual -> global)
+#include "common.cuh"
+
+namespace b200rl {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;           // 64 bf16 = 128 B = one 128B-swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+
+struct GemmParams {
+  int M, N;
+  int kb1, kb2;          // k-blocks (of 64) in segment 1 / 2
+  int num_m_blocks, num_n_blocks, splits, kb_per_split;
+  void* C;
+  long long ldc;
+  long long c_split_stride;  // elements between split-K slabs
+  int c_fp32;
+  const bf16* bias;
+  const bf16* residual;
+  long long ldr;
+  float alpha;
+};
+
+// ---- descriptors ---------------------------------------------------------------------------
+// Shared-memory matrix descriptor (tcgen05), 128B swizzle. Field layout checked against
+// cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start[0,14) lbo[16,30) sbo[32,46) version[46,48)
+// layout_type[61,64) (SWIZZLE_128B = 2); addresses/offsets in 16-byte units.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (InstrDescriptor): c_format[4,6)=F32(1), a_format[7,10)=BF16(1),
+// b_format[10,13)=BF16(1), a_major bit15, b_major bit16 (0 = K-major, 1 = MN-major),
+// n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((mn_major ? 1u : 0u) << 15) |
+         ((mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int STAGES_RAW = (220 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+};
+
+template <int BN, bool MN_MAJOR>
+__global__ void __launch_bounds__(256, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+            const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+            const GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // 1024-byte aligned tile ring (SWIZZLE_128B atoms are 1024 B)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB1);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB2);
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_smem, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
+  const int kb_total = p.kb1 + p.kb2;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_blocks;
+      const int rest = tile / p.num_m_blocks;
+      const int n_blk = rest % p.num_n_blocks;
+      const int split = rest / p.num_n_blocks;
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(kb_begin + p.kb_per_split, kb_total);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem_gen + stage * C::STAGE_BYTES;
+        uint8_t* sb = sa + A_TILE_BYTES;
+        const bool seg2 = kb >= p.kb1;
+        const CUtensorMap* ta = seg2 ? &tmA2 : &tmA1;
+        const CUtensorMap* tb = seg2 ? &tmB2 : &tmB1;
+        const int k0 = (seg2 ? kb - p.kb1 : kb) * BK;
+        mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+        if constexpr (!MN_MAJOR) {
+          tma_load_2d(sa, ta, &full_bar[stage], k0, m_blk * BM);
+          tma_load_2d(sb, tb, &full_bar[stage], k0, n_blk * BN);
+        } else {
+          // operand stored [k][mn]: boxes of 64 (mn) x 64 (k); one 8 KB slab per 64 mn
+#pragma unroll
+          for (int h = 0; h < BM / 64; ++h)
+            tma_load_2d(sa + h * 8192, ta, &full_bar[stage], m_blk * BM + h * 64, k0);
+#pragma unroll
+          for (int h = 0; h < BN / 64; ++h)
+            tma_load_2d(sb + h * 8192, tb, &full_bar[stage], n_blk * BN + h * 64, k0);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(BN, MN_MAJOR);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int rest = tile / p.num_m_blocks;
+      const int split = rest / p.num_n_blocks;
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(kb_begin + p.kb_per_split, kb_total);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          uint64_t da, db;
+          if constexpr (!MN_MAJOR) {
+            // K-major, rows of 128 B, 8-row swizzle atoms 1024 B apart; +32 B per K=16 step
+            da = make_smem_desc(sa + k * 32, 16, 1024);
+            db = make_smem_desc(sb + k * 32, 16, 1024);
+          } else {
+            // MN-major: 64(mn) x 8(k) atoms of 1024 B; next 64 mn at +8192 (LBO),
+            // next 8 k at +1024 (SBO); K=16 step = two k-groups = +2048 B
+            da = make_smem_desc(sa + k * 2048, 8192, 1024);
+            db = make_smem_desc(sb + k * 2048, 8192, 1024);
+          }
+          umma_bf16(tmem_d, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int m_blk = tile % p.num_m_blocks;
+      const int rest = tile / p.num_m_blocks;
+      const int n_blk = rest % p.num_n_blocks;
+      const int split = rest / p.num_n_blocks;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr0 = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr0 + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < p.N) {  // N is a multiple of 8 (checked on the host)
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * p.alpha;
+              if (p.bias) {
+                float b[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(p.bias + col), b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += b[i];
+              }
+              if (p.residual) {
+                float b[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(p.residual + (long long)row * p.ldr + col),
+                        b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += b[i];
+              }
+              if (p.c_fp32) {
+                float* dst = reinterpret_cast<float*>(p.C) + (long long)split * p.c_split_stride +
+                             (long long)row * p.ldc + col;
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+                bf16* dst = reinterpret_cast<bf16*>(p.C) + (long long)split * p.c_split_stride +
+                            (long long)row * p.ldc + col;
+                *reinterpret_cast<bf16x8*>(dst) = pack8(v);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over X[rows][inner] with leading dimension ld (elements), 128B swizzle.
+static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(B200RL_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || ((ld * 2) & 15u) != 0)
+    return set_error(B200RL_ERR_ARG, "gemm operand must be 16-byte aligned with ld %% 8 == 0 (ld=%llu)",
+                     (unsigned long long)ld);
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(B200RL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu ld=%llu)",
+                     (int)r, (unsigned long long)inner, (unsigned long long)rows,
+                     (unsigned long long)ld);
+  return 0;
+}
+
+struct GemmArgs {
+  const void *A1, *B1, *A2, *B2;
+  long long lda1, ldb1, lda2, ldb2;
+  int K1, K2;
+  void* C;
+  long long ldc;
+  int c_fp32;
+  const void* bias;
+  const void* residual;
+  long long ldr;
+  float alpha;
+  int M, N;
+  int mn_major;   // 0: TN (K-major operands). 1: operands stored [K][M] / [K][N]
+  int splits;     // split-K factor (fp32 output slabs, c_split_stride apart)
+  long long c_split_stride;
+  int force_bn;   // 0 = heuristic
+  int max_ctas;   // 0 = all SMs
+};
+
+template <int BN, bool MN>
+static int launch(const GemmArgs& a, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  GemmParams p;
+  p.M = a.M;
+  p.N = a.N;
+  p.kb1 = (a.K1 + BK - 1) / BK;
+  p.kb2 = (a.K2 + BK - 1) / BK;
+  p.num_m_blocks = (a.M + BM - 1) / BM;
+  p.num_n_blocks = (a.N + BN - 1) / BN;
+  const int kb_total = p.kb1 + p.kb2;
+  p.splits = a.splits < 1 ? 1 : (a.splits > kb_total ? kb_total : a.splits);
+  p.kb_per_split = (kb_total + p.splits - 1) / p.splits;
+  p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.C = a.C;
+  p.ldc = a.ldc;
+  p.c_split_stride = a.c_split_stride;
+  p.c_fp32 = a.c_fp32;
+  p.bias = reinterpret_cast<const bf16*>(a.bias);
+  p.residual = reinterpret_cast<const bf16*>(a.residual);
+  p.ldr = a.ldr;
+  p.alpha = a.alpha;
+
+  CUtensorMap tA1, tB1, tA2, tB2;
+  int rc;
+  if (!MN) {
+    if ((rc = make_map(&tA1, a.A1, a.K1, a.M, a.lda1, BK, BM))) return rc;
+    if ((rc = make_map(&tB1, a.B1, a.K1, a.N, a.ldb1, BK, BN))) return rc;
+    if (a.K2 > 0) {
+      if ((rc = make_map(&tA2, a.A2, a.K2, a.M, a.lda2, BK, BM))) return rc;
+      if ((rc = make_map(&tB2, a.B2, a.K2, a.N, a.ldb2, BK, BN))) return rc;
+    } else {
+      tA2 = tA1;
+      tB2 = tB1;
+    }
+  } else {
+    // stored [K][M] and [K][N]
+    if ((rc = make_map(&tA1, a.A1, a.M, a.K1, a.lda1, 64, BK))) return rc;
+    if ((rc = make_map(&tB1, a.B1, a.N, a.K1, a.ldb1, 64, BK))) return rc;
+    if (a.K2 > 0) {
+      if ((rc = make_map(&tA2, a.A2, a.M, a.K2, a.lda2, 64, BK))) return rc;
+      if ((rc = make_map(&tB2, a.B2, a.N, a.K2, a.ldb2, 64, BK))) return rc;
+    } else {
+      tA2 = tA1;
+      tB2 = tB1;
+    }
+  }
+  auto kern = gemm_kernel<BN, MN>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
+  int ctas = num_sms();
+  if (a.max_ctas > 0 && a.max_ctas < ctas) ctas = a.max_ctas;
+  if (tiles < ctas) ctas = tiles;
+  kern<<<ctas, 256, C::SMEM_BYTES, stream>>>(tA1, tB1, tA2, tB2, p);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
+int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
+  B200RL_REQUIRE(a.M > 0 && a.N > 0 && a.K1 > 0 && a.K2 >= 0, "gemm: bad shape M=%d N=%d K1=%d K2=%d",
+                 a.M, a.N, a.K1, a.K2);
+  B200RL_REQUIRE(a.A1 && a.B1 && a.C, "gemm: null operand");
+  B200RL_REQUIRE(a.K2 == 0 || (a.A2 && a.B2), "gemm: K2 > 0 needs A2/B2");
+  B200RL_REQUIRE(a.N % 8 == 0 && a.ldc % 8 == 0, "gemm: N and ldc must be multiples of 8 (N=%d ldc=%lld)",
+                 a.N, a.ldc);
+  B200RL_REQUIRE((reinterpret_cast<uintptr_t>(a.C) & 15u) == 0, "gemm: C must be 16-byte aligned");
+  B200RL_REQUIRE(a.splits <= 1 || a.c_fp32, "gemm: split-K needs fp32 output slabs");
+  if (a.residual)
+    B200RL_REQUIRE(a.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15u) == 0,
+                   "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
+  if (a.bias)
+    B200RL_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15u) == 0, "gemm: bias must be 16-byte aligned");
+  int bn = a.force_bn;
+  if (a.mn_major) {
+    B200RL_REQUIRE(a.M % 8 == 0, "gemm(dW form): M must be a multiple of 8");
+    if (bn == 0) bn = a.N <= 64 ? 64 : 128;
+    if (bn == 64) return launch<64, true>(a, stream);
+    if (bn == 128) return launch<128, true>(a, stream);
+    return set_error(B200RL_ERR_UNSUPPORTED, "gemm(dW form): BN=%d not instantiated", bn);
+  }
+  if (bn == 0) {
+    if (a.N <= 64) bn = 64;
+    else if (a.N <= 128) bn = 128;
+    else {
+      // pick the tile width with the best wave efficiency on this GPU
+      const int sms = num_sms();
+      const int mb = (a.M + BM - 1) / BM;
+      double best = -1;
+      const int cands[3] = {256, 192, 128};
+      for (int i = 0; i < 3; ++i) {
+        const int c = cands[i];
+        const long long tiles = (long long)mb * ((a.N + c - 1) / c);
+        const long long waves = (tiles + sms - 1) / sms;
+        // useful work / (waves * full-tile work); wider tiles get a small bonus for smem traffic
+        double eff = ((double)a.M * a.N) / ((double)waves * sms * BM * c);
+        eff *= (c == 256 ? 1.0 : (c == 192 ? 0.97 : 0.93));
+        if (eff > best) {
+          best = eff;
+          bn = c;
+        }
+      }
+    }
+  }
+  switch (bn) {
+    case 64: return launch<64, false>(a, stream);
+    case 128: return launch<128, false>(a, stream);
+    case 192: return launch<192, false>(a, stream);
+    case 256: return launch<256, false>(a, stream);
+    default: return set_error(B200RL_ERR_UNSUPPORTED, "gemm: BN=%d not instantiated", bn);
+  }
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+// C ABI — declared in include/b200rl.h
+extern "C" int b200rl_gemm(const void* A1, long long lda1, const void* B1, long long ldb1, int K1,
+                           const void* A2, long long lda2, const void* B2, long long ldb2, int K2,
+                           void* C, long long ldc, int c_fp32, const void* bias,
+                           const void* residual, long long ldr, float alpha, int M, int N,
+                           int mn_major, int splits, long long c_split_stride, int force_bn,
+                           int max_ctas, void* stream) {
+  GemmArgs a;
+  a.A1 = A1; a.B1 = B1; a.A2 = A2; a.B2 = B2;
+  a.lda1 = lda1; a.ldb1 = ldb1; a.lda2 = lda2; a.ldb2 = ldb2;
+  a.K1 = K1; a.K2 = K2;
+  a.C = C; a.ldc = ldc; a.c_fp32 = c_fp32;
+  a.bias = bias; a.residual = residual; a.ldr = ldr;
+  a.alpha = alpha; a.M = M; a.N = N;
+  a.mn_major = mn_major; a.splits = splits; a.c_split_stride = c_split_stride;
+  a.force_bn = force_bn; a.max_ctas = max_ctas;
+  return gemm_dispatch(a, reinterpret_cast<cudaStream_t>(stream));
+}

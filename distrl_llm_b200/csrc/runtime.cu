@@ -1,0 +1,48 @@
+// Library runtime: thread-local error string, device attribute cache, version.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace b200rl {
+
+static thread_local char g_last_error[1024] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace b200rl
+
+extern "C" const char* b200rl_last_error(void) { return b200rl::g_last_error; }
+
+extern "C" int b200rl_version(void) { return 100; }
+
+// Returns 0 when the current device is an sm_100 part (the only target of this library).
+extern "C" int b200rl_check_device(void) {
+  int dev = 0, major = 0, minor = 0;
+  B200RL_CUDA_OK(cudaGetDevice(&dev));
+  B200RL_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  B200RL_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10)
+    return b200rl::set_error(b200rl::B200RL_ERR_UNSUPPORTED,
+                             "libb200rl is built for sm_100a only; device %d is sm_%d%d", dev, major,
+                             minor);
+  return 0;
+}

@@ -1,0 +1,151 @@
+/*
+ * libb200rl — C ABI of the B200-native GRPO/PG learner hot path.
+ *
+ * Drop-in boundary for the learner math of BY571/DistRL-LLM (reference @ a1099fd).  The reference
+ * has no FFI of its own (pure Python over torch / Unsloth / bitsandbytes); each entry point below
+ * names the reference code it replaces (file:line relative to the reference root).  The Python
+ * mirror of the reference's Learner / GRPOLearner classes (distrl_llm_b200/learner.py) binds these
+ * through ctypes; INTEGRATION.md shows the stub a maintainer would add to distributed_actor.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on failure; b200rl_last_error() returns
+ *     a thread-local message.  The Python shim raises RuntimeError, so errors still surface through
+ *     ray.get() as RayTaskError like the reference's exceptions do.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the library never allocates
+ *     or frees caller-visible memory (exception: b200rl_p2p_alloc, whose buffers must be IPC-exportable).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden syncs.
+ *   - bf16 tensors are row-major, 16-byte aligned, leading dimensions multiples of 8.
+ */
+#ifndef B200RL_H
+#define B200RL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+const char* b200rl_last_error(void);
+int b200rl_version(void);
+int b200rl_check_device(void); /* 0 iff the current device is sm_100 */
+
+/* ---- G1/G6: tcgen05 GEMM (reference: every nn.Linear / LoRA matmul inside policy(...),
+ *      distributed_actor.py:241-243, and their backward, :385 / :483) --------------------------
+ * C[M,N] = alpha*(A1[M,K1].B1[N,K1]^T + A2[M,K2].B2[N,K2]^T) (+bias[N]) (+residual[M,N]).
+ * mn_major=0: operands K-major (row-major [rows][K]).  mn_major=1 ("dW form"): operands stored
+ * [K][M] and [K][N] (C = A^T.B, reduction over the leading index); splits>1 writes fp32 partial
+ * slabs c_split_stride elements apart.  force_bn / max_ctas = 0 for the defaults. */
+int b200rl_gemm(const void* A1, long long lda1, const void* B1, long long ldb1, int K1,
+                const void* A2, long long lda2, const void* B2, long long ldb2, int K2, void* C,
+                long long ldc, int c_fp32, const void* bias, const void* residual, long long ldr,
+                float alpha, int M, int N, int mn_major, int splits, long long c_split_stride,
+                int force_bn, int max_ctas, void* stream);
+
+/* ---- G2/G3/G5 row kernels (reference: Unsloth RMSNorm / RoPE / SwiGLU inside policy(...)) ---- */
+int b200rl_embed(const int* ids, const void* table, void* out, int M, int H, int vocab, void* stream);
+int b200rl_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps,
+                       void* stream);
+int b200rl_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd,
+                       const void* dres, void* dx, int M, int H, void* stream);
+int b200rl_rope_table(float* cs, int L, int head_dim, float theta, void* stream);
+int b200rl_rope(void* qkv, const float* cs, int M, int L, long long row_stride, int n_rot_heads,
+                int head_dim, int backward, void* stream);
+int b200rl_swiglu_fwd(const void* gu, void* act, int M, int I, void* stream);
+int b200rl_swiglu_bwd(const void* gu, const void* dact, void* dgu, int M, int I, void* stream);
+/* logits[:, P-1:L-1] row selection of distributed_actor.py:245-249 applied BEFORE lm_head */
+int b200rl_gather_rows(const void* x, void* out, int B, int L, int T, int start, int H, void* stream);
+int b200rl_scatter_rows(const void* d, void* dx, int B, int L, int T, int start, int H, void* stream);
+
+/* ---- G4: causal GQA attention with key-padding mask (reference: attention inside policy(...)
+ *      with attention_mask = cat(prompt_mask, answer_mask), distributed_actor.py:236-243) -------- */
+int b200rl_attn_fwd(const void* qkv, const int* key_mask, void* out, float* lse, int B, int L,
+                    int n_q_heads, int n_kv_heads, int head_dim, float scale, void* stream);
+int b200rl_attn_bwd(const void* qkv, const int* key_mask, const void* out, const void* dout,
+                    const float* lse, float* delta, void* dqkv, int B, int L, int n_q_heads,
+                    int n_kv_heads, int head_dim, float scale, void* stream);
+
+/* ---- G7: fused log-softmax + target gather + loss-gradient scale
+ *      (distributed_actor.py:252-260 scoring; :375 PG / :467-470 GRPO loss; :382/:479 scaling) --- */
+int b200rl_logprob(void* logits, long long ld, const int* targets, const float* coef, float* lp_out,
+                   int rows, int V, int write_grad, void* stream);
+int b200rl_loss_coef(const int* mask, const double* adv, float* coef, int* lens, int Bm, int T,
+                     int nb, void* stream);
+int b200rl_loss_value(const float* lp, const int* mask, const double* adv, double* accum, int Bm,
+                      int T, int grpo, void* stream);
+
+/* ---- G9: group-relative advantages + top-k (distributed_trainer.py:262-294) ---------------- */
+int b200rl_group_advantage_topk(const double* rewards, double* values, double* baselines,
+                                int* topk_idx, double* topk_val, int G, int C, int k, int grpo,
+                                void* stream);
+
+/* ---- NF4 base weights (reference: load_in_4bit=True, distributed_actor.py:16-17, :58-66) ---- */
+int b200rl_nf4_quantize(const void* w_bf16, void* packed, float* absmax, long long n, void* stream);
+int b200rl_nf4_dequant(const void* packed, const float* absmax, void* out_bf16, int rows, int cols,
+                       int transpose, void* stream);
+
+/* ---- G8: (P2P reduce +) Adam/AdamW over the flat LoRA buffer
+ *      (distributed_actor.py:283-294 export, :302-333 merge+step, :209-211 optimizer) ----------- */
+int b200rl_lora_reduce_adamw(float* p, float* m, float* v, const float* const* grads_host,
+                             float* const* params_peer_host, int world, int rank, long long n,
+                             int step, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int zero_local_grad, void* stream);
+int b200rl_p2p_barrier(unsigned int* const* flags_peer_host, int world, int rank, unsigned int epoch,
+                       void* stream);
+int b200rl_p2p_alloc(long long bytes, void** ptr, void* handle64);
+int b200rl_p2p_open(const void* handle64, void** ptr);
+int b200rl_p2p_close(void* ptr);
+int b200rl_p2p_free(void* ptr);
+int b200rl_lora_pack(const float* flat, void* arena_bf16, const void* descs_dev, int n_desc,
+                     int max_elems, void* stream);
+int b200rl_lora_grad_accum(float* flat, const void* descs_dev, int n_desc, int max_elems,
+                           void* stream);
+int b200rl_sizeof_pack_desc(void);
+int b200rl_sizeof_unpack_desc(void);
+
+/* ---- full learner (C++ host driver: 28-layer forward/backward over the kernels above) -------
+ *      reference: BaseLearner.compute_current_policy_probs (:215-261), Learner.compute_loss
+ *      (:349-395), GRPOLearner.compute_loss (:440-493), loss.backward() (:385, :483) ----------- */
+typedef struct b200rl_model_config {
+  int vocab, hidden, inter, n_layers, n_q_heads, n_kv_heads, head_dim;
+  int lora_r;
+  float lora_scale; /* alpha / r */
+  float rms_eps;
+  float rope_theta;
+  int max_tokens; /* largest B*L of a micro-batch the workspace is sized for */
+  int max_batch;  /* largest micro-batch (sequences) */
+  int max_seq;    /* largest L */
+} b200rl_model_config;
+
+/* per-layer device pointers (all frozen tensors owned by the caller) */
+typedef struct b200rl_layer_weights {
+  const void* qkv_packed;  const float* qkv_absmax;   /* NF4 [ (nq+2nkv)*hd, hidden ] */
+  const void* o_packed;    const float* o_absmax;     /* NF4 [ hidden, nq*hd ] */
+  const void* gu_packed;   const float* gu_absmax;    /* NF4 [ 2*inter, hidden ] (gate rows then up rows) */
+  const void* down_packed; const float* down_absmax;  /* NF4 [ hidden, inter ] */
+  const void* qkv_bias;                               /* bf16 [ (nq+2nkv)*hd ] */
+  const void* ln1_w; const void* ln2_w;               /* bf16 [ hidden ] */
+} b200rl_layer_weights;
+
+typedef struct b200rl_model b200rl_model;
+
+long long b200rl_model_workspace_bytes(const b200rl_model_config* cfg);
+long long b200rl_model_lora_numel(const b200rl_model_config* cfg);
+int b200rl_model_create(const b200rl_model_config* cfg, const b200rl_layer_weights* layers_host,
+                        const void* embed, const void* final_norm_w, const void* lm_head,
+                        const void* lm_head_t, float* lora_flat, float* lora_grad_flat,
+                        void* workspace, long long workspace_bytes, b200rl_model** out);
+int b200rl_model_destroy(b200rl_model* m);
+/* refresh the bf16 operand copies of the LoRA tensors after an optimizer step */
+int b200rl_model_sync_lora(b200rl_model* m, void* stream);
+/* one micro-batch: scores B sequences of length L = P+T, accumulates LoRA grads.
+ * ids [B,L] int32, attn_mask [B,L] int32 (1 = real token), answer_mask [B,T] int32, adv [B] f64,
+ * lp_out [B,T] f32 (per-token log-probs), loss_accum (device f64, += loss_m), nb = number of
+ * micro-batches of the step (1/nb scaling, distributed_actor.py:382/:479). backward=0 scores only. */
+int b200rl_model_microbatch(b200rl_model* m, const int* ids, const int* attn_mask,
+                            const int* answer_mask, const double* adv, float* lp_out,
+                            double* loss_accum, int B, int P, int T, int nb, int grpo, int backward,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H */

@@ -1,0 +1,300 @@
+"""Per-kernel parity tests (GPU): every libb200rl kernel against a plain torch fp32/fp64
+restatement of the same op on identical bf16-rounded inputs. Tolerances are stated per test."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, device, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(device=device, dtype=torch.bfloat16)
+
+
+def _rel_err(a, b):
+    a = a.double()
+    b = b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------
+# G1: tcgen05 GEMM
+# ------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    # (M, N, K1, K2, force_bn)
+    (128, 64, 64, 0, 0),
+    (128, 128, 128, 0, 0),
+    (256, 256, 512, 0, 0),
+    (300, 200, 192, 0, 0),        # ragged M, N (multiple of 8), K
+    (77, 72, 40, 0, 0),           # K tail (zero-filled by TMA), tiny
+    (1000, 512, 1024, 64, 0),     # LoRA side segment
+    (512, 384, 256, 64, 128),
+    (512, 384, 256, 128, 192),
+    (640, 4608, 3584, 64, 256),   # QKV-shaped
+    (4096, 1024, 2048, 0, 256),   # many tiles per CTA (pipeline wrap-around)
+    (4100, 3584, 1024, 64, 0),
+]
+
+
+@pytest.mark.parametrize("M,N,K1,K2,bn", GEMM_SHAPES)
+def test_gemm_tn(cuda, M, N, K1, K2, bn):
+    from distrl_llm_b200 import ops
+    a1 = _rand((M, K1), cuda, seed=1)
+    b1 = _rand((N, K1), cuda, seed=2)
+    a2 = _rand((M, K2), cuda, seed=3) if K2 else None
+    b2 = _rand((N, K2), cuda, seed=4) if K2 else None
+    out = ops.gemm(a1, b1, a2, b2, force_bn=bn)
+    torch.cuda.synchronize()
+    ref = a1.float() @ b1.float().T
+    if K2:
+        ref = ref + a2.float() @ b2.float().T
+    # bf16 output rounding: 2^-9 relative per element; accumulate in fp32 like the reference's autocast matmul
+    err = _rel_err(out, ref)
+    assert err < 4e-3, f"rel err {err}"
+    assert torch.isfinite(out.float()).all()
+
+
+def test_gemm_epilogues(cuda):
+    from distrl_llm_b200 import ops
+    M, N, K = 384, 320, 256
+    a = _rand((M, K), cuda, seed=1)
+    b = _rand((N, K), cuda, seed=2)
+    bias = _rand((N,), cuda, seed=3)
+    res = _rand((M, N), cuda, seed=4)
+    ref = 0.5 * (a.float() @ b.float().T) + bias.float()[None] + res.float()
+    out = ops.gemm(a, b, bias=bias, residual=res, alpha=0.5)
+    assert _rel_err(out, ref) < 4e-3
+    out32 = ops.gemm(a, b, bias=bias, residual=res, alpha=0.5, out_fp32=True)
+    assert out32.dtype == torch.float32
+    assert _rel_err(out32, ref) < 1e-5
+    # in-place residual (C aliases the residual) — used for x += o_proj(...)
+    res2 = res.clone()
+    ops.gemm(a, b, residual=res2, out=res2)
+    assert _rel_err(res2, a.float() @ b.float().T + res.float()) < 4e-3
+
+
+@pytest.mark.parametrize("tokens,Ny,Nu,splits", [
+    (64, 128, 64, 1), (512, 256, 64, 1), (1000, 384, 64, 4), (6896, 512, 64, 8), (2048, 1024, 128, 3),
+    (200, 136, 64, 2),
+])
+def test_gemm_dw(cuda, tokens, Ny, Nu, splits):
+    """dW form (both operands MN-major): slabs.sum(0) == y.T @ u."""
+    from distrl_llm_b200 import ops
+    y = _rand((tokens, Ny), cuda, seed=5)
+    u = _rand((tokens, Nu), cuda, seed=6)
+    slabs = ops.gemm_dw(y, u, splits=splits)
+    got = slabs.sum(0)
+    ref = y.float().T @ u.float()
+    err = _rel_err(got, ref)
+    assert err < 1e-4, f"rel err {err}"
+
+
+# ------------------------------------------------------------------------------------------------
+# row kernels
+# ------------------------------------------------------------------------------------------------
+def test_embed(cuda):
+    from distrl_llm_b200 import ops
+    table = _rand((512, 128), cuda, seed=1)
+    ids = torch.randint(0, 512, (300,), device=cuda, dtype=torch.int32)
+    out = ops.embed(ids, table)
+    assert torch.equal(out, table[ids.long()])
+
+
+@pytest.mark.parametrize("M,H", [(7, 128), (300, 3584), (64, 1024)])
+def test_rmsnorm(cuda, M, H):
+    from distrl_llm_b200 import ops
+    x = _rand((M, H), cuda, seed=1, scale=2.0)
+    w = (1 + 0.1 * torch.randn(H)).to(cuda, torch.bfloat16)
+    eps = 1e-6
+    y, rstd = ops.rmsnorm_fwd(x, w, eps)
+    xf = x.float().requires_grad_(True)
+    var = xf.pow(2).mean(-1, keepdim=True)
+    ref = w.float() * (xf * torch.rsqrt(var + eps))
+    assert _rel_err(y, ref) < 6e-3
+    assert _rel_err(rstd, torch.rsqrt(var + eps).squeeze(-1)) < 1e-5
+    dy = _rand((M, H), cuda, seed=2)
+    dres = _rand((M, H), cuda, seed=3)
+    ref.backward(dy.float())
+    dx = ops.rmsnorm_bwd(dy, x, w, rstd, dres)
+    assert _rel_err(dx, xf.grad + dres.float()) < 6e-3
+
+
+def _rope_ref(x, L, hd, theta):
+    # HF apply_rotary_pos_emb / rotate_half in fp32
+    M, nh, _ = x.shape
+    pos = (torch.arange(M, device=x.device) % L).float()
+    inv = 1.0 / (theta ** (torch.arange(0, hd, 2, device=x.device).float() / hd))
+    fr = pos[:, None] * inv[None]
+    emb = torch.cat([fr, fr], -1)
+    cos, sin = emb.cos()[:, None], emb.sin()[:, None]
+    x1, x2 = x[..., : hd // 2], x[..., hd // 2:]
+    rot = torch.cat([-x2, x1], -1)
+    return x * cos + rot * sin
+
+
+def test_rope(cuda):
+    from distrl_llm_b200 import ops
+    B, L, nq, nkv, hd, theta = 2, 48, 4, 2, 128, 1e6
+    qkv = _rand((B * L, (nq + 2 * nkv) * hd), cuda, seed=1)
+    orig = qkv.clone()
+    cs = ops.rope_table(L, hd, theta, cuda)
+    ops.rope_(qkv, cs, L, nq + nkv, hd)
+    ref = _rope_ref(orig[:, : (nq + nkv) * hd].float().view(B * L, nq + nkv, hd), L, hd, theta)
+    assert _rel_err(qkv[:, : (nq + nkv) * hd].float().view(B * L, nq + nkv, hd), ref) < 6e-3
+    assert torch.equal(qkv[:, (nq + nkv) * hd:], orig[:, (nq + nkv) * hd:])  # v untouched
+    # backward = transpose of the rotation: <R x, y> == <x, R^T y>
+    y = _rand((B * L, (nq + 2 * nkv) * hd), cuda, seed=2)
+    yt = y.clone()
+    ops.rope_(yt, cs, L, nq + nkv, hd, backward=True)
+    lhs = (qkv.float() * y.float())[:, : (nq + nkv) * hd].sum()
+    rhs = (orig.float() * yt.float())[:, : (nq + nkv) * hd].sum()
+    assert abs(lhs - rhs) / abs(lhs) < 2e-2
+
+
+def test_swiglu(cuda):
+    from distrl_llm_b200 import ops
+    M, I = 50, 256
+    gu = _rand((M, 2 * I), cuda, seed=1, scale=2.0)
+    act = ops.swiglu_fwd(gu)
+    g = gu[:, :I].float().requires_grad_(True)
+    u = gu[:, I:].float().requires_grad_(True)
+    ref = torch.nn.functional.silu(g) * u
+    assert _rel_err(act, ref) < 6e-3
+    dact = _rand((M, I), cuda, seed=2)
+    ref.backward(dact.float())
+    dgu = ops.swiglu_bwd(gu, dact)
+    assert _rel_err(dgu[:, :I], g.grad) < 6e-3
+    assert _rel_err(dgu[:, I:], u.grad) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# G7 fused log-softmax / gather / grad
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,V", [(9, 512), (64, 152064), (33, 8192)])
+def test_logprob(cuda, rows, V):
+    from distrl_llm_b200 import ops
+    logits = _rand((rows, V), cuda, seed=1, scale=3.0)
+    tg = torch.randint(0, V, (rows,), device=cuda, dtype=torch.int32)
+    coef = torch.randn(rows, device=cuda)
+    coef[0] = 0.0
+    z = logits.float().requires_grad_(True)
+    lp_ref = torch.log_softmax(z, -1).gather(1, tg.long()[:, None]).squeeze(1)
+    lp = ops.logprob(logits.clone(), tg)
+    # tolerance: fp32 log-softmax of identical bf16 logits, |dlp| <= 1e-5 * scale
+    assert (lp - lp_ref).abs().max().item() < 2e-5 * max(1.0, lp_ref.abs().max().item())
+    (lp_ref * coef).sum().backward()
+    work = logits.clone()
+    lp2 = ops.logprob(work, tg, coef, write_grad=True)
+    assert torch.equal(lp, lp2)
+    # dlogits stored in bf16
+    assert _rel_err(work, z.grad) < 6e-3
+    assert (work[0] == 0).all()
+
+
+def test_loss_coef_and_value(cuda):
+    from distrl_llm_b200 import ops
+    Bm, T, nb = 5, 40, 3
+    mask = torch.zeros(Bm, T, dtype=torch.int32)
+    lens = [40, 17, 1, 0, 23]
+    for i, n in enumerate(lens):
+        mask[i, :n] = 1
+    mask = mask.to(cuda)
+    adv = torch.tensor([0.5, -1.25, 2.0, 3.0, -0.1], dtype=torch.float64, device=cuda)
+    coef, ln = ops.loss_coef(mask, adv, nb)
+    assert ln.tolist() == lens
+    for i, n in enumerate(lens):
+        exp = 0.0 if n == 0 else -adv[i].item() / (n * Bm * nb)
+        assert torch.allclose(coef[i, :n], torch.full((n,), exp, device=cuda, dtype=torch.float32))
+        assert (coef[i, n:] == 0).all()
+    lp = -torch.rand(Bm, T, device=cuda)
+    acc = torch.zeros(1, dtype=torch.float64, device=cuda)
+    ops.loss_value(lp, mask, adv, acc, grpo=False)
+    ref = 0.0
+    for i, n in enumerate(lens):
+        if n:
+            ref += adv[i].item() * lp[i, :n].double().sum().item() / n
+    assert abs(acc.item() - (-ref / Bm)) < 1e-9
+    ops.loss_value(lp, mask, adv, acc, grpo=True)  # accumulates (reference returns the SUM, quirk Q2)
+    ref2 = -sum(adv[i].item() for i, n in enumerate(lens) if n) / Bm
+    assert abs(acc.item() - (-ref / Bm + ref2)) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------
+# G9 advantages / top-k : bit-exact against numpy (reference distributed_trainer.py:262-294)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("G,C,k", [(3, 8, 8), (5, 16, 4), (2, 256, 128), (4, 7, 16), (3, 130, 50)])
+def test_group_advantage_topk(cuda, G, C, k):
+    from distrl_llm_b200 import ops
+    rng = np.random.default_rng(C * 7 + k)
+    fmt = rng.choice([0.0, 0.1, 0.2, 0.35], size=(G, C))
+    acc = (rng.random((G, C)) < 0.3).astype(np.float64) + rng.random((G, C)) * 1e-3
+    rewards = np.stack([fmt, acc], -1)
+    vals, base, idx, val = ops.group_advantage_topk(torch.from_numpy(rewards).to(cuda), k, grpo=True)
+    for g in range(G):
+        s = rewards[g].sum(axis=1)
+        adv = (s - np.mean(s)) / (np.std(s) + 1e-8)
+        assert np.array_equal(vals[g].cpu().numpy(), adv), "advantages must be bit-identical to numpy"
+        assert base[g].item() == np.mean(s)
+        top = np.argsort(adv, kind="stable")[-k:]
+        assert np.array_equal(idx[g].cpu().numpy(), top)
+        assert np.array_equal(val[g].cpu().numpy(), adv[top])
+    vals_pg, base_pg, _, _ = ops.group_advantage_topk(torch.from_numpy(rewards).to(cuda), k, grpo=False)
+    assert np.array_equal(vals_pg.cpu().numpy(), rewards.sum(-1))
+
+
+# ------------------------------------------------------------------------------------------------
+# NF4
+# ------------------------------------------------------------------------------------------------
+NF4 = np.array([-1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453, -0.28444138169288635,
+                -0.18477343022823334, -0.09105003625154495, 0.0, 0.07958029955625534, 0.16093020141124725,
+                0.24611230194568634, 0.33791524171829224, 0.44070982933044434, 0.5626170039176941,
+                0.7229568362236023, 1.0], dtype=np.float32)
+
+
+def test_nf4_roundtrip(cuda):
+    from distrl_llm_b200 import ops
+    rows, cols = 136, 256
+    w = _rand((rows, cols), cuda, seed=1, scale=0.02)
+    packed, absmax = ops.nf4_quantize(w)
+    wf = w.float().cpu().numpy().reshape(-1, 64)
+    am = np.abs(wf).max(1)
+    assert np.array_equal(absmax.cpu().numpy(), am)
+    codes = np.abs((wf / am[:, None])[..., None] - NF4[None, None]).argmin(-1)
+    ref_packed = (codes[:, 0::2] << 4 | codes[:, 1::2]).astype(np.uint8).reshape(-1)
+    got = packed.cpu().numpy()
+    # ties at exact midpoints are measure-zero for random data
+    assert (got != ref_packed).mean() < 1e-4
+    deq = ops.nf4_dequant(packed, absmax, rows, cols)
+    lo, hi = got & 15, got >> 4
+    vals = np.stack([NF4[hi], NF4[lo]], -1).reshape(-1, 64) * am[:, None]
+    ref = torch.from_numpy(vals.reshape(rows, cols)).to(torch.bfloat16)
+    assert torch.equal(deq.cpu(), ref), "dequant must be bit-exact: bf16(code * absmax)"
+    deq_t = ops.nf4_dequant(packed, absmax, rows, cols, transpose=True)
+    assert torch.equal(deq_t.cpu(), ref.T.contiguous())
+
+
+# ------------------------------------------------------------------------------------------------
+# G8 Adam (single learner) vs torch.optim.Adam
+# ------------------------------------------------------------------------------------------------
+def test_adam_matches_torch(cuda):
+    from distrl_llm_b200 import ops
+    n = 4096 * 3 + 4
+    torch.manual_seed(0)
+    p0 = torch.randn(n, device=cuda) * 0.1
+    p = p0.clone()
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=2e-5, foreach=False, fused=False)
+    for step in range(1, 6):
+        g = torch.randn(n, device=cuda) * 10 ** (step - 3)
+        ref_p.grad = g.clone()
+        opt.step()
+        gbuf = g.clone()
+        ops.adamw_step(p, m, v, gbuf, step, 2e-5)
+        assert (gbuf == 0).all()
+        # fp32, same operation order as torch's single-tensor Adam: <= 2 ulp
+        assert torch.allclose(p, ref_p.data, rtol=3e-7, atol=1e-9), (p - ref_p.data).abs().max()
