@@ -2,8 +2,6 @@
 #include "common.cuh"
 using namespace b200rl;
 #define STUB(name, ...) extern "C" int name(__VA_ARGS__) { return set_error(B200RL_ERR_UNSUPPORTED, #name " not built yet"); }
-STUB(b200rl_attn_fwd, const void*, const int*, void*, float*, int, int, int, int, int, float, void*)
-STUB(b200rl_attn_bwd, const void*, const int*, const void*, const void*, const float*, float*, void*, int, int, int, int, int, float, void*)
 extern "C" long long b200rl_model_workspace_bytes(const void*) { return 0; }
 extern "C" long long b200rl_model_lora_numel(const void*) { return 0; }
 STUB(b200rl_model_create, const void*, const void*, const void*, const void*, const void*, const void*, float*, float*, void*, long long, void**)

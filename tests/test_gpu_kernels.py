@@ -298,3 +298,49 @@ def test_adam_matches_torch(cuda):
         assert (gbuf == 0).all()
         # fp32, same operation order as torch's single-tensor Adam: <= 2 ulp
         assert torch.allclose(p, ref_p.data, rtol=3e-7, atol=1e-9), (p - ref_p.data).abs().max()
+
+
+# ------------------------------------------------------------------------------------------------
+# G4 attention fwd/bwd vs a torch fp32 restatement (causal AND key-padding mask, GQA)
+# ------------------------------------------------------------------------------------------------
+def _attn_ref(qkv, key_mask, B, L, nq, nkv, hd):
+    x = qkv.float().view(B, L, nq + 2 * nkv, hd)
+    q = x[:, :, :nq].permute(0, 2, 1, 3)
+    k = x[:, :, nq:nq + nkv].permute(0, 2, 1, 3).repeat_interleave(nq // nkv, dim=1)
+    v = x[:, :, nq + nkv:].permute(0, 2, 1, 3).repeat_interleave(nq // nkv, dim=1)
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    causal = torch.tril(torch.ones(L, L, dtype=torch.bool, device=qkv.device))
+    ok = causal[None, None] & (key_mask.bool()[:, None, None, :])
+    s = s.masked_fill(~ok, float("-inf"))
+    p = torch.softmax(s, -1)
+    p = torch.nan_to_num(p, nan=0.0)  # rows without any visible key -> zeros (library convention)
+    o = p @ v
+    return o.permute(0, 2, 1, 3).reshape(B * L, nq * hd)
+
+
+@pytest.mark.parametrize("B,L,nq,nkv,hd", [(2, 48, 4, 2, 32), (2, 200, 4, 2, 64), (1, 333, 14, 2, 128),
+                                            (3, 64, 4, 4, 128), (2, 130, 7, 1, 128)])
+def test_attention(cuda, B, L, nq, nkv, hd):
+    from distrl_llm_b200 import ops
+    qkv = _rand((B * L, (nq + 2 * nkv) * hd), cuda, seed=1)
+    key_mask = torch.ones(B, L, dtype=torch.int32, device=cuda)
+    key_mask[0, :5] = 0             # left padding (prompt side)
+    key_mask[-1, L - 7:] = 0        # right padding (completion side)
+    out, lse = ops.attn_fwd(qkv, key_mask, B, L, nq, nkv, hd)
+    qr = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qr, key_mask, B, L, nq, nkv, hd)
+    valid_q = torch.ones(B, L, dtype=torch.bool, device=cuda)
+    valid_q[0, :5] = False          # queries that see no key: undefined in HF, zeros here
+    vq = valid_q.view(-1)
+    assert torch.isfinite(out.float()).all()
+    assert _rel_err(out[vq], ref[vq]) < 8e-3
+    assert (out[~vq] == 0).all()
+    dout = _rand((B * L, nq * hd), cuda, seed=2)
+    (ref * dout.float()).sum().backward()
+    dqkv = ops.attn_bwd(qkv, key_mask, out, dout, lse, B, L, nq, nkv, hd)
+    assert torch.isfinite(dqkv.float()).all()
+    g = qr.grad
+    nqh = nq * hd
+    for name, sl in (("dq", slice(0, nqh)), ("dk", slice(nqh, nqh + nkv * hd)), ("dv", slice(nqh + nkv * hd, None))):
+        err = _rel_err(dqkv[:, sl], g[:, sl])
+        assert err < 2e-2, f"{name} rel err {err}"
