@@ -22,7 +22,7 @@ class ModelConfig(C.Structure):
         ("vocab", c_int), ("hidden", c_int), ("inter", c_int), ("n_layers", c_int),
         ("n_q_heads", c_int), ("n_kv_heads", c_int), ("head_dim", c_int),
         ("lora_r", c_int), ("lora_scale", c_float), ("rms_eps", c_float), ("rope_theta", c_float),
-        ("max_tokens", c_int), ("max_batch", c_int), ("max_seq", c_int),
+        ("max_tokens", c_int), ("max_batch", c_int), ("max_seq", c_int), ("max_score_rows", c_int),
     ]
 
 
@@ -79,6 +79,7 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_ll, C.POINTER(c_void_p)]),
     "b200rl_model_destroy": (c_int, [c_void_p]),
     "b200rl_model_sync_lora": (c_int, [c_void_p, c_void_p]),
+    "b200rl_model_debug_ptr": (c_void_p, [c_void_p, C.c_char_p, c_int]),
     "b200rl_model_microbatch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }

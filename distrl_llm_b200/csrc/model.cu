@@ -1,0 +1,656 @@
+// C++ host driver of the learner hot path: Qwen2-style causal LM (NF4 base + LoRA on
+// q,k,v,o,gate,up,down) forward -> per-token log-probs -> PG/GRPO loss -> backward into the flat
+// fp32 LoRA gradient buffer.  One call = one micro-batch of the reference's hot loop.
+//
+// Reference being replaced (file:line in /root/reference):
+//   BaseLearner.compute_current_policy_probs   distributed_actor.py:215-261
+//     :233-239  full_inputs / full_attention_mask  -> ids [B,L], attn_mask [B,L] (L = P+T)
+//     :241-243  policy(...).logits                 -> layer loop below (lm_head only at the T scored rows)
+//     :245-249  shift / slice                      -> rows P-1..L-2 predict tokens P..L-1
+//     :252-260  log_softmax + gather               -> b200rl logprob kernel (G7)
+//   Learner.compute_loss :375 / GRPOLearner.compute_loss :467-470, :382/:479 (1/num_batches),
+//   loss.backward() :385/:483                      -> analytic backward below (store, no recompute)
+//   LoRA spec helper.py:25-45 (7 target modules, bias none, dropout 0)
+//
+// LoRA math per projection: y = x W^T + s (x A^T) B^T, s = alpha/r.  Fused groups (qkv, o, gate|up,
+// down) use block-structured operand copies so one GEMM mainloop covers base + LoRA:
+//   Acat [K2, Kin] (A_j stacked, zero padded to K2 = roundup(nproj*r, 64)),  Bcat [Nout, K2]
+//   (block diagonal), and their transposes for the backward GEMMs.
+#include "common.cuh"
+#include "b200rl.h"
+#include <vector>
+#include <string.h>
+#include <new>
+
+namespace b200rl {
+
+// from the other translation units
+struct GemmArgs {
+  const void *A1, *B1, *A2, *B2;
+  long long lda1, ldb1, lda2, ldb2;
+  int K1, K2;
+  void* C;
+  long long ldc;
+  int c_fp32;
+  const void* bias;
+  const void* residual;
+  long long ldr;
+  float alpha;
+  int M, N;
+  int mn_major;
+  int splits;
+  long long c_split_stride;
+  int force_bn;
+  int max_ctas;
+};
+int gemm_dispatch(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" {
+int b200rl_embed(const int*, const void*, void*, int, int, int, void*);
+int b200rl_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, void*);
+int b200rl_rmsnorm_bwd(const void*, const void*, const void*, const float*, const void*, void*, int, int, void*);
+int b200rl_rope_table(float*, int, int, float, void*);
+int b200rl_rope(void*, const float*, int, int, long long, int, int, int, void*);
+int b200rl_swiglu_fwd(const void*, void*, int, int, void*);
+int b200rl_swiglu_bwd(const void*, const void*, void*, int, int, void*);
+int b200rl_gather_rows(const void*, void*, int, int, int, int, int, void*);
+int b200rl_scatter_rows(const void*, void*, int, int, int, int, int, void*);
+int b200rl_attn_fwd(const void*, const int*, void*, float*, int, int, int, int, int, float, void*);
+int b200rl_attn_bwd(const void*, const int*, const void*, const void*, const float*, float*, void*, int, int, int, int, int, float, void*);
+int b200rl_logprob(void*, long long, const int*, const float*, float*, int, int, int, void*);
+int b200rl_loss_coef(const int*, const double*, float*, int*, int, int, int, void*);
+int b200rl_loss_value(const float*, const int*, const double*, double*, int, int, int, void*);
+int b200rl_nf4_dequant(const void*, const float*, void*, int, int, int, void*);
+int b200rl_lora_pack(const float*, void*, const void*, int, int, void*);
+}
+
+namespace {
+
+struct PackDescH {  // must match PackDesc in optim.cu
+  long long src_off;
+  int rows, cols;
+  long long dst_off;
+  int dst_ld;
+  int transpose;
+};
+
+struct AccumBlock {
+  long long dst_off;  // into the flat grad buffer
+  int rows, cols;     // destination tensor shape
+  int row_off, col_off;
+  int transpose;
+};
+struct AccumArgs {
+  AccumBlock blk[3];
+  int nblk;
+  const float* slabs;
+  long long slab_stride;
+  int splits;
+  int ld;
+};
+
+__global__ void grad_accum_kernel(float* __restrict__ flat, const AccumArgs a) {
+  const AccumBlock d = a.blk[blockIdx.y];
+  const long long n = (long long)d.rows * d.cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / d.cols), j = (int)(idx % d.cols);
+    const long long o = d.transpose ? (long long)(d.row_off + j) * a.ld + d.col_off + i
+                                    : (long long)(d.row_off + i) * a.ld + d.col_off + j;
+    float acc = 0.f;
+    for (int s = 0; s < a.splits; ++s) acc += a.slabs[(long long)s * a.slab_stride + o];  // fixed order
+    flat[d.dst_off + idx] += acc;
+  }
+}
+
+__global__ void targets_kernel(const int* __restrict__ ids, int* __restrict__ targets, int L, int P,
+                               int T, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = i / T, t = i % T;
+  targets[i] = ids[(long long)b * L + P + t];
+}
+
+inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+// one fused projection group
+struct Group {
+  int Kin, Nout, nproj, K2;
+  int out_dims[3];       // per projection output rows
+  // offsets (elements) into the bf16 LoRA operand arena of the layer
+  long long acat, acat_t, bcat, bcat_t;
+  // flat fp32 offsets of A_j / B_j
+  long long a_off[3], b_off[3];
+};
+
+}  // namespace
+
+struct b200rl_model {
+  b200rl_model_config cfg;
+  std::vector<b200rl_layer_weights> layers;
+  const bf16 *embed, *final_norm, *lm_head, *lm_head_t;
+  float *lora_flat, *lora_grad;
+  long long lora_numel;
+  int QKV, QD;  // qkv row width, q width
+  std::vector<Group> groups;  // 4 per layer: qkv, o, gu, down
+  long long arena_per_layer;
+  int K2max;
+  // workspace pointers
+  uint8_t* ws;
+  long long ws_bytes;
+  bf16* arena;          // bf16 LoRA operand copies, all layers
+  void* pack_descs;     // device PackDescH[n_pack]
+  int n_pack, pack_max_elems;
+  bf16* X;              // [(n_layers+1)][Mt][H]
+  struct LayerAct {
+    bf16 *h1, *qkv, *attn_o, *x_mid, *h2, *gu, *act, *u_qkv, *u_o, *u_gu, *u_d;
+    float *rstd1, *rstd2, *lse;
+  };
+  std::vector<LayerAct> act;
+  bf16 *wbuf, *xsel, *hsel, *logits, *dhsel, *dx, *dh, *dact, *dgu, *dattn, *dqkv, *du;
+  float *rstd_f, *lp, *coef, *delta, *slabs, *rope_cs;
+  int *targets, *lens;
+  long long slab_elems;
+  int rope_L;
+};
+
+static void build_groups(b200rl_model* m) {
+  const b200rl_model_config& c = m->cfg;
+  const int H = c.hidden, I = c.inter, r = c.lora_r;
+  const int QD = c.n_q_heads * c.head_dim, KD = c.n_kv_heads * c.head_dim;
+  m->QD = QD;
+  m->QKV = QD + 2 * KD;
+  long long flat = 0;
+  m->groups.clear();
+  m->K2max = 64;
+  long long arena_layer = 0;
+  for (int l = 0; l < c.n_layers; ++l) {
+    long long arena = 0;
+    auto add = [&](int Kin, int nproj, const int* outs) {
+      Group g;
+      g.Kin = Kin;
+      g.nproj = nproj;
+      g.Nout = 0;
+      for (int j = 0; j < nproj; ++j) {
+        g.out_dims[j] = outs[j];
+        g.Nout += outs[j];
+      }
+      g.K2 = (int)align_up((long long)nproj * r, 64);
+      if (g.K2 > m->K2max) m->K2max = g.K2;
+      // flat layout: per projection A [r, Kin] then B [out, r] (PEFT lora_A.weight / lora_B.weight)
+      for (int j = 0; j < nproj; ++j) {
+        g.a_off[j] = flat;
+        flat += (long long)r * Kin;
+        g.b_off[j] = flat;
+        flat += (long long)outs[j] * r;
+      }
+      g.acat = arena;   arena += (long long)g.K2 * Kin;
+      g.acat_t = arena; arena += (long long)Kin * g.K2;
+      g.bcat = arena;   arena += (long long)g.Nout * g.K2;
+      g.bcat_t = arena; arena += (long long)g.K2 * g.Nout;
+      arena = align_up(arena, 64);
+      m->groups.push_back(g);
+    };
+    const int o_qkv[3] = {QD, KD, KD};
+    const int o_o[1] = {H};
+    const int o_gu[2] = {I, I};
+    const int o_d[1] = {H};
+    add(H, 3, o_qkv);
+    add(QD, 1, o_o);
+    add(H, 2, o_gu);
+    add(I, 1, o_d);
+    arena_layer = arena;
+  }
+  m->arena_per_layer = arena_layer;
+  m->lora_numel = align_up(flat, 4);
+}
+
+static int dw_splits(int tokens, int Ny, int bn_cols) {
+  // enough (tile, split) work units to cover the SMs; the GEMM clamps to the k-block count
+  const int tiles = ((Ny + 127) / 128) * ((bn_cols + 63) / 64 > 1 ? (bn_cols + 127) / 128 : 1);
+  int s = (num_sms() + tiles - 1) / tiles;
+  const int kb = (tokens + 63) / 64;
+  if (s > kb) s = kb;
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  const int per = (kb + s - 1) / s;
+  return (kb + per - 1) / per;
+}
+
+struct WsPlan {
+  long long total;
+  long long off_arena, off_pack, off_X, off_wbuf, off_xsel, off_hsel, off_logits, off_dhsel, off_dx,
+      off_dh, off_dact, off_dgu, off_dattn, off_dqkv, off_du, off_rstd_f, off_lp, off_coef, off_delta,
+      off_slabs, off_rope, off_targets, off_lens, off_layers;
+  long long per_layer;
+  long long slab_elems;
+};
+
+static WsPlan plan_ws(const b200rl_model* m) {
+  const b200rl_model_config& c = m->cfg;
+  const long long Mt = c.max_tokens, H = c.hidden, I = c.inter, V = c.vocab;
+  const long long R = c.max_score_rows;
+  const long long QKV = m->QKV, QD = m->QD;
+  WsPlan p;
+  long long o = 0;
+  auto take = [&](long long bytes) {
+    long long at = o;
+    o = align_up(o + bytes, 1024);
+    return at;
+  };
+  p.off_arena = take(m->arena_per_layer * c.n_layers * 2);
+  p.off_pack = take((long long)sizeof(PackDescH) * 28 * c.n_layers);
+  p.off_X = take((long long)(c.n_layers + 1) * Mt * H * 2);
+  long long wmax = std::max(std::max(QKV * H, QD * H), std::max(2 * I * H, I * H));
+  p.off_wbuf = take(wmax * 2);
+  p.off_xsel = take(R * H * 2);
+  p.off_hsel = take(R * H * 2);
+  p.off_logits = take(R * V * 2);
+  p.off_dhsel = take(R * H * 2);
+  p.off_dx = take(Mt * H * 2);
+  p.off_dh = take(Mt * H * 2);
+  p.off_dact = take(Mt * I * 2);
+  p.off_dgu = take(Mt * 2 * I * 2);
+  p.off_dattn = take(Mt * QD * 2);
+  p.off_dqkv = take(Mt * QKV * 2);
+  p.off_du = take(Mt * m->K2max * 2);
+  p.off_rstd_f = take(R * 4);
+  p.off_lp = take(R * 4);
+  p.off_coef = take(R * 4);
+  p.off_delta = take((long long)c.max_batch * c.n_q_heads * c.max_seq * 4);
+  long long nmax = std::max(std::max(QKV, 2 * I), std::max(H, I));
+  p.slab_elems = 16 * std::max(nmax, (long long)128) * m->K2max;  // generous: <=16 splits
+  // tighter: splits * Ny is bounded by ~ (num_sms/tiles+1) * Ny <= 2*128*num_sms for Ny < 128*sms
+  long long bound = (long long)(2 * 128 * 160 + nmax) * m->K2max;
+  if (p.slab_elems > bound) p.slab_elems = bound;
+  p.off_slabs = take(p.slab_elems * 4);
+  p.off_rope = take((long long)c.max_seq * c.head_dim * 4);
+  p.off_targets = take(R * 4);
+  p.off_lens = take((long long)c.max_batch * 4);
+  p.off_layers = o;
+  long long lo = 0;
+  auto ltake = [&](long long bytes) { lo = align_up(lo + bytes, 1024); };
+  ltake(Mt * H * 2);        // h1
+  ltake(Mt * QKV * 2);      // qkv
+  ltake(Mt * QD * 2);       // attn_o
+  ltake(Mt * H * 2);        // x_mid
+  ltake(Mt * H * 2);        // h2
+  ltake(Mt * 2 * I * 2);    // gu
+  ltake(Mt * I * 2);        // act
+  for (int j = 0; j < 4; ++j) ltake(Mt * m->K2max * 2);  // u_*
+  ltake(Mt * 4);            // rstd1
+  ltake(Mt * 4);            // rstd2
+  ltake((long long)c.max_batch * c.n_q_heads * c.max_seq * 4);  // lse
+  p.per_layer = lo;
+  p.total = p.off_layers + lo * c.n_layers;
+  return p;
+}
+
+static int validate_cfg(const b200rl_model_config* c) {
+  B200RL_REQUIRE(c != nullptr, "model: null config");
+  B200RL_REQUIRE(c->vocab > 0 && c->vocab % 8 == 0, "model: vocab must be a multiple of 8");
+  B200RL_REQUIRE(c->hidden % 64 == 0 && c->inter % 64 == 0, "model: hidden and inter must be multiples of 64 (NF4 blocks)");
+  B200RL_REQUIRE(c->head_dim == 32 || c->head_dim == 64 || c->head_dim == 128, "model: head_dim must be 32/64/128");
+  B200RL_REQUIRE(c->n_kv_heads > 0 && c->n_q_heads % c->n_kv_heads == 0, "model: bad head counts");
+  B200RL_REQUIRE((c->n_q_heads * c->head_dim) % 64 == 0 && (c->n_kv_heads * c->head_dim) % 64 == 0,
+                 "model: head widths must be multiples of 64");
+  B200RL_REQUIRE(c->lora_r > 0 && c->lora_r % 8 == 0, "model: lora_r must be a positive multiple of 8");
+  B200RL_REQUIRE(c->n_layers > 0 && c->max_tokens > 0 && c->max_batch > 0 && c->max_seq > 0 &&
+                     c->max_score_rows > 0, "model: bad sizes");
+  return 0;
+}
+
+extern "C" long long b200rl_model_lora_numel(const b200rl_model_config* cfg) {
+  if (validate_cfg(cfg)) return -1;
+  b200rl_model m;
+  m.cfg = *cfg;
+  build_groups(&m);
+  return m.lora_numel;
+}
+
+extern "C" long long b200rl_model_workspace_bytes(const b200rl_model_config* cfg) {
+  if (validate_cfg(cfg)) return -1;
+  b200rl_model m;
+  m.cfg = *cfg;
+  build_groups(&m);
+  return plan_ws(&m).total;
+}
+
+extern "C" int b200rl_model_create(const b200rl_model_config* cfg, const b200rl_layer_weights* layers_host,
+                                   const void* embed, const void* final_norm_w, const void* lm_head,
+                                   const void* lm_head_t, float* lora_flat, float* lora_grad_flat,
+                                   void* workspace, long long workspace_bytes, b200rl_model** out) {
+  int rc = validate_cfg(cfg);
+  if (rc) return rc;
+  B200RL_REQUIRE(layers_host && embed && final_norm_w && lm_head && lm_head_t && lora_flat &&
+                     lora_grad_flat && workspace && out, "model_create: null pointer");
+  b200rl_model* m = new (std::nothrow) b200rl_model();
+  B200RL_REQUIRE(m != nullptr, "model_create: out of host memory");
+  m->cfg = *cfg;
+  m->layers.assign(layers_host, layers_host + cfg->n_layers);
+  m->embed = (const bf16*)embed;
+  m->final_norm = (const bf16*)final_norm_w;
+  m->lm_head = (const bf16*)lm_head;
+  m->lm_head_t = (const bf16*)lm_head_t;
+  m->lora_flat = lora_flat;
+  m->lora_grad = lora_grad_flat;
+  build_groups(m);
+  WsPlan p = plan_ws(m);
+  if (workspace_bytes < p.total) {
+    delete m;
+    return set_error(B200RL_ERR_ARG, "model_create: workspace too small (%lld < %lld)", workspace_bytes, p.total);
+  }
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023u) != 0) {
+    delete m;
+    return set_error(B200RL_ERR_ARG, "model_create: workspace must be 1024-byte aligned");
+  }
+  uint8_t* w = (uint8_t*)workspace;
+  m->ws = w;
+  m->ws_bytes = p.total;
+  m->arena = (bf16*)(w + p.off_arena);
+  m->pack_descs = w + p.off_pack;
+  m->X = (bf16*)(w + p.off_X);
+  m->wbuf = (bf16*)(w + p.off_wbuf);
+  m->xsel = (bf16*)(w + p.off_xsel);
+  m->hsel = (bf16*)(w + p.off_hsel);
+  m->logits = (bf16*)(w + p.off_logits);
+  m->dhsel = (bf16*)(w + p.off_dhsel);
+  m->dx = (bf16*)(w + p.off_dx);
+  m->dh = (bf16*)(w + p.off_dh);
+  m->dact = (bf16*)(w + p.off_dact);
+  m->dgu = (bf16*)(w + p.off_dgu);
+  m->dattn = (bf16*)(w + p.off_dattn);
+  m->dqkv = (bf16*)(w + p.off_dqkv);
+  m->du = (bf16*)(w + p.off_du);
+  m->rstd_f = (float*)(w + p.off_rstd_f);
+  m->lp = (float*)(w + p.off_lp);
+  m->coef = (float*)(w + p.off_coef);
+  m->delta = (float*)(w + p.off_delta);
+  m->slabs = (float*)(w + p.off_slabs);
+  m->slab_elems = p.slab_elems;
+  m->rope_cs = (float*)(w + p.off_rope);
+  m->targets = (int*)(w + p.off_targets);
+  m->lens = (int*)(w + p.off_lens);
+  m->rope_L = 0;
+  const b200rl_model_config& c = m->cfg;
+  const long long Mt = c.max_tokens, H = c.hidden, I = c.inter;
+  m->act.resize(c.n_layers);
+  for (int l = 0; l < c.n_layers; ++l) {
+    uint8_t* b = w + p.off_layers + p.per_layer * l;
+    long long lo = 0;
+    auto ltake = [&](long long bytes) {
+      uint8_t* at = b + lo;
+      lo = align_up(lo + bytes, 1024);
+      return at;
+    };
+    b200rl_model::LayerAct& a = m->act[l];
+    a.h1 = (bf16*)ltake(Mt * H * 2);
+    a.qkv = (bf16*)ltake(Mt * m->QKV * 2);
+    a.attn_o = (bf16*)ltake(Mt * m->QD * 2);
+    a.x_mid = (bf16*)ltake(Mt * H * 2);
+    a.h2 = (bf16*)ltake(Mt * H * 2);
+    a.gu = (bf16*)ltake(Mt * 2 * I * 2);
+    a.act = (bf16*)ltake(Mt * I * 2);
+    a.u_qkv = (bf16*)ltake(Mt * m->K2max * 2);
+    a.u_o = (bf16*)ltake(Mt * m->K2max * 2);
+    a.u_gu = (bf16*)ltake(Mt * m->K2max * 2);
+    a.u_d = (bf16*)ltake(Mt * m->K2max * 2);
+    a.rstd1 = (float*)ltake(Mt * 4);
+    a.rstd2 = (float*)ltake(Mt * 4);
+    a.lse = (float*)ltake((long long)c.max_batch * c.n_q_heads * c.max_seq * 4);
+  }
+  // pack descriptors (fp32 master -> 4 bf16 operand layouts per projection)
+  std::vector<PackDescH> descs;
+  int max_elems = 0;
+  const int r = c.lora_r;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const long long base = m->arena_per_layer * l;
+    for (int gi = 0; gi < 4; ++gi) {
+      const Group& g = m->groups[l * 4 + gi];
+      int row_off = 0;
+      for (int j = 0; j < g.nproj; ++j) {
+        // A_j [r, Kin] -> Acat rows j*r.. (ld Kin) ; AcatT cols j*r.. (ld K2, transposed)
+        descs.push_back({g.a_off[j], r, g.Kin, base + g.acat + (long long)j * r * g.Kin, g.Kin, 0});
+        descs.push_back({g.a_off[j], r, g.Kin, base + g.acat_t + (long long)j * r, g.K2, 1});
+        // B_j [out_j, r] -> Bcat rows row_off.., cols j*r.. (ld K2) ; BcatT rows j*r.., cols row_off.. (ld Nout)
+        descs.push_back({g.b_off[j], g.out_dims[j], r, base + g.bcat + (long long)row_off * g.K2 + j * r, g.K2, 0});
+        descs.push_back({g.b_off[j], g.out_dims[j], r, base + g.bcat_t + (long long)j * r * g.Nout + row_off, g.Nout, 1});
+        max_elems = std::max(max_elems, std::max(r * g.Kin, g.out_dims[j] * r));
+        row_off += g.out_dims[j];
+      }
+    }
+  }
+  m->n_pack = (int)descs.size();
+  m->pack_max_elems = max_elems;
+  cudaError_t e = cudaMemcpy(m->pack_descs, descs.data(), descs.size() * sizeof(PackDescH), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(m->arena, 0, (size_t)(m->arena_per_layer * c.n_layers * 2));
+  if (e != cudaSuccess) {
+    delete m;
+    return set_error(B200RL_ERR_CUDA, "model_create: %s", cudaGetErrorString(e));
+  }
+  *out = m;
+  return 0;
+}
+
+extern "C" int b200rl_model_destroy(b200rl_model* m) {
+  delete m;
+  return 0;
+}
+
+extern "C" int b200rl_model_sync_lora(b200rl_model* m, void* stream) {
+  B200RL_REQUIRE(m != nullptr, "model_sync_lora: null model");
+  return b200rl_lora_pack(m->lora_flat, m->arena, m->pack_descs, m->n_pack, m->pack_max_elems, stream);
+}
+
+// named buffer lookup for parity bisection (tests only)
+extern "C" void* b200rl_model_debug_ptr(b200rl_model* m, const char* name, int layer) {
+  if (!m || !name) return nullptr;
+  const long long Mt = m->cfg.max_tokens, H = m->cfg.hidden;
+  if (!strcmp(name, "x")) return m->X + (long long)layer * Mt * H;
+  if (!strcmp(name, "logits")) return m->logits;
+  if (!strcmp(name, "hsel")) return m->hsel;
+  if (!strcmp(name, "dx")) return m->dx;
+  if (!strcmp(name, "dqkv")) return m->dqkv;
+  if (!strcmp(name, "wbuf")) return m->wbuf;
+  if (layer < 0 || layer >= m->cfg.n_layers) return nullptr;
+  b200rl_model::LayerAct& a = m->act[layer];
+  if (!strcmp(name, "h1")) return a.h1;
+  if (!strcmp(name, "qkv")) return a.qkv;
+  if (!strcmp(name, "attn_o")) return a.attn_o;
+  if (!strcmp(name, "x_mid")) return a.x_mid;
+  if (!strcmp(name, "h2")) return a.h2;
+  if (!strcmp(name, "gu")) return a.gu;
+  if (!strcmp(name, "act")) return a.act;
+  if (!strcmp(name, "u_qkv")) return a.u_qkv;
+  return nullptr;
+}
+
+#define RC(expr)              \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc) return _rc;      \
+  } while (0)
+
+namespace {
+
+int gemm_tn(cudaStream_t st, const bf16* A1, long long lda1, const bf16* B1, long long ldb1, int K1,
+            const bf16* A2, long long lda2, const bf16* B2, long long ldb2, int K2, bf16* C,
+            long long ldc, const bf16* bias, const bf16* residual, long long ldr, float alpha, int M,
+            int N) {
+  GemmArgs a;
+  a.A1 = A1; a.B1 = B1; a.A2 = A2; a.B2 = B2;
+  a.lda1 = lda1; a.ldb1 = ldb1; a.lda2 = lda2; a.ldb2 = ldb2;
+  a.K1 = K1; a.K2 = K2; a.C = C; a.ldc = ldc; a.c_fp32 = 0;
+  a.bias = bias; a.residual = residual; a.ldr = ldr; a.alpha = alpha;
+  a.M = M; a.N = N; a.mn_major = 0; a.splits = 1; a.c_split_stride = 0;
+  a.force_bn = 0; a.max_ctas = 0;
+  return gemm_dispatch(a, st);
+}
+
+// LoRA weight gradients of one group from (dY, u') and (x, du):
+//   dBcat = dY^T . u'  -> B_j blocks ; dAcat^T = x^T . du -> A_j blocks (transposed unpack)
+int lora_dw(b200rl_model* m, cudaStream_t st, const Group& g, const bf16* dY, long long ld_dy,
+            const bf16* u, const bf16* x, long long ld_x, const bf16* du, int M) {
+  for (int pass = 0; pass < 2; ++pass) {
+    const bf16* Y = pass == 0 ? dY : x;
+    const long long ldy = pass == 0 ? ld_dy : ld_x;
+    const int Ny = pass == 0 ? g.Nout : g.Kin;
+    const bf16* U = pass == 0 ? u : du;
+    const int splits = dw_splits(M, Ny, g.K2);
+    const long long stride = (long long)Ny * g.K2;
+    if ((long long)splits * stride > m->slab_elems)
+      return set_error(B200RL_ERR_STATE, "lora_dw: slab scratch too small (%lld > %lld)", (long long)splits * stride, m->slab_elems);
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A1 = Y; a.lda1 = ldy; a.B1 = U; a.ldb1 = g.K2; a.K1 = M; a.K2 = 0;
+    a.C = m->slabs; a.ldc = g.K2; a.c_fp32 = 1; a.alpha = 1.f;
+    a.M = Ny; a.N = g.K2; a.mn_major = 1; a.splits = splits; a.c_split_stride = stride;
+    RC(gemm_dispatch(a, st));
+    AccumArgs acc;
+    memset(&acc, 0, sizeof(acc));
+    acc.nblk = g.nproj;
+    acc.slabs = m->slabs;
+    acc.slab_stride = stride;
+    acc.splits = splits;
+    acc.ld = g.K2;
+    int row_off = 0, max_elems = 0;
+    const int r = m->cfg.lora_r;
+    for (int j = 0; j < g.nproj; ++j) {
+      AccumBlock& b = acc.blk[j];
+      if (pass == 0) {  // dB_j [out_j, r] = slab[row_off + i][j*r + jj]
+        b.dst_off = g.b_off[j]; b.rows = g.out_dims[j]; b.cols = r;
+        b.row_off = row_off; b.col_off = j * r; b.transpose = 0;
+      } else {          // dA_j [r, Kin]: dA_j[i][k] = slab[k][j*r + i]
+        b.dst_off = g.a_off[j]; b.rows = r; b.cols = g.Kin;
+        b.row_off = 0; b.col_off = j * r; b.transpose = 1;
+      }
+      max_elems = std::max(max_elems, b.rows * b.cols);
+      row_off += g.out_dims[j];
+    }
+    int bx = (max_elems + 255) / 256;
+    if (bx > 128) bx = 128;
+    dim3 grid(bx, g.nproj);
+    grad_accum_kernel<<<grid, 256, 0, st>>>(m->lora_grad, acc);
+    B200RL_LAUNCH_OK();
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const int* attn_mask,
+                                       const int* answer_mask, const double* adv, float* lp_out,
+                                       double* loss_accum, int B, int P, int T, int nb, int grpo,
+                                       int backward, void* stream) {
+  B200RL_REQUIRE(m && ids && attn_mask && answer_mask, "model_microbatch: null pointer");
+  const b200rl_model_config& c = m->cfg;
+  const int L = P + T, M = B * L, R = B * T;
+  B200RL_REQUIRE(B > 0 && P >= 1 && T >= 1, "model_microbatch: need B>0, P>=1, T>=1 (B=%d P=%d T=%d)", B, P, T);
+  B200RL_REQUIRE(M <= c.max_tokens && B <= c.max_batch && L <= c.max_seq && R <= c.max_score_rows,
+                 "model_microbatch: batch exceeds the workspace (B=%d L=%d)", B, L);
+  B200RL_REQUIRE(!backward || (adv && nb >= 1), "model_microbatch: backward needs adv and nb");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int H = c.hidden, I = c.inter, QKV = m->QKV, QD = m->QD, V = c.vocab;
+  const long long Mt = c.max_tokens;
+  const float s = c.lora_scale;
+  const float attn_scale = 1.0f / sqrtf((float)c.head_dim);
+
+  if (m->rope_L != L) {
+    RC(b200rl_rope_table(m->rope_cs, L, c.head_dim, c.rope_theta, stream));
+    m->rope_L = L;
+  }
+  // ---------------- forward ----------------
+  RC(b200rl_embed(ids, m->embed, m->X, M, H, V, stream));
+  for (int l = 0; l < c.n_layers; ++l) {
+    const b200rl_layer_weights& w = m->layers[l];
+    b200rl_model::LayerAct& a = m->act[l];
+    const bf16* ar = m->arena + m->arena_per_layer * l;
+    const Group& gq = m->groups[l * 4 + 0];
+    const Group& go = m->groups[l * 4 + 1];
+    const Group& gg = m->groups[l * 4 + 2];
+    const Group& gd = m->groups[l * 4 + 3];
+    bf16* x = m->X + (long long)l * Mt * H;
+    bf16* xn = m->X + (long long)(l + 1) * Mt * H;
+    RC(b200rl_rmsnorm_fwd(x, w.ln1_w, a.h1, a.rstd1, M, H, c.rms_eps, stream));
+    RC(gemm_tn(st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    RC(b200rl_nf4_dequant(w.qkv_packed, w.qkv_absmax, m->wbuf, QKV, H, 0, stream));
+    RC(gemm_tn(st, a.h1, H, m->wbuf, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, gq.K2, a.qkv, QKV,
+               (const bf16*)w.qkv_bias, nullptr, 0, 1.f, M, QKV));
+    RC(b200rl_rope(a.qkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 0, stream));
+    RC(b200rl_attn_fwd(a.qkv, attn_mask, a.attn_o, a.lse, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
+    RC(gemm_tn(st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 0, stream));
+    RC(gemm_tn(st, a.attn_o, QD, m->wbuf, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, go.K2, a.x_mid, H,
+               nullptr, x, H, 1.f, M, H));
+    RC(b200rl_rmsnorm_fwd(a.x_mid, w.ln2_w, a.h2, a.rstd2, M, H, c.rms_eps, stream));
+    RC(gemm_tn(st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    RC(b200rl_nf4_dequant(w.gu_packed, w.gu_absmax, m->wbuf, 2 * I, H, 0, stream));
+    RC(gemm_tn(st, a.h2, H, m->wbuf, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, gg.K2, a.gu, 2 * I,
+               nullptr, nullptr, 0, 1.f, M, 2 * I));
+    RC(b200rl_swiglu_fwd(a.gu, a.act, M, I, stream));
+    RC(gemm_tn(st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    RC(b200rl_nf4_dequant(w.down_packed, w.down_absmax, m->wbuf, H, I, 0, stream));
+    RC(gemm_tn(st, a.act, I, m->wbuf, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, gd.K2, xn, H, nullptr,
+               a.x_mid, H, 1.f, M, H));
+  }
+  // head: only the T scored positions (rows P-1 .. L-2) go through the final norm and lm_head
+  bf16* xf = m->X + (long long)c.n_layers * Mt * H;
+  RC(b200rl_gather_rows(xf, m->xsel, B, L, T, P - 1, H, stream));
+  RC(b200rl_rmsnorm_fwd(m->xsel, m->final_norm, m->hsel, m->rstd_f, R, H, c.rms_eps, stream));
+  RC(gemm_tn(st, m->hsel, H, m->lm_head, H, H, nullptr, 0, nullptr, 0, 0, m->logits, V, nullptr, nullptr, 0, 1.f, R, V));
+  targets_kernel<<<(R + 255) / 256, 256, 0, st>>>(ids, m->targets, L, P, T, R);
+  B200RL_LAUNCH_OK();
+  if (backward) RC(b200rl_loss_coef(answer_mask, adv, m->coef, m->lens, B, T, nb, stream));
+  float* lp = lp_out ? lp_out : m->lp;
+  RC(b200rl_logprob(m->logits, V, m->targets, backward ? m->coef : nullptr, lp, R, V, backward ? 1 : 0, stream));
+  if (loss_accum && adv) RC(b200rl_loss_value(lp, answer_mask, adv, loss_accum, B, T, grpo, stream));
+  if (!backward) return 0;
+
+  // ---------------- backward ----------------
+  RC(gemm_tn(st, m->logits, V, m->lm_head_t, V, V, nullptr, 0, nullptr, 0, 0, m->dhsel, H, nullptr, nullptr, 0, 1.f, R, H));
+  RC(b200rl_rmsnorm_bwd(m->dhsel, m->xsel, m->final_norm, m->rstd_f, nullptr, m->dhsel, R, H, stream));
+  RC(b200rl_scatter_rows(m->dhsel, m->dx, B, L, T, P - 1, H, stream));
+  for (int l = c.n_layers - 1; l >= 0; --l) {
+    const b200rl_layer_weights& w = m->layers[l];
+    b200rl_model::LayerAct& a = m->act[l];
+    const bf16* ar = m->arena + m->arena_per_layer * l;
+    const Group& gq = m->groups[l * 4 + 0];
+    const Group& go = m->groups[l * 4 + 1];
+    const Group& gg = m->groups[l * 4 + 2];
+    const Group& gd = m->groups[l * 4 + 3];
+    bf16* x = m->X + (long long)l * Mt * H;
+    // ---- down projection
+    RC(gemm_tn(st, m->dx, H, ar + gd.bcat_t, H, H, nullptr, 0, nullptr, 0, 0, m->du, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    RC(lora_dw(m, st, gd, m->dx, H, a.u_d, a.act, I, m->du, M));
+    RC(b200rl_nf4_dequant(w.down_packed, w.down_absmax, m->wbuf, H, I, 1, stream));  // Wd^T [I, H]
+    RC(gemm_tn(st, m->dx, H, m->wbuf, H, H, m->du, gd.K2, ar + gd.acat_t, gd.K2, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
+    RC(b200rl_swiglu_bwd(a.gu, m->dact, m->dgu, M, I, stream));
+    // ---- gate|up
+    RC(gemm_tn(st, m->dgu, 2 * I, ar + gg.bcat_t, 2 * I, 2 * I, nullptr, 0, nullptr, 0, 0, m->du, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    RC(lora_dw(m, st, gg, m->dgu, 2 * I, a.u_gu, a.h2, H, m->du, M));
+    RC(b200rl_nf4_dequant(w.gu_packed, w.gu_absmax, m->wbuf, 2 * I, H, 1, stream));  // Wgu^T [H, 2I]
+    RC(gemm_tn(st, m->dgu, 2 * I, m->wbuf, 2 * I, 2 * I, m->du, gg.K2, ar + gg.acat_t, gg.K2, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+    RC(b200rl_rmsnorm_bwd(m->dh, a.x_mid, w.ln2_w, a.rstd2, m->dx, m->dx, M, H, stream));
+    // ---- o projection
+    RC(gemm_tn(st, m->dx, H, ar + go.bcat_t, H, H, nullptr, 0, nullptr, 0, 0, m->du, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    RC(lora_dw(m, st, go, m->dx, H, a.u_o, a.attn_o, QD, m->du, M));
+    RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 1, stream));  // Wo^T [QD, H]
+    RC(gemm_tn(st, m->dx, H, m->wbuf, H, H, m->du, go.K2, ar + go.acat_t, go.K2, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
+    // ---- attention + rope
+    RC(b200rl_attn_bwd(a.qkv, attn_mask, a.attn_o, m->dattn, a.lse, m->delta, m->dqkv, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
+    RC(b200rl_rope(m->dqkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 1, stream));
+    // ---- qkv projection
+    RC(gemm_tn(st, m->dqkv, QKV, ar + gq.bcat_t, QKV, QKV, nullptr, 0, nullptr, 0, 0, m->du, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    RC(lora_dw(m, st, gq, m->dqkv, QKV, a.u_qkv, a.h1, H, m->du, M));
+    if (l > 0) {  // embeddings are frozen: layer 0 needs no input gradient
+      RC(b200rl_nf4_dequant(w.qkv_packed, w.qkv_absmax, m->wbuf, QKV, H, 1, stream));  // Wqkv^T [H, QKV]
+      RC(gemm_tn(st, m->dqkv, QKV, m->wbuf, QKV, QKV, m->du, gq.K2, ar + gq.acat_t, gq.K2, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+      RC(b200rl_rmsnorm_bwd(m->dh, x, w.ln1_w, a.rstd1, m->dx, m->dx, M, H, stream));
+    }
+  }
+  return 0;
+}

@@ -113,6 +113,7 @@ typedef struct b200rl_model_config {
   int max_tokens; /* largest B*L of a micro-batch the workspace is sized for */
   int max_batch;  /* largest micro-batch (sequences) */
   int max_seq;    /* largest L */
+  int max_score_rows; /* largest B*T (rows that reach lm_head) */
 } b200rl_model_config;
 
 /* per-layer device pointers (all frozen tensors owned by the caller) */
@@ -140,6 +141,8 @@ int b200rl_model_sync_lora(b200rl_model* m, void* stream);
  * ids [B,L] int32, attn_mask [B,L] int32 (1 = real token), answer_mask [B,T] int32, adv [B] f64,
  * lp_out [B,T] f32 (per-token log-probs), loss_accum (device f64, += loss_m), nb = number of
  * micro-batches of the step (1/nb scaling, distributed_actor.py:382/:479). backward=0 scores only. */
+/* device pointer of a named activation buffer (parity bisection in tests; NULL if unknown) */
+void* b200rl_model_debug_ptr(b200rl_model* m, const char* name, int layer);
 int b200rl_model_microbatch(b200rl_model* m, const int* ids, const int* attn_mask,
                             const int* answer_mask, const double* adv, float* lp_out,
                             double* loss_accum, int B, int P, int T, int nb, int grpo, int backward,
