@@ -80,6 +80,9 @@ SIGNATURES = {
     "b200rl_model_destroy": (c_int, [c_void_p]),
     "b200rl_model_sync_lora": (c_int, [c_void_p, c_void_p]),
     "b200rl_model_debug_ptr": (c_void_p, [c_void_p, C.c_char_p, c_int]),
+    "b200rl_model_profile": (c_int, [c_void_p, c_int]),
+    "b200rl_model_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200rl_launch_count": (c_ll, []),
     "b200rl_model_microbatch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }

@@ -37,6 +37,7 @@ int set_error(int code, const char* fmt, ...);
 
 #define B200RL_LAUNCH_OK()                                                                \
   do {                                                                                    \
+    ++::b200rl::g_launch_count;                                                           \
     cudaError_t _e = cudaGetLastError();                                                  \
     if (_e != cudaSuccess)                                                                \
       return ::b200rl::set_error(::b200rl::B200RL_ERR_CUDA, "kernel launch failed: %s (%s:%d)", \
@@ -44,6 +45,7 @@ int set_error(int code, const char* fmt, ...);
   } while (0)
 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+extern long long g_launch_count;  // kernels launched by this library (bench.py's gpu_launches)
 
 typedef __nv_bfloat16 bf16;
 

@@ -156,7 +156,25 @@ struct b200rl_model {
   int *targets, *lens;
   long long slab_elems;
   int rope_L;
+  // optional per-op CUDA-event profiling (bench.py roofline / DESIGN.md breakdown)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_cat;
+  std::vector<double> prof_work;
+  int prof_n = 0;
 };
+
+enum { CAT_GEMM = 0, CAT_GEMM_SKINNY = 1, CAT_GEMM_DW = 2, CAT_DEQUANT = 3, CAT_ATTN_FWD = 4, CAT_ATTN_BWD = 5,
+       CAT_ROW = 6, CAT_LOGPROB = 7, CAT_MISC = 8, CAT_END = -1, NCAT = 9 };
+
+static inline void prof_mark(b200rl_model* m, cudaStream_t st, int cat, double work) {
+  if (!m->prof_on || m->prof_n >= (int)m->prof_ev.size()) return;
+  cudaEventRecord(m->prof_ev[m->prof_n], st);
+  m->prof_cat[m->prof_n] = cat;
+  m->prof_work[m->prof_n] = work;
+  ++m->prof_n;
+}
+#define PM(cat, work) prof_mark(m, st, (cat), (double)(work))
 
 static void build_groups(b200rl_model* m) {
   const b200rl_model_config& c = m->cfg;
@@ -477,7 +495,7 @@ extern "C" void* b200rl_model_debug_ptr(b200rl_model* m, const char* name, int l
 
 namespace {
 
-int gemm_tn(cudaStream_t st, const bf16* A1, long long lda1, const bf16* B1, long long ldb1, int K1,
+int gemm_tn(b200rl_model* m, int cat, cudaStream_t st, const bf16* A1, long long lda1, const bf16* B1, long long ldb1, int K1,
             const bf16* A2, long long lda2, const bf16* B2, long long ldb2, int K2, bf16* C,
             long long ldc, const bf16* bias, const bf16* residual, long long ldr, float alpha, int M,
             int N) {
@@ -488,6 +506,7 @@ int gemm_tn(cudaStream_t st, const bf16* A1, long long lda1, const bf16* B1, lon
   a.bias = bias; a.residual = residual; a.ldr = ldr; a.alpha = alpha;
   a.M = M; a.N = N; a.mn_major = 0; a.splits = 1; a.c_split_stride = 0;
   a.force_bn = 0; a.max_ctas = 0;
+  PM(cat, 2.0 * M * N * K1 + (K2 ? 2.0 * M * N * m->cfg.lora_r : 0.0));
   return gemm_dispatch(a, st);
 }
 
@@ -509,7 +528,9 @@ int lora_dw(b200rl_model* m, cudaStream_t st, const Group& g, const bf16* dY, lo
     a.A1 = Y; a.lda1 = ldy; a.B1 = U; a.ldb1 = g.K2; a.K1 = M; a.K2 = 0;
     a.C = m->slabs; a.ldc = g.K2; a.c_fp32 = 1; a.alpha = 1.f;
     a.M = Ny; a.N = g.K2; a.mn_major = 1; a.splits = splits; a.c_split_stride = stride;
+    PM(CAT_GEMM_DW, 2.0 * M * Ny * m->cfg.lora_r * g.nproj);
     RC(gemm_dispatch(a, st));
+    PM(CAT_MISC, 0);
     AccumArgs acc;
     memset(&acc, 0, sizeof(acc));
     acc.nblk = g.nproj;
@@ -564,6 +585,7 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
     m->rope_L = L;
   }
   // ---------------- forward ----------------
+  PM(CAT_ROW, 2.0 * M * H * 2);
   RC(b200rl_embed(ids, m->embed, m->X, M, H, V, stream));
   for (int l = 0; l < c.n_layers; ++l) {
     const b200rl_layer_weights& w = m->layers[l];
@@ -575,44 +597,64 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
     const Group& gd = m->groups[l * 4 + 3];
     bf16* x = m->X + (long long)l * Mt * H;
     bf16* xn = m->X + (long long)(l + 1) * Mt * H;
+    PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(x, w.ln1_w, a.h1, a.rstd1, M, H, c.rms_eps, stream));
-    RC(gemm_tn(st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    PM(CAT_DEQUANT, 2.5625 * (QKV) * (H));
     RC(b200rl_nf4_dequant(w.qkv_packed, w.qkv_absmax, m->wbuf, QKV, H, 0, stream));
-    RC(gemm_tn(st, a.h1, H, m->wbuf, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, gq.K2, a.qkv, QKV,
+    RC(gemm_tn(m, CAT_GEMM, st, a.h1, H, m->wbuf, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, gq.K2, a.qkv, QKV,
                (const bf16*)w.qkv_bias, nullptr, 0, 1.f, M, QKV));
+    PM(CAT_ROW, 2.0 * M * (c.n_q_heads + c.n_kv_heads) * c.head_dim * 2);
     RC(b200rl_rope(a.qkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 0, stream));
+    PM(CAT_ATTN_FWD, 2.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
     RC(b200rl_attn_fwd(a.qkv, attn_mask, a.attn_o, a.lse, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
-    RC(gemm_tn(st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    PM(CAT_DEQUANT, 2.5625 * (H) * (QD));
     RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 0, stream));
-    RC(gemm_tn(st, a.attn_o, QD, m->wbuf, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, go.K2, a.x_mid, H,
+    RC(gemm_tn(m, CAT_GEMM, st, a.attn_o, QD, m->wbuf, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, go.K2, a.x_mid, H,
                nullptr, x, H, 1.f, M, H));
+    PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(a.x_mid, w.ln2_w, a.h2, a.rstd2, M, H, c.rms_eps, stream));
-    RC(gemm_tn(st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    PM(CAT_DEQUANT, 2.5625 * (2 * I) * (H));
     RC(b200rl_nf4_dequant(w.gu_packed, w.gu_absmax, m->wbuf, 2 * I, H, 0, stream));
-    RC(gemm_tn(st, a.h2, H, m->wbuf, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, gg.K2, a.gu, 2 * I,
+    RC(gemm_tn(m, CAT_GEMM, st, a.h2, H, m->wbuf, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, gg.K2, a.gu, 2 * I,
                nullptr, nullptr, 0, 1.f, M, 2 * I));
+    PM(CAT_ROW, 3.0 * M * I * 2);
     RC(b200rl_swiglu_fwd(a.gu, a.act, M, I, stream));
-    RC(gemm_tn(st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    PM(CAT_DEQUANT, 2.5625 * (H) * (I));
     RC(b200rl_nf4_dequant(w.down_packed, w.down_absmax, m->wbuf, H, I, 0, stream));
-    RC(gemm_tn(st, a.act, I, m->wbuf, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, gd.K2, xn, H, nullptr,
+    RC(gemm_tn(m, CAT_GEMM, st, a.act, I, m->wbuf, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, gd.K2, xn, H, nullptr,
                a.x_mid, H, 1.f, M, H));
   }
   // head: only the T scored positions (rows P-1 .. L-2) go through the final norm and lm_head
   bf16* xf = m->X + (long long)c.n_layers * Mt * H;
+  PM(CAT_ROW, 2.0 * R * H * 2);
   RC(b200rl_gather_rows(xf, m->xsel, B, L, T, P - 1, H, stream));
+  PM(CAT_ROW, 2.0 * R * H * 2);
   RC(b200rl_rmsnorm_fwd(m->xsel, m->final_norm, m->hsel, m->rstd_f, R, H, c.rms_eps, stream));
-  RC(gemm_tn(st, m->hsel, H, m->lm_head, H, H, nullptr, 0, nullptr, 0, 0, m->logits, V, nullptr, nullptr, 0, 1.f, R, V));
+  RC(gemm_tn(m, CAT_GEMM, st, m->hsel, H, m->lm_head, H, H, nullptr, 0, nullptr, 0, 0, m->logits, V, nullptr, nullptr, 0, 1.f, R, V));
+  PM(CAT_MISC, 0);
   targets_kernel<<<(R + 255) / 256, 256, 0, st>>>(ids, m->targets, L, P, T, R);
   B200RL_LAUNCH_OK();
+  PM(CAT_MISC, 0);
   if (backward) RC(b200rl_loss_coef(answer_mask, adv, m->coef, m->lens, B, T, nb, stream));
   float* lp = lp_out ? lp_out : m->lp;
+  PM(CAT_LOGPROB, (backward ? 2.0 : 1.0) * R * V * 2);
   RC(b200rl_logprob(m->logits, V, m->targets, backward ? m->coef : nullptr, lp, R, V, backward ? 1 : 0, stream));
+  PM(CAT_MISC, 0);
   if (loss_accum && adv) RC(b200rl_loss_value(lp, answer_mask, adv, loss_accum, B, T, grpo, stream));
-  if (!backward) return 0;
+  if (!backward) {
+    PM(CAT_END, 0);
+    return 0;
+  }
 
   // ---------------- backward ----------------
-  RC(gemm_tn(st, m->logits, V, m->lm_head_t, V, V, nullptr, 0, nullptr, 0, 0, m->dhsel, H, nullptr, nullptr, 0, 1.f, R, H));
+  RC(gemm_tn(m, CAT_GEMM, st, m->logits, V, m->lm_head_t, V, V, nullptr, 0, nullptr, 0, 0, m->dhsel, H, nullptr, nullptr, 0, 1.f, R, H));
+  PM(CAT_ROW, 3.0 * R * H * 2);
   RC(b200rl_rmsnorm_bwd(m->dhsel, m->xsel, m->final_norm, m->rstd_f, nullptr, m->dhsel, R, H, stream));
+  PM(CAT_ROW, 1.0 * (R + M) * H * 2);
   RC(b200rl_scatter_rows(m->dhsel, m->dx, B, L, T, P - 1, H, stream));
   for (int l = c.n_layers - 1; l >= 0; --l) {
     const b200rl_layer_weights& w = m->layers[l];
@@ -624,33 +666,74 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
     const Group& gd = m->groups[l * 4 + 3];
     bf16* x = m->X + (long long)l * Mt * H;
     // ---- down projection
-    RC(gemm_tn(st, m->dx, H, ar + gd.bcat_t, H, H, nullptr, 0, nullptr, 0, 0, m->du, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, m->dx, H, ar + gd.bcat_t, H, H, nullptr, 0, nullptr, 0, 0, m->du, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
     RC(lora_dw(m, st, gd, m->dx, H, a.u_d, a.act, I, m->du, M));
+    PM(CAT_DEQUANT, 2.5625 * (H) * (I));
     RC(b200rl_nf4_dequant(w.down_packed, w.down_absmax, m->wbuf, H, I, 1, stream));  // Wd^T [I, H]
-    RC(gemm_tn(st, m->dx, H, m->wbuf, H, H, m->du, gd.K2, ar + gd.acat_t, gd.K2, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
+    RC(gemm_tn(m, CAT_GEMM, st, m->dx, H, m->wbuf, H, H, m->du, gd.K2, ar + gd.acat_t, gd.K2, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
+    PM(CAT_ROW, 5.0 * M * I * 2);
     RC(b200rl_swiglu_bwd(a.gu, m->dact, m->dgu, M, I, stream));
     // ---- gate|up
-    RC(gemm_tn(st, m->dgu, 2 * I, ar + gg.bcat_t, 2 * I, 2 * I, nullptr, 0, nullptr, 0, 0, m->du, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, m->dgu, 2 * I, ar + gg.bcat_t, 2 * I, 2 * I, nullptr, 0, nullptr, 0, 0, m->du, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
     RC(lora_dw(m, st, gg, m->dgu, 2 * I, a.u_gu, a.h2, H, m->du, M));
+    PM(CAT_DEQUANT, 2.5625 * (2 * I) * (H));
     RC(b200rl_nf4_dequant(w.gu_packed, w.gu_absmax, m->wbuf, 2 * I, H, 1, stream));  // Wgu^T [H, 2I]
-    RC(gemm_tn(st, m->dgu, 2 * I, m->wbuf, 2 * I, 2 * I, m->du, gg.K2, ar + gg.acat_t, gg.K2, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+    RC(gemm_tn(m, CAT_GEMM, st, m->dgu, 2 * I, m->wbuf, 2 * I, 2 * I, m->du, gg.K2, ar + gg.acat_t, gg.K2, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+    PM(CAT_ROW, 4.0 * M * H * 2);
     RC(b200rl_rmsnorm_bwd(m->dh, a.x_mid, w.ln2_w, a.rstd2, m->dx, m->dx, M, H, stream));
     // ---- o projection
-    RC(gemm_tn(st, m->dx, H, ar + go.bcat_t, H, H, nullptr, 0, nullptr, 0, 0, m->du, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, m->dx, H, ar + go.bcat_t, H, H, nullptr, 0, nullptr, 0, 0, m->du, go.K2, nullptr, nullptr, 0, s, M, go.K2));
     RC(lora_dw(m, st, go, m->dx, H, a.u_o, a.attn_o, QD, m->du, M));
+    PM(CAT_DEQUANT, 2.5625 * (H) * (QD));
     RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 1, stream));  // Wo^T [QD, H]
-    RC(gemm_tn(st, m->dx, H, m->wbuf, H, H, m->du, go.K2, ar + go.acat_t, go.K2, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
+    RC(gemm_tn(m, CAT_GEMM, st, m->dx, H, m->wbuf, H, H, m->du, go.K2, ar + go.acat_t, go.K2, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
     // ---- attention + rope
+    PM(CAT_ATTN_BWD, 4.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
     RC(b200rl_attn_bwd(a.qkv, attn_mask, a.attn_o, m->dattn, a.lse, m->delta, m->dqkv, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
+    PM(CAT_ROW, 2.0 * M * (c.n_q_heads + c.n_kv_heads) * c.head_dim * 2);
     RC(b200rl_rope(m->dqkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 1, stream));
     // ---- qkv projection
-    RC(gemm_tn(st, m->dqkv, QKV, ar + gq.bcat_t, QKV, QKV, nullptr, 0, nullptr, 0, 0, m->du, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, m->dqkv, QKV, ar + gq.bcat_t, QKV, QKV, nullptr, 0, nullptr, 0, 0, m->du, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
     RC(lora_dw(m, st, gq, m->dqkv, QKV, a.u_qkv, a.h1, H, m->du, M));
     if (l > 0) {  // embeddings are frozen: layer 0 needs no input gradient
+      PM(CAT_DEQUANT, 2.5625 * (QKV) * (H));
       RC(b200rl_nf4_dequant(w.qkv_packed, w.qkv_absmax, m->wbuf, QKV, H, 1, stream));  // Wqkv^T [H, QKV]
-      RC(gemm_tn(st, m->dqkv, QKV, m->wbuf, QKV, QKV, m->du, gq.K2, ar + gq.acat_t, gq.K2, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+      RC(gemm_tn(m, CAT_GEMM, st, m->dqkv, QKV, m->wbuf, QKV, QKV, m->du, gq.K2, ar + gq.acat_t, gq.K2, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+      PM(CAT_ROW, 4.0 * M * H * 2);
       RC(b200rl_rmsnorm_bwd(m->dh, x, w.ln1_w, a.rstd1, m->dx, m->dx, M, H, stream));
     }
   }
+  PM(CAT_END, 0);
+  return 0;
+}
+
+// ---- profiling API (bench.py) ---------------------------------------------------------------------
+extern "C" int b200rl_model_profile(b200rl_model* m, int enable) {
+  B200RL_REQUIRE(m != nullptr, "model_profile: null model");
+  if (enable && m->prof_ev.empty()) {
+    const int cap = 1 << 16;
+    m->prof_ev.resize(cap);
+    m->prof_cat.resize(cap);
+    m->prof_work.resize(cap);
+    for (int i = 0; i < cap; ++i) B200RL_CUDA_OK(cudaEventCreate(&m->prof_ev[i]));
+  }
+  m->prof_on = enable != 0;
+  m->prof_n = 0;
+  return 0;
+}
+
+// Sums per category since the last read: ms[NCAT], work[NCAT] (flops or bytes), count[NCAT]. Synchronises.
+extern "C" int b200rl_model_profile_read(b200rl_model* m, double* ms, double* work, long long* count) {
+  B200RL_REQUIRE(m && ms && work && count, "model_profile_read: null pointer");
+  for (int i = 0; i < NCAT; ++i) { ms[i] = 0; work[i] = 0; count[i] = 0; }
+  if (m->prof_n > 0) B200RL_CUDA_OK(cudaEventSynchronize(m->prof_ev[m->prof_n - 1]));
+  for (int i = 0; i + 1 < m->prof_n; ++i) {
+    const int c = m->prof_cat[i];
+    if (c < 0) continue;
+    float t = 0.f;
+    B200RL_CUDA_OK(cudaEventElapsedTime(&t, m->prof_ev[i], m->prof_ev[i + 1]));
+    ms[c] += t; work[c] += m->prof_work[i]; count[c] += 1;
+  }
+  m->prof_n = 0;
   return 0;
 }

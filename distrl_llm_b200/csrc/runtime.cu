@@ -6,6 +6,7 @@
 namespace b200rl {
 
 static thread_local char g_last_error[1024] = "";
+long long g_launch_count = 0;
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -33,6 +34,8 @@ int num_sms() {
 extern "C" const char* b200rl_last_error(void) { return b200rl::g_last_error; }
 
 extern "C" int b200rl_version(void) { return 100; }
+
+extern "C" long long b200rl_launch_count(void) { return b200rl::g_launch_count; }
 
 // Returns 0 when the current device is an sm_100 part (the only target of this library).
 extern "C" int b200rl_check_device(void) {

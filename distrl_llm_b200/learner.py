@@ -1,0 +1,219 @@
+"""Learner / GRPOLearner: same method surface as the reference's Ray actors
+(distributed_actor.py:196-514), with the learner math running in libb200rl (sm_100a CUDA).
+
+Method-by-method mirror (reference line numbers in each docstring).  Differences that are deliberate
+and documented in DESIGN.md:
+  * token ids may be passed instead of strings (tokenizer = IdTokenizer) — removes quirk Q6;
+  * the loss scalar is accumulated on the device, one .item() per compute_loss instead of one per
+    micro-batch (:387 / :485);
+  * multi-learner mode: compute_gradients leaves the gradients in a peer-mapped device buffer and
+    apply_merged_gradients runs the fused P2P reduce + Adam on EVERY learner (fixes quirk Q4); the
+    reference's dict-of-CPU-tensors exchange is still available (export_gradients / a list of dicts
+    passed to apply_merged_gradients) and is what the parity tests use.
+There is no CPU or torch fallback: constructing a learner without libb200rl / a B200 raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .policy import LMConfig, Policy
+
+try:  # Ray is the reference's process model; optional here (not installed in the build image)
+    import ray  # type: ignore
+
+    def _remote(cls):
+        return ray.remote(num_gpus=1, num_cpus=1)(cls)
+except Exception:  # pragma: no cover
+    ray = None
+
+    def _remote(cls):
+        return cls
+
+
+class IdTokenizer:
+    """Token-id passthrough with the reference's padding rules (distributed_actor.py:217-229):
+    batch_encode_plus(items, padding='max_length', padding_side=..., max_length=..., truncation=True)."""
+
+    def __init__(self, pad_id=0):
+        self.pad_token_id = pad_id
+
+    def batch_encode_plus(self, items, return_tensors="pt", padding="max_length", padding_side="right",
+                          max_length=None, truncation=True):
+        n = len(items)
+        ids = np.full((n, max_length), self.pad_token_id, dtype=np.int32)
+        mask = np.zeros((n, max_length), dtype=np.int32)
+        for i, it in enumerate(items):
+            it = list(it)[:max_length]
+            if not it:
+                continue
+            if padding_side == "left":
+                ids[i, max_length - len(it):] = it
+                mask[i, max_length - len(it):] = 1
+            else:
+                ids[i, :len(it)] = it
+                mask[i, :len(it)] = 1
+        return {"input_ids": torch.from_numpy(ids), "attention_mask": torch.from_numpy(mask)}
+
+
+class BaseLearner:
+    """reference BaseLearner (distributed_actor.py:196-333)."""
+
+    learner_type = "pg"
+
+    def __init__(self, policy: Policy, tokenizer, config: dict, gpu_id=0, generator=None, reference_quirks=True):
+        self.policy = policy
+        self.tokenizer = tokenizer
+        self.model_gpu_id = gpu_id                                # :28 (informational)
+        self.update_batch_size = config["train_batch_size"]       # :29
+        self.max_new_tokens = config["max_new_tokens"]            # :31
+        self.max_prompt_tokens = config["max_prompt_tokens"]      # :213
+        self.lr = config["lr"]                                    # :210
+        self.weight_decay = config.get("weight_decay", 0.0)       # commented out in the reference (:210)
+        self.lora_save_path = config.get("lora_save_path", "lora_request_math")
+        self.reference_quirks = reference_quirks
+        self.generator = generator
+        self.p2p = None  # set by enable_p2p()
+        self._pinned = {}
+
+    # ---- tokenise + pad (:217-239) ------------------------------------------------------------
+    def _encode(self, messages, answers):
+        P, T = self.max_prompt_tokens, self.max_new_tokens
+        inputs = self.tokenizer.batch_encode_plus(messages, return_tensors="pt", padding="max_length",
+                                                  padding_side="left", max_length=P, truncation=True)
+        tok_ans = self.tokenizer.batch_encode_plus(answers, return_tensors="pt", max_length=T,
+                                                   padding="max_length", padding_side="right", truncation=True)
+        ids = torch.cat([inputs["input_ids"], tok_ans["input_ids"]], dim=1).to(torch.int32)
+        am = torch.cat([inputs["attention_mask"], tok_ans["attention_mask"]], dim=1).to(torch.int32)
+        return ids, am, tok_ans["attention_mask"].to(torch.int32)
+
+    def _h2d(self, t):
+        return t.contiguous().pin_memory().to(self.policy.device, non_blocking=True)
+
+    def compute_current_policy_probs(self, policy, messages, answers):
+        """(:215-261) -> (action_log_probs [B,T] fp32, answer_mask [B,T]) on the device; scoring only."""
+        ids, am, ansm = self._encode(messages, answers)
+        B = ids.shape[0]
+        lp = torch.empty(B, self.max_new_tokens, device=policy.device, dtype=torch.float32)
+        d_ansm = self._h2d(ansm)
+        policy.microbatch(self._h2d(ids), self._h2d(am), d_ansm, None, self.max_prompt_tokens,
+                          self.max_new_tokens, 1, False, backward=False, lp_out=lp)
+        return lp, d_ansm
+
+    # ---- loss + backward (:349-395 PG, :440-493 GRPO) ---------------------------------------------
+    def compute_loss(self, messages, answers, rewards):
+        rewards = np.asarray([float(r) for r in rewards], dtype=np.float64)   # :350 / :441 (float64)
+        n = len(messages)
+        nb = (n + self.update_batch_size - 1) // self.update_batch_size      # :354-356
+        pol = self.policy
+        pol.zero_grad()                                                       # :358 / :450
+        pol.loss_accum.zero_()
+        grpo = self.learner_type == "grpo"
+        for i in range(nb):
+            s, e = i * self.update_batch_size, min((i + 1) * self.update_batch_size, n)
+            r = rewards[s:e]
+            # :367 / :459  `if batch_rewards.all() == 0: continue` — true when ANY reward is exactly 0 (quirk Q1)
+            if self.reference_quirks and not bool(np.all(r != 0)):
+                continue
+            ids, am, ansm = self._encode(messages[s:e], answers[s:e])
+            pol.microbatch(self._h2d(ids), self._h2d(am), self._h2d(ansm), self._h2d(torch.from_numpy(r)),
+                           self.max_prompt_tokens, self.max_new_tokens, nb, grpo, backward=True)
+        return float(pol.loss_accum.item())   # sum of per-micro-batch losses (quirk Q2), one sync
+
+    # ---- gradient export / merge (:283-333) --------------------------------------------------------
+    def export_gradients(self):
+        """{PEFT name: CPU tensor} (:289-293) from ONE device->host copy of the flat buffer."""
+        host = self.policy.lora_grad.detach().cpu()
+        return {k: v.clone() for k, v in self.policy.named_views(host).items()}
+
+    def _compute_gradients(self, problems, answers, rewards, export=True):
+        loss = self.compute_loss(problems, answers, rewards)   # zero_grad + compute_loss (:285-286)
+        return (self.export_gradients() if export else {}), loss
+
+    def compute_gradients(self, candidates):
+        """(:296-300). With P2P enabled the gradients stay on the device (returns ({}, loss))."""
+        problems, answers, rewards = candidates
+        return self._compute_gradients(problems, answers, rewards, export=self.p2p is None)
+
+    def apply_merged_gradients(self, gradients_list=None):
+        """(:302-333). Reference path: list of gradient dicts -> mean -> Adam. P2P path: fused one-shot
+        reduce + Adam + write-back on every learner (gradients_list ignored)."""
+        pol = self.policy
+        if self.p2p is not None:
+            self.p2p.reduce_adam_step(pol, self.lr, self.weight_decay)
+            return
+        if not gradients_list:
+            print("No gradients to merge.")
+            return
+        n = len(gradients_list)
+        merged = None
+        for g in gradients_list:   # :316-319 (sum) ... :322-323 (divide)
+            flat = torch.zeros(pol.lora_numel, dtype=torch.float32)
+            views = pol.named_views(flat)
+            for k, v in g.items():
+                views[k].copy_(v)
+            merged = flat if merged is None else merged + flat
+        merged /= n
+        pol.lora_grad.copy_(merged.to(pol.device))                    # :326-328
+        pol.optimizer_step(self.lr, weight_decay=self.weight_decay)   # :331-333
+
+    def enable_p2p(self, group):
+        self.p2p = group
+
+    # ---- misc actor surface --------------------------------------------------------------------------
+    def generate(self, messages, sampling_params=None):
+        """(:174-180) generation is the generator's job (vLLM or a stub), not part of the hot path."""
+        if self.generator is None:
+            raise RuntimeError("this learner has no generator attached")
+        return self.generator.generate(messages, sampling_params)
+
+    def save_checkpoint(self, path):
+        """(:263-264) LoRA adapter state dict with PEFT names."""
+        import os
+        os.makedirs(path, exist_ok=True)
+        torch.save(self.policy.lora_state_dict(), os.path.join(path, "adapter_model.pt"))
+
+    def save_adapter(self):
+        """(:84-86)"""
+        self.save_checkpoint(self.lora_save_path)
+
+
+class Learner(BaseLearner):
+    """reference Learner (PG), distributed_actor.py:336-416."""
+
+    learner_type = "pg"
+
+    def train(self, candidates):
+        """(:397-416): flatten, subtract the per-problem baseline (`r - b`, :406), compute_loss, step."""
+        problems, answers, rewards = [], [], []
+        for cand in candidates:
+            for a, p, r, b in zip(cand["answers"], cand["problem"], cand["rewards"], cand["baselines"]):
+                problems.extend(p)
+                answers.extend(a)
+                rewards.extend(np.asarray(r) - b)
+        loss = self.compute_loss(problems, answers, rewards)
+        self.policy.optimizer_step(self.lr, weight_decay=self.weight_decay)
+        return loss
+
+
+class GRPOLearner(BaseLearner):
+    """reference GRPOLearner, distributed_actor.py:419-514."""
+
+    learner_type = "grpo"
+
+    def train(self, candidates):
+        """(:495-514)"""
+        problems, answers, rewards = [], [], []
+        for cand in candidates:
+            for a, p, r in zip(cand["answers"], cand["problem"], cand["rewards"]):
+                problems.extend(p)
+                answers.extend(a)
+                rewards.extend(r)
+        loss = self.compute_loss(problems, answers, rewards)
+        self.policy.optimizer_step(self.lr, weight_decay=self.weight_decay)
+        return loss
+
+
+RemoteLearner = _remote(Learner) if ray is not None else Learner
+RemoteGRPOLearner = _remote(GRPOLearner) if ray is not None else GRPOLearner

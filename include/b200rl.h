@@ -148,6 +148,13 @@ int b200rl_model_microbatch(b200rl_model* m, const int* ids, const int* attn_mas
                             double* loss_accum, int B, int P, int T, int nb, int grpo, int backward,
                             void* stream);
 
+/* per-op CUDA-event profiling of the driver (categories: 0 gemm, 1 skinny LoRA gemm, 2 dW gemm, 3 nf4
+ * dequant, 4 attn fwd, 5 attn bwd, 6 row kernels, 7 logprob, 8 misc); read() returns sums since the last
+ * read: ms[9], work[9] (algorithmic flops or bytes), count[9]. */
+int b200rl_model_profile(b200rl_model* m, int enable);
+int b200rl_model_profile_read(b200rl_model* m, double* ms, double* work, long long* count);
+long long b200rl_launch_count(void); /* kernels launched by the library so far */
+
 #ifdef __cplusplus
 }
 #endif

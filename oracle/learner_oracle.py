@@ -185,7 +185,7 @@ def compute_loss(params, cfg, ids, attn_mask, answer_mask, rewards, P, train_bat
     """Learner.compute_loss (distributed_actor.py:349-395) / GRPOLearner.compute_loss (:440-493).
     Accumulates .grad on the LoRA tensors of `params` (those with requires_grad) and returns the float
     the reference returns: the SUM over micro-batches of the per-micro-batch mean loss (quirk Q2)."""
-    rewards = torch.as_tensor(np.asarray(rewards), dtype=torch.float64)  # :350 / :441 -> float64 tensor
+    rewards = torch.as_tensor(np.asarray(rewards), dtype=torch.float64).to(ids.device)  # :350 / :441 -> float64 tensor .to("cuda")
     N = ids.shape[0]
     nb = (N + train_batch_size - 1) // train_batch_size  # :354-356
     total = 0.0

@@ -1,0 +1,181 @@
+"""End-to-end parity (GPU): the libb200rl learner (through the reference-shaped Learner / GRPOLearner
+classes and the C ABI) against
+  (a) the committed golden vectors produced by the REFERENCE's own code (tests/golden/cfg1_learner.npz,
+      BASELINE config 1), and
+  (b) the pinned oracle (oracle/learner_oracle.py) on larger seeded synthetic batches.
+
+Tolerances (floating point; the CUDA path computes in bf16 with fp32 accumulation like the reference's
+autocast, the oracle/golden in fp32):
+  per-token log-prob  |d| <= 4e-2 ;  loss |d| <= 2e-2*|loss| + 2e-3 ;
+  LoRA grads: global cosine >= 0.999 and global rel-L2 <= 5e-2, per-tensor cosine >= 0.99.
+The bf16-autocast golden (also generated from the reference) differs from its own fp32 golden by a
+similar amount (tests/test_oracle.py::test_bf16_autocast_golden_is_close_to_fp32).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import learner_oracle as lo  # noqa: E402  (checker only)
+from tests.golden_utils import load_cfg1  # noqa: E402
+
+
+def _mk_cfg(ocfg):
+    from distrl_llm_b200.policy import LMConfig
+    return LMConfig(vocab=ocfg.vocab, hidden=ocfg.hidden, inter=ocfg.inter, n_layers=ocfg.n_layers,
+                    n_q_heads=ocfg.n_q_heads, n_kv_heads=ocfg.n_kv_heads, head_dim=ocfg.head_dim,
+                    lora_r=ocfg.lora_r, lora_alpha=ocfg.lora_alpha, rms_eps=ocfg.rms_eps, rope_theta=ocfg.rope_theta)
+
+
+def _mk_learner(kind, ocfg, params, nf4, P, T, B, device, lr=2e-5, quirks=True):
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer, Learner
+    from distrl_llm_b200.policy import Policy
+    pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, device, max_batch=B, P=P, T=T)
+    config = {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": lr}
+    cls = Learner if kind == "pg" else GRPOLearner
+    return cls(pol, IdTokenizer(), config, reference_quirks=quirks)
+
+
+def _compare_grads(got: dict, ref: dict, ocfg, pol, cos_min=0.999, rel_max=5e-2):
+    va, vb = [], []
+    for i in range(ocfg.n_layers):
+        for m in lo.LORA_MODULES:
+            for ab in ("A", "B"):
+                a = got[pol.peft_name(i, m, ab)].double().flatten()
+                b = ref[f"l{i}.{m}.{ab}"].double().flatten().cpu()
+                if b.norm() > 0:
+                    c = (a @ b) / (a.norm() * b.norm() + 1e-300)
+                    assert c > 0.99, f"l{i}.{m}.{ab} cosine {c.item():.5f}"
+                va.append(a)
+                vb.append(b)
+    va, vb = torch.cat(va), torch.cat(vb)
+    cos = ((va @ vb) / (va.norm() * vb.norm())).item()
+    rel = ((va - vb).norm() / vb.norm()).item()
+    assert cos >= cos_min and rel <= rel_max, f"global cosine {cos:.6f}, rel-L2 {rel:.4f}"
+    return cos, rel
+
+
+# ---------------------------------------------------------------------------------------------------
+# (a) golden vectors from the reference's own code — BASELINE config 1
+# ---------------------------------------------------------------------------------------------------
+def test_cfg1_logprobs_vs_reference_golden(cuda):
+    z, ocfg, params, nf4, prompts, answers = load_cfg1()
+    P, T, B = int(z["P"]), int(z["T"]), int(z["train_batch_size"])
+    ln = _mk_learner("pg", ocfg, params, nf4, P, T, B, cuda)
+    lp, mask = ln.compute_current_policy_probs(ln.policy, prompts[:B], answers[:B])
+    assert np.array_equal(mask.cpu().numpy(), z["answer_mask_mb0"])
+    m = mask.bool().cpu()
+    d = (lp.cpu()[m] - torch.from_numpy(z["fp32.logp_mb0"])[m]).abs().max().item()
+    assert d < 4e-2, f"max |dlogp| {d}"
+
+
+@pytest.mark.parametrize("kind", ["pg", "grpo"])
+def test_cfg1_gradients_vs_reference_golden(cuda, kind):
+    z, ocfg, params, nf4, prompts, answers = load_cfg1()
+    P, T, B = int(z["P"]), int(z["T"]), int(z["train_batch_size"])
+    ln = _mk_learner(kind, ocfg, params, nf4, P, T, B, cuda)
+    r = z["rewards"] - z["baseline"] if kind == "pg" else z["grpo_adv"]
+    grads, loss = ln._compute_gradients(prompts, answers, list(r))
+    # PG loss = -mean(lp_seq * r) with sum(r) = 0 is a small difference of O(6) numbers: its error bound is
+    # max|dlp| * mean|r| per micro-batch (the bf16 golden itself is 6e-3 away from the fp32 golden)
+    loss_tol = 4e-2 * sum(np.abs(r[i:i + B]).mean() for i in range(0, len(r), B)) + 2e-3
+    for mode in ("fp32", "bf16"):
+        ref_loss = float(z[f"{mode}.{kind}.loss"])
+        assert abs(loss - ref_loss) <= loss_tol, (mode, loss, ref_loss)
+        ref = {n: torch.from_numpy(z[f"{mode}.{kind}.grad.{n}"]) for n in lo.lora_names(ocfg)}
+        _compare_grads(grads, ref, ocfg, ln.policy)
+
+
+def test_cfg1_quirk_q1_skip(cuda):
+    z, ocfg, params, nf4, prompts, answers = load_cfg1()
+    P, T, B = int(z["P"]), int(z["T"]), int(z["train_batch_size"])
+    ln = _mk_learner("grpo", ocfg, params, nf4, P, T, B, cuda)
+    grads, loss = ln._compute_gradients(prompts, answers, list(z["fp32.q1.rewards"]))
+    assert abs(loss - float(z["fp32.q1.loss"])) < 1e-9  # GRPO loss value = -mean(adv) of the trained micro-batch: exact
+    ref = torch.from_numpy(z["fp32.q1.grad.l0.q.B"]).double().flatten()
+    got = grads[ln.policy.peft_name(0, "q", "B")].double().flatten()
+    assert (got @ ref) / (got.norm() * ref.norm()) > 0.999
+
+
+def test_cfg1_merge_and_step_vs_reference_golden(cuda):
+    """Two learners' gradient dicts through apply_merged_gradients (reference :302-333 semantics)."""
+    z, ocfg, params, nf4, prompts, answers = load_cfg1()
+    P, T, B = int(z["P"]), int(z["T"]), int(z["train_batch_size"])
+    ln = _mk_learner("pg", ocfg, params, nf4, P, T, B, cuda)
+    r = list(z["rewards"] - z["baseline"])
+    g1, _ = ln._compute_gradients(prompts[:2], answers[:2], r[:2])
+    g2, _ = ln._compute_gradients(prompts[2:], answers[2:], r[2:])
+    before = ln.policy.lora_state_dict()
+    ln.apply_merged_gradients([g1, g2])
+    after = ln.policy.lora_state_dict()
+    # Adam's first step moves every weight by ~lr*sign(g): compare the UPDATE direction with the reference's
+    num = den = 0.0
+    for i in range(ocfg.n_layers):
+        for m in lo.LORA_MODULES:
+            for ab in ("A", "B"):
+                k = ln.policy.peft_name(i, m, ab)
+                ref_delta = torch.from_numpy(z[f"fp32.merged_step.l{i}.{m}.{ab}"]) - torch.from_numpy(z[f"param.l{i}.{m}.{ab}"])
+                d = (after[k] - before[k]).double()
+                num += (d.flatten() @ ref_delta.double().flatten()).item()
+                den += d.norm().item() ** 2
+                assert (d.abs() <= 2e-5 * 1.001).all()  # |step| <= lr on step 1
+    assert num / den > 0.97, "merged Adam update must point the same way as the reference's"
+    assert (ln.policy.lora_grad == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# (b) oracle on larger seeded batches (ragged lengths, several micro-batches, head_dim 64 and 128)
+# ---------------------------------------------------------------------------------------------------
+CASES = [
+    # name, cfg kwargs, N, P, T, B, learner
+    ("hd64_grpo", dict(vocab=8192, hidden=512, inter=1024, n_layers=4, n_q_heads=8, n_kv_heads=2, head_dim=64, lora_r=16, lora_alpha=16), 6, 24, 40, 4, "grpo"),
+    ("hd128_pg", dict(vocab=4096, hidden=512, inter=1536, n_layers=3, n_q_heads=4, n_kv_heads=2, head_dim=128, lora_r=16, lora_alpha=32), 5, 70, 130, 2, "pg"),
+    ("r32_grpo", dict(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=4, n_kv_heads=4, head_dim=64, lora_r=32, lora_alpha=16), 8, 16, 48, 8, "grpo"),
+]
+
+
+@pytest.mark.parametrize("name,ckw,N,P,T,B,kind", CASES, ids=[c[0] for c in CASES])
+def test_learner_vs_oracle(cuda, name, ckw, N, P, T, B, kind):
+    ocfg = lo.OracleConfig(**ckw)
+    params, nf4 = lo.make_params(ocfg, seed=11)
+    prompts, answers, rewards = lo.make_batch(ocfg, N, P, T, seed=3, ragged=True, group_size=N, learner=kind)
+    # oracle in fp32 on the GPU (checker only; same code that is pinned on CPU against the goldens)
+    dparams = {k: (v.detach().to(cuda).requires_grad_(v.requires_grad)) for k, v in params.items()}
+    ids, am, ansm = lo.pad_batch(prompts, answers, P, T)
+    ref_grads, ref_loss = lo.compute_gradients(dparams, ocfg, ids.to(cuda), am.to(cuda), ansm.to(cuda), rewards, P, B, kind)
+    ln = _mk_learner(kind, ocfg, params, nf4, P, T, B, cuda)
+    grads, loss = ln._compute_gradients(prompts, answers, list(rewards))
+    loss_tol = 4e-2 * sum(np.abs(rewards[i:i + B]).mean() for i in range(0, N, B)) + 2e-3
+    assert abs(loss - ref_loss) <= loss_tol, (loss, ref_loss)
+    _compare_grads(grads, ref_grads, ocfg, ln.policy)
+    # scoring-only API agrees with the oracle's per-token log-probs
+    with torch.no_grad():
+        lp_ref = lo.compute_current_policy_probs(dparams, ocfg, ids[:B].to(cuda), am[:B].to(cuda), P)
+    lp, mask = ln.compute_current_policy_probs(ln.policy, prompts[:B], answers[:B])
+    m = mask.bool()
+    assert (lp[m] - lp_ref[m]).abs().max().item() < 4e-2
+
+
+def test_train_step_updates_like_adam(cuda):
+    """GRPOLearner.train (reference :495-514): after the step, params == Adam(params, our grads) and the
+    bf16 operand copies are refreshed (a second scoring call sees the new adapter)."""
+    ocfg = lo.OracleConfig(vocab=1024, hidden=256, inter=512, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=64,
+                           lora_r=16, lora_alpha=16)
+    params, nf4 = lo.make_params(ocfg, seed=5)
+    P, T, B = 8, 24, 4
+    prompts, answers, rewards = lo.make_batch(ocfg, 4, P, T, seed=9, ragged=True, group_size=4, learner="grpo")
+    ln = _mk_learner("grpo", ocfg, params, nf4, P, T, B, cuda, lr=1e-3)
+    lp0, _ = ln.compute_current_policy_probs(ln.policy, prompts, answers)
+    g, _ = ln._compute_gradients(prompts, answers, list(rewards), export=False)
+    gflat = ln.policy.lora_grad.clone()
+    p0 = ln.policy.lora_flat.clone()
+    cand = [{"answers": [answers], "problem": [prompts], "rewards": [rewards]}]
+    ln.train(cand)
+    refp = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([refp], lr=1e-3, foreach=False, fused=False)
+    refp.grad = gflat
+    opt.step()
+    assert torch.allclose(ln.policy.lora_flat, refp.data, rtol=1e-6, atol=1e-9)
+    lp1, mask = ln.compute_current_policy_probs(ln.policy, prompts, answers)
+    assert (lp1 - lp0)[mask.bool()].abs().max() > 1e-4  # adapter change is visible to the next forward
