@@ -76,7 +76,7 @@ SIGNATURES = {
     "b200rl_model_workspace_bytes": (c_ll, [C.POINTER(ModelConfig)]),
     "b200rl_model_lora_numel": (c_ll, [C.POINTER(ModelConfig)]),
     "b200rl_model_create": (c_int, [C.POINTER(ModelConfig), C.POINTER(LayerWeights), c_void_p, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, c_void_p, c_void_p, c_ll, C.POINTER(c_void_p)]),
+                                    c_void_p, c_void_p, c_void_p, c_ll, C.POINTER(c_void_p)]),
     "b200rl_model_destroy": (c_int, [c_void_p]),
     "b200rl_model_sync_lora": (c_int, [c_void_p, c_void_p]),
     "b200rl_model_debug_ptr": (c_void_p, [c_void_p, C.c_char_p, c_int]),

@@ -9,9 +9,10 @@
 // * Operands are bf16, accumulation fp32 in TMEM, output bf16 or fp32.
 // * The second (A2,B2) segment is the LoRA side path: A2 = s*(X.A^T) (the rank-r intermediate),
 //   B2 = LoRA B, so "base GEMM + LoRA" is one mainloop over K1+K2 with no extra pass over C.
-// * Two layouts: TN (both operands K-major: activations x weights) and the "dW" form where both
-//   operands are MN-major (C[N_out, r] = Y^T . U, reduction over tokens), with optional split-K
-//   into fp32 partial slabs (deterministic: the slabs are summed in fixed order by the caller).
+// * Three operand layouts, selected per operand through the UMMA descriptors (no transposes in HBM):
+//   TN (both K-major: activations x weights^T), "dX" (A K-major, B MN-major: dY . W with W as
+//   stored [out][in]) and "dW" (both MN-major: C[N_out, r] = Y^T . U, reduction over tokens) with
+//   optional split-K into fp32 partial slabs (deterministic: summed in fixed order by the caller).
 //
 // Structure (one CTA per SM, 256 threads):
 //   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
@@ -58,9 +59,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // Instruction descriptor (InstrDescriptor): c_format[4,6)=F32(1), a_format[7,10)=BF16(1),
 // b_format[10,13)=BF16(1), a_major bit15, b_major bit16 (0 = K-major, 1 = MN-major),
 // n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((mn_major ? 1u : 0u) << 15) |
-         ((mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) |
+         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 template <int BN>
@@ -74,7 +75,7 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 };
 
-template <int BN, bool MN_MAJOR>
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -140,14 +141,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         const CUtensorMap* tb = seg2 ? &tmB2 : &tmB1;
         const int k0 = (seg2 ? kb - p.kb1 : kb) * BK;
         mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-        if constexpr (!MN_MAJOR) {
+        // K-major operand: one box of [rows][64 k].  MN-major operand (stored [k][mn]): boxes of
+        // 64 (mn) x 64 (k), one 8 KB slab per 64 mn.
+        if constexpr (!A_MN) {
           tma_load_2d(sa, ta, &full_bar[stage], k0, m_blk * BM);
-          tma_load_2d(sb, tb, &full_bar[stage], k0, n_blk * BN);
         } else {
-          // operand stored [k][mn]: boxes of 64 (mn) x 64 (k); one 8 KB slab per 64 mn
 #pragma unroll
           for (int h = 0; h < BM / 64; ++h)
             tma_load_2d(sa + h * 8192, ta, &full_bar[stage], m_blk * BM + h * 64, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(sb, tb, &full_bar[stage], k0, n_blk * BN);
+        } else {
 #pragma unroll
           for (int h = 0; h < BN / 64; ++h)
             tma_load_2d(sb + h * 8192, tb, &full_bar[stage], n_blk * BN + h * 64, k0);
@@ -160,7 +165,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(BN, MN_MAJOR);
+    constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
@@ -181,17 +186,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          uint64_t da, db;
-          if constexpr (!MN_MAJOR) {
-            // K-major, rows of 128 B, 8-row swizzle atoms 1024 B apart; +32 B per K=16 step
-            da = make_smem_desc(sa + k * 32, 16, 1024);
-            db = make_smem_desc(sb + k * 32, 16, 1024);
-          } else {
-            // MN-major: 64(mn) x 8(k) atoms of 1024 B; next 64 mn at +8192 (LBO),
-            // next 8 k at +1024 (SBO); K=16 step = two k-groups = +2048 B
-            da = make_smem_desc(sa + k * 2048, 8192, 1024);
-            db = make_smem_desc(sb + k * 2048, 8192, 1024);
-          }
+          // K-major: rows of 128 B, 8-row swizzle atoms 1024 B apart; +32 B per K=16 step.
+          // MN-major: 64(mn) x 8(k) atoms of 1024 B; next 64 mn at +8192 (LBO), next 8 k at +1024
+          // (SBO); K=16 step = two k-groups = +2048 B.
+          const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024)
+                                   : make_smem_desc(sa + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
+                                   : make_smem_desc(sb + k * 32, 16, 1024);
           umma_bf16(tmem_d, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
@@ -326,14 +327,14 @@ struct GemmArgs {
   long long ldr;
   float alpha;
   int M, N;
-  int mn_major;   // 0: TN (K-major operands). 1: operands stored [K][M] / [K][N]
+  int mn_major;   // bit0: A stored [K][M] (MN-major), bit1: B stored [K][N]. 0 = TN, 3 = dW form, 2 = dX form
   int splits;     // split-K factor (fp32 output slabs, c_split_stride apart)
   long long c_split_stride;
   int force_bn;   // 0 = heuristic
   int max_ctas;   // 0 = all SMs
 };
 
-template <int BN, bool MN>
+template <int BN, bool A_MN, bool B_MN>
 static int launch(const GemmArgs& a, cudaStream_t stream) {
   using C = Cfg<BN>;
   GemmParams p;
@@ -358,29 +359,17 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
 
   CUtensorMap tA1, tB1, tA2, tB2;
   int rc;
-  if (!MN) {
-    if ((rc = make_map(&tA1, a.A1, a.K1, a.M, a.lda1, BK, BM))) return rc;
-    if ((rc = make_map(&tB1, a.B1, a.K1, a.N, a.ldb1, BK, BN))) return rc;
-    if (a.K2 > 0) {
-      if ((rc = make_map(&tA2, a.A2, a.K2, a.M, a.lda2, BK, BM))) return rc;
-      if ((rc = make_map(&tB2, a.B2, a.K2, a.N, a.ldb2, BK, BN))) return rc;
-    } else {
-      tA2 = tA1;
-      tB2 = tB1;
-    }
+  // K-major: X[rows][K] -> dims {K, rows}, box {64, tile rows}.  MN-major: X[K][mn] -> dims {mn, K}, box {64, 64}.
+  if ((rc = A_MN ? make_map(&tA1, a.A1, a.M, a.K1, a.lda1, 64, BK) : make_map(&tA1, a.A1, a.K1, a.M, a.lda1, BK, BM))) return rc;
+  if ((rc = B_MN ? make_map(&tB1, a.B1, a.N, a.K1, a.ldb1, 64, BK) : make_map(&tB1, a.B1, a.K1, a.N, a.ldb1, BK, BN))) return rc;
+  if (a.K2 > 0) {
+    if ((rc = A_MN ? make_map(&tA2, a.A2, a.M, a.K2, a.lda2, 64, BK) : make_map(&tA2, a.A2, a.K2, a.M, a.lda2, BK, BM))) return rc;
+    if ((rc = B_MN ? make_map(&tB2, a.B2, a.N, a.K2, a.ldb2, 64, BK) : make_map(&tB2, a.B2, a.K2, a.N, a.ldb2, BK, BN))) return rc;
   } else {
-    // stored [K][M] and [K][N]
-    if ((rc = make_map(&tA1, a.A1, a.M, a.K1, a.lda1, 64, BK))) return rc;
-    if ((rc = make_map(&tB1, a.B1, a.N, a.K1, a.ldb1, 64, BK))) return rc;
-    if (a.K2 > 0) {
-      if ((rc = make_map(&tA2, a.A2, a.M, a.K2, a.lda2, 64, BK))) return rc;
-      if ((rc = make_map(&tB2, a.B2, a.N, a.K2, a.ldb2, 64, BK))) return rc;
-    } else {
-      tA2 = tA1;
-      tB2 = tB1;
-    }
+    tA2 = tA1;
+    tB2 = tB1;
   }
-  auto kern = gemm_kernel<BN, MN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -411,11 +400,13 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
   if (a.bias)
     B200RL_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15u) == 0, "gemm: bias must be 16-byte aligned");
   int bn = a.force_bn;
-  if (a.mn_major) {
+  const bool a_mn = (a.mn_major & 1) != 0, b_mn = (a.mn_major & 2) != 0;
+  if (a_mn) {
+    B200RL_REQUIRE(b_mn, "gemm: A MN-major with B K-major is not instantiated");
     B200RL_REQUIRE(a.M % 8 == 0, "gemm(dW form): M must be a multiple of 8");
     if (bn == 0) bn = a.N <= 64 ? 64 : 128;
-    if (bn == 64) return launch<64, true>(a, stream);
-    if (bn == 128) return launch<128, true>(a, stream);
+    if (bn == 64) return launch<64, true, true>(a, stream);
+    if (bn == 128) return launch<128, true, true>(a, stream);
     return set_error(B200RL_ERR_UNSUPPORTED, "gemm(dW form): BN=%d not instantiated", bn);
   }
   if (bn == 0) {
@@ -441,11 +432,20 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
       }
     }
   }
+  if (b_mn) {
+    switch (bn) {
+      case 64: return launch<64, false, true>(a, stream);
+      case 128: return launch<128, false, true>(a, stream);
+      case 192: return launch<192, false, true>(a, stream);
+      case 256: return launch<256, false, true>(a, stream);
+      default: return set_error(B200RL_ERR_UNSUPPORTED, "gemm: BN=%d not instantiated", bn);
+    }
+  }
   switch (bn) {
-    case 64: return launch<64, false>(a, stream);
-    case 128: return launch<128, false>(a, stream);
-    case 192: return launch<192, false>(a, stream);
-    case 256: return launch<256, false>(a, stream);
+    case 64: return launch<64, false, false>(a, stream);
+    case 128: return launch<128, false, false>(a, stream);
+    case 192: return launch<192, false, false>(a, stream);
+    case 256: return launch<256, false, false>(a, stream);
     default: return set_error(B200RL_ERR_UNSUPPORTED, "gemm: BN=%d not instantiated", bn);
   }
 }

@@ -15,7 +15,8 @@
 // LoRA math per projection: y = x W^T + s (x A^T) B^T, s = alpha/r.  Fused groups (qkv, o, gate|up,
 // down) use block-structured operand copies so one GEMM mainloop covers base + LoRA:
 //   Acat [K2, Kin] (A_j stacked, zero padded to K2 = roundup(nproj*r, 64)),  Bcat [Nout, K2]
-//   (block diagonal), and their transposes for the backward GEMMs.
+//   (block diagonal).  Backward GEMMs read W / Acat / Bcat as stored through MN-major UMMA descriptors
+//   (no transposed copies, no transposed dequant).
 #include "common.cuh"
 #include "b200rl.h"
 #include <vector>
@@ -122,7 +123,7 @@ struct Group {
   int Kin, Nout, nproj, K2;
   int out_dims[3];       // per projection output rows
   // offsets (elements) into the bf16 LoRA operand arena of the layer
-  long long acat, acat_t, bcat, bcat_t;
+  long long acat, bcat;
   // flat fp32 offsets of A_j / B_j
   long long a_off[3], b_off[3];
 };
@@ -132,7 +133,7 @@ struct Group {
 struct b200rl_model {
   b200rl_model_config cfg;
   std::vector<b200rl_layer_weights> layers;
-  const bf16 *embed, *final_norm, *lm_head, *lm_head_t;
+  const bf16 *embed, *final_norm, *lm_head;
   float *lora_flat, *lora_grad;
   long long lora_numel;
   int QKV, QD;  // qkv row width, q width
@@ -207,9 +208,7 @@ static void build_groups(b200rl_model* m) {
         flat += (long long)outs[j] * r;
       }
       g.acat = arena;   arena += (long long)g.K2 * Kin;
-      g.acat_t = arena; arena += (long long)Kin * g.K2;
       g.bcat = arena;   arena += (long long)g.Nout * g.K2;
-      g.bcat_t = arena; arena += (long long)g.K2 * g.Nout;
       arena = align_up(arena, 64);
       m->groups.push_back(g);
     };
@@ -340,11 +339,11 @@ extern "C" long long b200rl_model_workspace_bytes(const b200rl_model_config* cfg
 
 extern "C" int b200rl_model_create(const b200rl_model_config* cfg, const b200rl_layer_weights* layers_host,
                                    const void* embed, const void* final_norm_w, const void* lm_head,
-                                   const void* lm_head_t, float* lora_flat, float* lora_grad_flat,
+                                   float* lora_flat, float* lora_grad_flat,
                                    void* workspace, long long workspace_bytes, b200rl_model** out) {
   int rc = validate_cfg(cfg);
   if (rc) return rc;
-  B200RL_REQUIRE(layers_host && embed && final_norm_w && lm_head && lm_head_t && lora_flat &&
+  B200RL_REQUIRE(layers_host && embed && final_norm_w && lm_head && lora_flat &&
                      lora_grad_flat && workspace && out, "model_create: null pointer");
   b200rl_model* m = new (std::nothrow) b200rl_model();
   B200RL_REQUIRE(m != nullptr, "model_create: out of host memory");
@@ -353,7 +352,6 @@ extern "C" int b200rl_model_create(const b200rl_model_config* cfg, const b200rl_
   m->embed = (const bf16*)embed;
   m->final_norm = (const bf16*)final_norm_w;
   m->lm_head = (const bf16*)lm_head;
-  m->lm_head_t = (const bf16*)lm_head_t;
   m->lora_flat = lora_flat;
   m->lora_grad = lora_grad_flat;
   build_groups(m);
@@ -431,12 +429,10 @@ extern "C" int b200rl_model_create(const b200rl_model_config* cfg, const b200rl_
       const Group& g = m->groups[l * 4 + gi];
       int row_off = 0;
       for (int j = 0; j < g.nproj; ++j) {
-        // A_j [r, Kin] -> Acat rows j*r.. (ld Kin) ; AcatT cols j*r.. (ld K2, transposed)
+        // A_j [r, Kin] -> Acat rows j*r.. (ld Kin)
         descs.push_back({g.a_off[j], r, g.Kin, base + g.acat + (long long)j * r * g.Kin, g.Kin, 0});
-        descs.push_back({g.a_off[j], r, g.Kin, base + g.acat_t + (long long)j * r, g.K2, 1});
-        // B_j [out_j, r] -> Bcat rows row_off.., cols j*r.. (ld K2) ; BcatT rows j*r.., cols row_off.. (ld Nout)
+        // B_j [out_j, r] -> Bcat rows row_off.., cols j*r.. (ld K2)
         descs.push_back({g.b_off[j], g.out_dims[j], r, base + g.bcat + (long long)row_off * g.K2 + j * r, g.K2, 0});
-        descs.push_back({g.b_off[j], g.out_dims[j], r, base + g.bcat_t + (long long)j * r * g.Nout + row_off, g.Nout, 1});
         max_elems = std::max(max_elems, std::max(r * g.Kin, g.out_dims[j] * r));
         row_off += g.out_dims[j];
       }
@@ -495,7 +491,7 @@ extern "C" void* b200rl_model_debug_ptr(b200rl_model* m, const char* name, int l
 
 namespace {
 
-int gemm_tn(b200rl_model* m, int cat, cudaStream_t st, const bf16* A1, long long lda1, const bf16* B1, long long ldb1, int K1,
+int gemm_l(b200rl_model* m, int cat, int layout, cudaStream_t st, const bf16* A1, long long lda1, const bf16* B1, long long ldb1, int K1,
             const bf16* A2, long long lda2, const bf16* B2, long long ldb2, int K2, bf16* C,
             long long ldc, const bf16* bias, const bf16* residual, long long ldr, float alpha, int M,
             int N) {
@@ -504,7 +500,7 @@ int gemm_tn(b200rl_model* m, int cat, cudaStream_t st, const bf16* A1, long long
   a.lda1 = lda1; a.ldb1 = ldb1; a.lda2 = lda2; a.ldb2 = ldb2;
   a.K1 = K1; a.K2 = K2; a.C = C; a.ldc = ldc; a.c_fp32 = 0;
   a.bias = bias; a.residual = residual; a.ldr = ldr; a.alpha = alpha;
-  a.M = M; a.N = N; a.mn_major = 0; a.splits = 1; a.c_split_stride = 0;
+  a.M = M; a.N = N; a.mn_major = layout; a.splits = 1; a.c_split_stride = 0;
   a.force_bn = 0; a.max_ctas = 0;
   PM(cat, 2.0 * M * N * K1 + (K2 ? 2.0 * M * N * m->cfg.lora_r : 0.0));
   return gemm_dispatch(a, st);
@@ -527,7 +523,7 @@ int lora_dw(b200rl_model* m, cudaStream_t st, const Group& g, const bf16* dY, lo
     memset(&a, 0, sizeof(a));
     a.A1 = Y; a.lda1 = ldy; a.B1 = U; a.ldb1 = g.K2; a.K1 = M; a.K2 = 0;
     a.C = m->slabs; a.ldc = g.K2; a.c_fp32 = 1; a.alpha = 1.f;
-    a.M = Ny; a.N = g.K2; a.mn_major = 1; a.splits = splits; a.c_split_stride = stride;
+    a.M = Ny; a.N = g.K2; a.mn_major = 3; a.splits = splits; a.c_split_stride = stride;
     PM(CAT_GEMM_DW, 2.0 * M * Ny * m->cfg.lora_r * g.nproj);
     RC(gemm_dispatch(a, st));
     PM(CAT_MISC, 0);
@@ -599,33 +595,33 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
     bf16* xn = m->X + (long long)(l + 1) * Mt * H;
     PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(x, w.ln1_w, a.h1, a.rstd1, M, H, c.rms_eps, stream));
-    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
     PM(CAT_DEQUANT, 2.5625 * (QKV) * (H));
     RC(b200rl_nf4_dequant(w.qkv_packed, w.qkv_absmax, m->wbuf, QKV, H, 0, stream));
-    RC(gemm_tn(m, CAT_GEMM, st, a.h1, H, m->wbuf, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, gq.K2, a.qkv, QKV,
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.h1, H, m->wbuf, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, gq.K2, a.qkv, QKV,
                (const bf16*)w.qkv_bias, nullptr, 0, 1.f, M, QKV));
     PM(CAT_ROW, 2.0 * M * (c.n_q_heads + c.n_kv_heads) * c.head_dim * 2);
     RC(b200rl_rope(a.qkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 0, stream));
     PM(CAT_ATTN_FWD, 2.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
     RC(b200rl_attn_fwd(a.qkv, attn_mask, a.attn_o, a.lse, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
-    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
     PM(CAT_DEQUANT, 2.5625 * (H) * (QD));
     RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 0, stream));
-    RC(gemm_tn(m, CAT_GEMM, st, a.attn_o, QD, m->wbuf, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, go.K2, a.x_mid, H,
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.attn_o, QD, m->wbuf, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, go.K2, a.x_mid, H,
                nullptr, x, H, 1.f, M, H));
     PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(a.x_mid, w.ln2_w, a.h2, a.rstd2, M, H, c.rms_eps, stream));
-    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
     PM(CAT_DEQUANT, 2.5625 * (2 * I) * (H));
     RC(b200rl_nf4_dequant(w.gu_packed, w.gu_absmax, m->wbuf, 2 * I, H, 0, stream));
-    RC(gemm_tn(m, CAT_GEMM, st, a.h2, H, m->wbuf, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, gg.K2, a.gu, 2 * I,
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, m->wbuf, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, gg.K2, a.gu, 2 * I,
                nullptr, nullptr, 0, 1.f, M, 2 * I));
     PM(CAT_ROW, 3.0 * M * I * 2);
     RC(b200rl_swiglu_fwd(a.gu, a.act, M, I, stream));
-    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
     PM(CAT_DEQUANT, 2.5625 * (H) * (I));
     RC(b200rl_nf4_dequant(w.down_packed, w.down_absmax, m->wbuf, H, I, 0, stream));
-    RC(gemm_tn(m, CAT_GEMM, st, a.act, I, m->wbuf, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, gd.K2, xn, H, nullptr,
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.act, I, m->wbuf, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, gd.K2, xn, H, nullptr,
                a.x_mid, H, 1.f, M, H));
   }
   // head: only the T scored positions (rows P-1 .. L-2) go through the final norm and lm_head
@@ -634,7 +630,7 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
   RC(b200rl_gather_rows(xf, m->xsel, B, L, T, P - 1, H, stream));
   PM(CAT_ROW, 2.0 * R * H * 2);
   RC(b200rl_rmsnorm_fwd(m->xsel, m->final_norm, m->hsel, m->rstd_f, R, H, c.rms_eps, stream));
-  RC(gemm_tn(m, CAT_GEMM, st, m->hsel, H, m->lm_head, H, H, nullptr, 0, nullptr, 0, 0, m->logits, V, nullptr, nullptr, 0, 1.f, R, V));
+  RC(gemm_l(m, CAT_GEMM, 0, st, m->hsel, H, m->lm_head, H, H, nullptr, 0, nullptr, 0, 0, m->logits, V, nullptr, nullptr, 0, 1.f, R, V));
   PM(CAT_MISC, 0);
   targets_kernel<<<(R + 255) / 256, 256, 0, st>>>(ids, m->targets, L, P, T, R);
   B200RL_LAUNCH_OK();
@@ -651,7 +647,7 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
   }
 
   // ---------------- backward ----------------
-  RC(gemm_tn(m, CAT_GEMM, st, m->logits, V, m->lm_head_t, V, V, nullptr, 0, nullptr, 0, 0, m->dhsel, H, nullptr, nullptr, 0, 1.f, R, H));
+  RC(gemm_l(m, CAT_GEMM, 2, st, m->logits, V, m->lm_head, H, V, nullptr, 0, nullptr, 0, 0, m->dhsel, H, nullptr, nullptr, 0, 1.f, R, H));
   PM(CAT_ROW, 3.0 * R * H * 2);
   RC(b200rl_rmsnorm_bwd(m->dhsel, m->xsel, m->final_norm, m->rstd_f, nullptr, m->dhsel, R, H, stream));
   PM(CAT_ROW, 1.0 * (R + M) * H * 2);
@@ -665,40 +661,41 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
     const Group& gg = m->groups[l * 4 + 2];
     const Group& gd = m->groups[l * 4 + 3];
     bf16* x = m->X + (long long)l * Mt * H;
-    // ---- down projection
-    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, m->dx, H, ar + gd.bcat_t, H, H, nullptr, 0, nullptr, 0, 0, m->du, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    // Backward GEMMs read W (and the LoRA operands) exactly as stored: B operand MN-major (layout 2).
+    // ---- down projection:  X[l+1] = x_mid + act.Wd^T + u_d.Bd^T
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + gd.bcat, gd.K2, H, nullptr, 0, nullptr, 0, 0, m->du, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
     RC(lora_dw(m, st, gd, m->dx, H, a.u_d, a.act, I, m->du, M));
     PM(CAT_DEQUANT, 2.5625 * (H) * (I));
-    RC(b200rl_nf4_dequant(w.down_packed, w.down_absmax, m->wbuf, H, I, 1, stream));  // Wd^T [I, H]
-    RC(gemm_tn(m, CAT_GEMM, st, m->dx, H, m->wbuf, H, H, m->du, gd.K2, ar + gd.acat_t, gd.K2, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
+    RC(b200rl_nf4_dequant(w.down_packed, w.down_absmax, m->wbuf, H, I, 0, stream));
+    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, m->wbuf, I, H, m->du, gd.K2, ar + gd.acat, I, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
     PM(CAT_ROW, 5.0 * M * I * 2);
     RC(b200rl_swiglu_bwd(a.gu, m->dact, m->dgu, M, I, stream));
-    // ---- gate|up
-    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, m->dgu, 2 * I, ar + gg.bcat_t, 2 * I, 2 * I, nullptr, 0, nullptr, 0, 0, m->du, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    // ---- gate|up:  gu = h2.Wgu^T + u_gu.Bgu^T
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dgu, 2 * I, ar + gg.bcat, gg.K2, 2 * I, nullptr, 0, nullptr, 0, 0, m->du, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
     RC(lora_dw(m, st, gg, m->dgu, 2 * I, a.u_gu, a.h2, H, m->du, M));
     PM(CAT_DEQUANT, 2.5625 * (2 * I) * (H));
-    RC(b200rl_nf4_dequant(w.gu_packed, w.gu_absmax, m->wbuf, 2 * I, H, 1, stream));  // Wgu^T [H, 2I]
-    RC(gemm_tn(m, CAT_GEMM, st, m->dgu, 2 * I, m->wbuf, 2 * I, 2 * I, m->du, gg.K2, ar + gg.acat_t, gg.K2, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+    RC(b200rl_nf4_dequant(w.gu_packed, w.gu_absmax, m->wbuf, 2 * I, H, 0, stream));
+    RC(gemm_l(m, CAT_GEMM, 2, st, m->dgu, 2 * I, m->wbuf, H, 2 * I, m->du, gg.K2, ar + gg.acat, H, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
     PM(CAT_ROW, 4.0 * M * H * 2);
     RC(b200rl_rmsnorm_bwd(m->dh, a.x_mid, w.ln2_w, a.rstd2, m->dx, m->dx, M, H, stream));
-    // ---- o projection
-    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, m->dx, H, ar + go.bcat_t, H, H, nullptr, 0, nullptr, 0, 0, m->du, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    // ---- o projection:  x_mid = x + attn_o.Wo^T + u_o.Bo^T
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + go.bcat, go.K2, H, nullptr, 0, nullptr, 0, 0, m->du, go.K2, nullptr, nullptr, 0, s, M, go.K2));
     RC(lora_dw(m, st, go, m->dx, H, a.u_o, a.attn_o, QD, m->du, M));
     PM(CAT_DEQUANT, 2.5625 * (H) * (QD));
-    RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 1, stream));  // Wo^T [QD, H]
-    RC(gemm_tn(m, CAT_GEMM, st, m->dx, H, m->wbuf, H, H, m->du, go.K2, ar + go.acat_t, go.K2, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
+    RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 0, stream));
+    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, m->wbuf, QD, H, m->du, go.K2, ar + go.acat, QD, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
     // ---- attention + rope
     PM(CAT_ATTN_BWD, 4.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
     RC(b200rl_attn_bwd(a.qkv, attn_mask, a.attn_o, m->dattn, a.lse, m->delta, m->dqkv, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
     PM(CAT_ROW, 2.0 * M * (c.n_q_heads + c.n_kv_heads) * c.head_dim * 2);
     RC(b200rl_rope(m->dqkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 1, stream));
-    // ---- qkv projection
-    RC(gemm_tn(m, CAT_GEMM_SKINNY, st, m->dqkv, QKV, ar + gq.bcat_t, QKV, QKV, nullptr, 0, nullptr, 0, 0, m->du, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    // ---- qkv projection:  qkv = h1.Wqkv^T + u_qkv.Bqkv^T + bias
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dqkv, QKV, ar + gq.bcat, gq.K2, QKV, nullptr, 0, nullptr, 0, 0, m->du, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
     RC(lora_dw(m, st, gq, m->dqkv, QKV, a.u_qkv, a.h1, H, m->du, M));
     if (l > 0) {  // embeddings are frozen: layer 0 needs no input gradient
       PM(CAT_DEQUANT, 2.5625 * (QKV) * (H));
-      RC(b200rl_nf4_dequant(w.qkv_packed, w.qkv_absmax, m->wbuf, QKV, H, 1, stream));  // Wqkv^T [H, QKV]
-      RC(gemm_tn(m, CAT_GEMM, st, m->dqkv, QKV, m->wbuf, QKV, QKV, m->du, gq.K2, ar + gq.acat_t, gq.K2, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+      RC(b200rl_nf4_dequant(w.qkv_packed, w.qkv_absmax, m->wbuf, QKV, H, 0, stream));
+      RC(gemm_l(m, CAT_GEMM, 2, st, m->dqkv, QKV, m->wbuf, H, QKV, m->du, gq.K2, ar + gq.acat, H, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
       PM(CAT_ROW, 4.0 * M * H * 2);
       RC(b200rl_rmsnorm_bwd(m->dh, x, w.ln1_w, a.rstd1, m->dx, m->dx, M, H, stream));
     }

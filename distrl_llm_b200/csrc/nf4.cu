@@ -53,22 +53,41 @@ __global__ void nf4_quant_kernel(const bf16* __restrict__ w, uint8_t* __restrict
   packed[blk * 32 + lane] = (uint8_t)((hi << 4) | lo);
 }
 
-// row-major dequant: out[i] = bf16(code * absmax); each thread expands 4 bytes -> 8 values
-__global__ void nf4_dequant_kernel(const uint8_t* __restrict__ packed,
-                                   const float* __restrict__ absmax, bf16* __restrict__ out,
-                                   long long n8) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  const uint32_t q = reinterpret_cast<const uint32_t*>(packed)[i];
-  const float am = absmax[i >> 3];  // 8 values per thread, 64 per block
-  float f[8];
+// row-major dequant: out[i] = bf16(code * absmax).  Each thread expands 4 packed bytes -> 8 values
+// (one 16-byte store); consecutive lanes take consecutive words, so a warp reads 128 B and writes
+// 512 B contiguously.  The 16-entry level table is expanded to a 256-entry byte -> (hi, lo) table
+// in shared memory: a __constant__ lookup with a per-lane index serialises up to 16-way.
+__global__ void __launch_bounds__(256)
+nf4_dequant_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ absmax,
+                   bf16* __restrict__ out, long long n8) {
+  __shared__ float2 lut[256];
+  lut[threadIdx.x] = make_float2(c_nf4[threadIdx.x >> 4], c_nf4[threadIdx.x & 15]);
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += stride * U) {
+    uint32_t q[U];
+    float am[U];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const uint32_t byte = (q >> (8 * b)) & 0xFFu;
-    f[2 * b] = c_nf4[byte >> 4] * am;
-    f[2 * b + 1] = c_nf4[byte & 15u] * am;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      q[u] = i < n8 ? __ldg(reinterpret_cast<const uint32_t*>(packed) + i) : 0u;
+      am[u] = i < n8 ? __ldg(absmax + (i >> 3)) : 0.f;  // 8 values per word, 64 per block
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n8) {
+        bf16x8 o;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float2 v = lut[(q[u] >> (8 * b)) & 0xFFu];
+          o.v[b] = __floats2bfloat162_rn(v.x * am[u], v.y * am[u]);
+        }
+        reinterpret_cast<bf16x8*>(out)[i] = o;
+      }
+    }
   }
-  reinterpret_cast<bf16x8*>(out)[i] = pack8(f);
 }
 
 // transposed dequant: W is [rows, cols] row-major (cols % 64 == 0), out = W^T [cols, rows].
@@ -137,8 +156,11 @@ extern "C" int b200rl_nf4_dequant(const void* packed, const float* absmax, void*
                  "nf4_dequant: cols must be a multiple of 64 (rows=%d cols=%d)", rows, cols);
   if (!transpose) {
     const long long n8 = (long long)rows * cols / 8;
-    nf4_dequant_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, STREAM>>>(
-        (const uint8_t*)packed, absmax, (bf16*)out_bf16, n8);
+    long long blocks = (n8 + 256 * 4 - 1) / (256 * 4);
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    nf4_dequant_kernel<<<(unsigned)blocks, 256, 0, STREAM>>>((const uint8_t*)packed, absmax,
+                                                                (bf16*)out_bf16, n8);
   } else {
     B200RL_REQUIRE(rows % 8 == 0, "nf4_dequant(transpose): rows must be a multiple of 8");
     dim3 grid(cols / 64, (rows + 63) / 64);

@@ -15,15 +15,16 @@ BF16 = torch.bfloat16
 
 
 def gemm(a1, b1, a2=None, b2=None, *, bias=None, residual=None, alpha=1.0, out=None,
-         out_fp32=False, force_bn=0, max_ctas=0):
-    """C[M,N] = alpha*(a1 @ b1.T + a2 @ b2.T) + bias + residual ; a*: [M,K*], b*: [N,K*] (bf16)."""
+         out_fp32=False, force_bn=0, max_ctas=0, b_mn=False):
+    """C[M,N] = alpha*(a1 @ b1.T + a2 @ b2.T) + bias + residual ; a*: [M,K*], b*: [N,K*] (bf16).
+    b_mn=True: the B operands are stored [K*, N] (C = a1 @ b1 + a2 @ b2), read through MN-major descriptors."""
     M, K1 = a1.shape
-    N = b1.shape[0]
-    assert b1.shape[1] == K1 and a1.dtype == BF16 and b1.dtype == BF16
+    N = b1.shape[1] if b_mn else b1.shape[0]
+    assert (b1.shape[0] if b_mn else b1.shape[1]) == K1 and a1.dtype == BF16 and b1.dtype == BF16
     K2 = 0
     if a2 is not None:
         K2 = a2.shape[1]
-        assert a2.shape[0] == M and b2.shape == (N, K2)
+        assert a2.shape[0] == M and b2.shape == ((K2, N) if b_mn else (N, K2))
     if out is None:
         out = torch.empty(M, N, device=a1.device, dtype=torch.float32 if out_fp32 else BF16)
     check(lib().b200rl_gemm(
@@ -31,7 +32,7 @@ def gemm(a1, b1, a2=None, b2=None, *, bias=None, residual=None, alpha=1.0, out=N
         ptr(a2), a2.stride(0) if a2 is not None else 0, ptr(b2), b2.stride(0) if b2 is not None else 0, K2,
         ptr(out), out.stride(0), 1 if out.dtype == torch.float32 else 0,
         ptr(bias), ptr(residual), residual.stride(0) if residual is not None else 0,
-        float(alpha), M, N, 0, 1, 0, force_bn, max_ctas, stream()), "gemm")
+        float(alpha), M, N, 2 if b_mn else 0, 1, 0, force_bn, max_ctas, stream()), "gemm")
     return out
 
 
@@ -48,7 +49,7 @@ def gemm_dw(y, u, *, splits=1, force_bn=0):
     out = torch.empty(splits, Ny, Nu, device=y.device, dtype=torch.float32)
     check(lib().b200rl_gemm(
         ptr(y), y.stride(0), ptr(u), u.stride(0), Kt, None, 0, None, 0, 0,
-        ptr(out), Nu, 1, None, None, 0, 1.0, Ny, Nu, 1, splits, Ny * Nu, force_bn, 0, stream()), "gemm_dw")
+        ptr(out), Nu, 1, None, None, 0, 1.0, Ny, Nu, 3, splits, Ny * Nu, force_bn, 0, stream()), "gemm_dw")
     return out
 
 

@@ -94,7 +94,7 @@ class Policy:
         self.adam_v = torch.zeros(n, **f32)
         self.opt_step = 0
         self.layers = []      # per layer dict of device tensors
-        self.embed = self.final_norm = self.lm_head = self.lm_head_t = None
+        self.embed = self.final_norm = self.lm_head = None
         self.handle = None
         self.workspace = None
         self.loss_accum = torch.zeros(1, device=self.device, dtype=torch.float64)
@@ -125,7 +125,7 @@ class Policy:
         aligned = (base + 1023) // 1024 * 1024
         h = C.c_void_p()
         check(lib().b200rl_model_create(C.byref(self.ccfg), wl, ptr(self.embed), ptr(self.final_norm),
-                                        ptr(self.lm_head), ptr(self.lm_head_t), ptr(self.lora_flat),
+                                        ptr(self.lm_head), ptr(self.lora_flat),
                                         ptr(self.lora_grad), aligned, int(nbytes), C.byref(h)), "model_create")
         self.handle = h
         self.sync_lora()
@@ -157,7 +157,6 @@ class Policy:
         H, I = cfg.hidden, cfg.inter
         self.embed = rnd(cfg.vocab, H)
         self.lm_head = rnd(cfg.vocab, H)
-        self.lm_head_t = self.lm_head.t().contiguous()
         self.final_norm = torch.ones(H, **bf)
         for _ in range(cfg.n_layers):
             L = {}
@@ -202,7 +201,6 @@ class Policy:
 
         self.embed = bf(params["embed"])
         self.lm_head = bf(params["lm_head"])
-        self.lm_head_t = self.lm_head.t().contiguous()
         self.final_norm = bf(params["final_norm"])
         for i in range(cfg.n_layers):
             L = {}

@@ -31,9 +31,10 @@ int b200rl_check_device(void); /* 0 iff the current device is sm_100 */
 /* ---- G1/G6: tcgen05 GEMM (reference: every nn.Linear / LoRA matmul inside policy(...),
  *      distributed_actor.py:241-243, and their backward, :385 / :483) --------------------------
  * C[M,N] = alpha*(A1[M,K1].B1[N,K1]^T + A2[M,K2].B2[N,K2]^T) (+bias[N]) (+residual[M,N]).
- * mn_major=0: operands K-major (row-major [rows][K]).  mn_major=1 ("dW form"): operands stored
- * [K][M] and [K][N] (C = A^T.B, reduction over the leading index); splits>1 writes fp32 partial
- * slabs c_split_stride elements apart.  force_bn / max_ctas = 0 for the defaults. */
+ * mn_major bit0: A stored [K][M]; bit1: B stored [K][N] (read through MN-major UMMA descriptors, no
+ * transposes in HBM).  0 = TN (x . W^T), 2 = "dX form" (dY . W, W as stored), 3 = "dW form" (Y^T . U,
+ * reduction over tokens); splits>1 writes fp32 partial slabs c_split_stride elements apart.
+ * force_bn / max_ctas = 0 for the defaults. */
 int b200rl_gemm(const void* A1, long long lda1, const void* B1, long long ldb1, int K1,
                 const void* A2, long long lda2, const void* B2, long long ldb2, int K2, void* C,
                 long long ldc, int c_fp32, const void* bias, const void* residual, long long ldr,
@@ -132,7 +133,7 @@ long long b200rl_model_workspace_bytes(const b200rl_model_config* cfg);
 long long b200rl_model_lora_numel(const b200rl_model_config* cfg);
 int b200rl_model_create(const b200rl_model_config* cfg, const b200rl_layer_weights* layers_host,
                         const void* embed, const void* final_norm_w, const void* lm_head,
-                        const void* lm_head_t, float* lora_flat, float* lora_grad_flat,
+                        float* lora_flat, float* lora_grad_flat,
                         void* workspace, long long workspace_bytes, b200rl_model** out);
 int b200rl_model_destroy(b200rl_model* m);
 /* refresh the bf16 operand copies of the LoRA tensors after an optimizer step */

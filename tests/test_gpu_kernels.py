@@ -76,6 +76,23 @@ def test_gemm_epilogues(cuda):
     assert _rel_err(res2, a.float() @ b.float().T + res.float()) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K1,K2,bn", [(128, 64, 64, 0, 0), (300, 200, 192, 0, 0), (1000, 512, 1024, 64, 0),
+                                           (640, 3584, 4608, 64, 256), (4100, 1024, 2048, 64, 192),
+                                           (512, 384, 256, 128, 128), (6896, 3584, 1024, 64, 0)])
+def test_gemm_dx_form(cuda, M, N, K1, K2, bn):
+    """dX form: C = A1 @ B1 + A2 @ B2 with the B operands stored [K, N] (weights as stored [out, in])."""
+    from distrl_llm_b200 import ops
+    a1 = _rand((M, K1), cuda, seed=1)
+    b1 = _rand((K1, N), cuda, seed=2)
+    a2 = _rand((M, K2), cuda, seed=3) if K2 else None
+    b2 = _rand((K2, N), cuda, seed=4) if K2 else None
+    out = ops.gemm(a1, b1, a2, b2, force_bn=bn, b_mn=True)
+    ref = a1.float() @ b1.float()
+    if K2:
+        ref = ref + a2.float() @ b2.float()
+    assert _rel_err(out, ref) < 4e-3
+
+
 @pytest.mark.parametrize("tokens,Ny,Nu,splits", [
     (64, 128, 64, 1), (512, 256, 64, 1), (1000, 384, 64, 4), (6896, 512, 64, 8), (2048, 1024, 128, 3),
     (200, 136, 64, 2),
