@@ -285,6 +285,7 @@ def main():
     for _ in range(2):
         e2e_step()
     ms_e2e, _, _ = timed(e2e_step, args.steps)
+    ms_dev2, _, _ = timed(device_step, args.steps)   # diagnostic: same region without the nvidia-smi sampler
 
     # per-category CUDA-event profile of ONE extra step (same stream; events between consecutive launches)
     import ctypes as C
@@ -329,7 +330,7 @@ def main():
                 "dtype": "bf16", "data": "synthetic", "config": config_dict(args),
                 "e2e": {"value": e2e_val, "unit": "completion tokens/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "ms_per_step_no_sampler": ms_dev2, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "profile_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
                 "profile_launches": {k: int(v["launches"]) for k, v in prof.items()}}
         print(json.dumps(line), flush=True)

@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200rl_gemm": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int,
                             c_void_p, c_ll, c_int, c_void_p, c_void_p, c_ll, c_float, c_int, c_int,
                             c_int, c_int, c_ll, c_int, c_int, c_void_p]),
+    "b200rl_gemm_set_cta_pair": (c_int, [c_int]),
     "b200rl_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200rl_rmsnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "b200rl_rmsnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

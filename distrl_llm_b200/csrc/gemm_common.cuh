@@ -1,0 +1,150 @@
+// Shared pieces of the tcgen05 GEMM kernels (single-CTA and CTA-pair variants): tile constants,
+// kernel parameters, UMMA descriptors, tensor-map construction, host argument block.
+#pragma once
+#include "common.cuh"
+
+namespace b200rl {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;           // 64 bf16 = 128 B = one 128B-swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+
+struct GemmParams {
+  int M, N;
+  int kb1, kb2;          // k-blocks (of 64) in segment 1 / 2
+  int num_m_blocks, num_n_blocks, splits, kb_per_split;
+  void* C;
+  long long ldc;
+  long long c_split_stride;  // elements between split-K slabs
+  int c_fp32;
+  const bf16* bias;
+  const bf16* residual;
+  long long ldr;
+  float alpha;
+};
+
+// ---- descriptors ---------------------------------------------------------------------------
+// Shared-memory matrix descriptor (tcgen05), 128B swizzle. Field layout checked against
+// cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start[0,14) lbo[16,30) sbo[32,46) version[46,48)
+// layout_type[61,64) (SWIZZLE_128B = 2); addresses/offsets in 16-byte units.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (InstrDescriptor): c_format[4,6)=F32(1), a_format[7,10)=BF16(1),
+// b_format[10,13)=BF16(1), a_major bit15, b_major bit16 (0 = K-major, 1 = MN-major),
+// n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) |
+         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+
+// epilogue shared by both kernels: 32 accumulator columns of one row -> alpha / bias / residual -> global
+__device__ __forceinline__ void epilogue_store32(const GemmParams& p, const uint32_t* r, int row, int col0,
+                                                 int split) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    if (col < p.N) {  // N is a multiple of 8 (checked on the host)
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * p.alpha;
+      if (p.bias) {
+        float b[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(p.bias + col), b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += b[i];
+      }
+      if (p.residual) {
+        float b[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(p.residual + (long long)row * p.ldr + col), b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += b[i];
+      }
+      if (p.c_fp32) {
+        float* dst = reinterpret_cast<float*>(p.C) + (long long)split * p.c_split_stride +
+                     (long long)row * p.ldc + col;
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+        bf16* dst = reinterpret_cast<bf16*>(p.C) + (long long)split * p.c_split_stride +
+                    (long long)row * p.ldc + col;
+        *reinterpret_cast<bf16x8*>(dst) = pack8(v);
+      }
+    }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over X[rows][inner] with leading dimension ld (elements), 128B swizzle.
+inline int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(B200RL_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || ((ld * 2) & 15u) != 0)
+    return set_error(B200RL_ERR_ARG, "gemm operand must be 16-byte aligned with ld %% 8 == 0 (ld=%llu)",
+                     (unsigned long long)ld);
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(B200RL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu ld=%llu)",
+                     (int)r, (unsigned long long)inner, (unsigned long long)rows,
+                     (unsigned long long)ld);
+  return 0;
+}
+
+struct GemmArgs {
+  const void *A1, *B1, *A2, *B2;
+  long long lda1, ldb1, lda2, ldb2;
+  int K1, K2;
+  void* C;
+  long long ldc;
+  int c_fp32;
+  const void* bias;
+  const void* residual;
+  long long ldr;
+  float alpha;
+  int M, N;
+  int mn_major;   // bit0: A stored [K][M] (MN-major), bit1: B stored [K][N]. 0 = TN, 3 = dW form, 2 = dX form
+  int splits;     // split-K factor (fp32 output slabs, c_split_stride apart)
+  long long c_split_stride;
+  int force_bn;   // 0 = heuristic
+  int max_ctas;   // 0 = all SMs
+};
+
+
+int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream);  // gemm2_tcgen05.cu
+bool gemm_pair_enabled();
+
+}  // namespace b200rl

@@ -19,50 +19,9 @@
 //   warp 1   : MMA issuer     (one thread: tcgen05.mma kind::f16, M=128, N=BN, K=16 per instr)
 //   warp 2   : TMEM allocator (2 accumulator stages so the epilogue overlaps the next mainloop)
 //   warps 4-7: epilogue       (tcgen05.ld 32x32b -> registers -> alpha/bias/residual -> global)
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace b200rl {
-
-static constexpr int BM = 128;
-static constexpr int BK = 64;           // 64 bf16 = 128 B = one 128B-swizzle row
-static constexpr int UMMA_K = 16;
-static constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
-
-struct GemmParams {
-  int M, N;
-  int kb1, kb2;          // k-blocks (of 64) in segment 1 / 2
-  int num_m_blocks, num_n_blocks, splits, kb_per_split;
-  void* C;
-  long long ldc;
-  long long c_split_stride;  // elements between split-K slabs
-  int c_fp32;
-  const bf16* bias;
-  const bf16* residual;
-  long long ldr;
-  float alpha;
-};
-
-// ---- descriptors ---------------------------------------------------------------------------
-// Shared-memory matrix descriptor (tcgen05), 128B swizzle. Field layout checked against
-// cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start[0,14) lbo[16,30) sbo[32,46) version[46,48)
-// layout_type[61,64) (SWIZZLE_128B = 2); addresses/offsets in 16-byte units.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
-  return d;
-}
-// Instruction descriptor (InstrDescriptor): c_format[4,6)=F32(1), a_format[7,10)=BF16(1),
-// b_format[10,13)=BF16(1), a_major bit15, b_major bit16 (0 = K-major, 1 = MN-major),
-// n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) |
-         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
 
 template <int BN>
 struct Cfg {
@@ -225,40 +184,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         tmem_ld_32x32(taddr0 + c * 32, r);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) {  // N is a multiple of 8 (checked on the host)
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * p.alpha;
-              if (p.bias) {
-                float b[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(p.bias + col), b);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += b[i];
-              }
-              if (p.residual) {
-                float b[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(p.residual + (long long)row * p.ldr + col),
-                        b);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += b[i];
-              }
-              if (p.c_fp32) {
-                float* dst = reinterpret_cast<float*>(p.C) + (long long)split * p.c_split_stride +
-                             (long long)row * p.ldc + col;
-                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              } else {
-                bf16* dst = reinterpret_cast<bf16*>(p.C) + (long long)split * p.c_split_stride +
-                            (long long)row * p.ldc + col;
-                *reinterpret_cast<bf16x8*>(dst) = pack8(v);
-              }
-            }
-          }
-        }
+        if (row_ok) epilogue_store32(p, r, row, col0, split);
       }
       tc_fence_before();
       __syncwarp();
@@ -273,66 +199,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
-
-// ---- host side -----------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
-            cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-// 2-D bf16 tensor map over X[rows][inner] with leading dimension ld (elements), 128B swizzle.
-static int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
-                    uint32_t box_inner, uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return set_error(B200RL_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || ((ld * 2) & 15u) != 0)
-    return set_error(B200RL_ERR_ARG, "gemm operand must be 16-byte aligned with ld %% 8 == 0 (ld=%llu)",
-                     (unsigned long long)ld);
-  cuuint64_t dims[2] = {inner, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {box_inner, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return set_error(B200RL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu ld=%llu)",
-                     (int)r, (unsigned long long)inner, (unsigned long long)rows,
-                     (unsigned long long)ld);
-  return 0;
-}
-
-struct GemmArgs {
-  const void *A1, *B1, *A2, *B2;
-  long long lda1, ldb1, lda2, ldb2;
-  int K1, K2;
-  void* C;
-  long long ldc;
-  int c_fp32;
-  const void* bias;
-  const void* residual;
-  long long ldr;
-  float alpha;
-  int M, N;
-  int mn_major;   // bit0: A stored [K][M] (MN-major), bit1: B stored [K][N]. 0 = TN, 3 = dW form, 2 = dX form
-  int splits;     // split-K factor (fp32 output slabs, c_split_stride apart)
-  long long c_split_stride;
-  int force_bn;   // 0 = heuristic
-  int max_ctas;   // 0 = all SMs
-};
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const GemmArgs& a, cudaStream_t stream) {
@@ -408,6 +274,29 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
     if (bn == 64) return launch<64, true, true>(a, stream);
     if (bn == 128) return launch<128, true, true>(a, stream);
     return set_error(B200RL_ERR_UNSUPPORTED, "gemm(dW form): BN=%d not instantiated", bn);
+  }
+  // CTA-pair kernel (cta_group::2, 256-row tiles) for the large activation x weight GEMMs
+  if (gemm_pair_enabled() && a.splits <= 1 && a.M > BM && a.N >= 128 &&
+      (a.force_bn == 0 || a.force_bn == 128 || a.force_bn == 256)) {
+    int pbn = a.force_bn;
+    if (pbn == 0) {
+      const int clusters = num_sms() / 2;
+      const int mb = (a.M + 2 * BM - 1) / (2 * BM);
+      double best = -1;
+      const int cands[2] = {256, 128};
+      for (int i = 0; i < 2; ++i) {
+        const int c = cands[i];
+        const long long tiles = (long long)mb * ((a.N + c - 1) / c);
+        const long long waves = (tiles + clusters - 1) / clusters;
+        double eff = ((double)a.M * a.N) / ((double)waves * clusters * 2 * BM * c);
+        eff *= (c == 256 ? 1.0 : 0.94);
+        if (eff > best) {
+          best = eff;
+          pbn = c;
+        }
+      }
+    }
+    return gemm_pair_dispatch(a, pbn, stream);
   }
   if (bn == 0) {
     if (a.N <= 64) bn = 64;

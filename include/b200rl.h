@@ -40,6 +40,8 @@ int b200rl_gemm(const void* A1, long long lda1, const void* B1, long long ldb1, 
                 long long ldc, int c_fp32, const void* bias, const void* residual, long long ldr,
                 float alpha, int M, int N, int mn_major, int splits, long long c_split_stride,
                 int force_bn, int max_ctas, void* stream);
+/* bisection switch: 1 (default) = CTA-pair (cta_group::2) kernels where applicable, 0 = single-CTA kernels only */
+int b200rl_gemm_set_cta_pair(int enable);
 
 /* ---- G2/G3/G5 row kernels (reference: Unsloth RMSNorm / RoPE / SwiGLU inside policy(...)) ---- */
 int b200rl_embed(const int* ids, const void* table, void* out, int M, int H, int vocab, void* stream);

@@ -39,8 +39,17 @@ GEMM_SHAPES = [
 ]
 
 
+@pytest.fixture(params=[1, 0], ids=["cta_pair", "single_cta"])
+def gemm_mode(request, cuda):
+    """Run the GEMM tests through both kernel families (cta_group::2 pair tiles / single-CTA tiles)."""
+    from distrl_llm_b200 import _capi
+    _capi.lib().b200rl_gemm_set_cta_pair(request.param)
+    yield request.param
+    _capi.lib().b200rl_gemm_set_cta_pair(1)
+
+
 @pytest.mark.parametrize("M,N,K1,K2,bn", GEMM_SHAPES)
-def test_gemm_tn(cuda, M, N, K1, K2, bn):
+def test_gemm_tn(cuda, gemm_mode, M, N, K1, K2, bn):
     from distrl_llm_b200 import ops
     a1 = _rand((M, K1), cuda, seed=1)
     b1 = _rand((N, K1), cuda, seed=2)
@@ -57,7 +66,7 @@ def test_gemm_tn(cuda, M, N, K1, K2, bn):
     assert torch.isfinite(out.float()).all()
 
 
-def test_gemm_epilogues(cuda):
+def test_gemm_epilogues(cuda, gemm_mode):
     from distrl_llm_b200 import ops
     M, N, K = 384, 320, 256
     a = _rand((M, K), cuda, seed=1)
@@ -79,7 +88,7 @@ def test_gemm_epilogues(cuda):
 @pytest.mark.parametrize("M,N,K1,K2,bn", [(128, 64, 64, 0, 0), (300, 200, 192, 0, 0), (1000, 512, 1024, 64, 0),
                                            (640, 3584, 4608, 64, 256), (4100, 1024, 2048, 64, 192),
                                            (512, 384, 256, 128, 128), (6896, 3584, 1024, 64, 0)])
-def test_gemm_dx_form(cuda, M, N, K1, K2, bn):
+def test_gemm_dx_form(cuda, gemm_mode, M, N, K1, K2, bn):
     """dX form: C = A1 @ B1 + A2 @ B2 with the B operands stored [K, N] (weights as stored [out, in])."""
     from distrl_llm_b200 import ops
     a1 = _rand((M, K1), cuda, seed=1)
