@@ -214,8 +214,7 @@ def main():
     group = None
     kw = {}
     if world > 1:
-        group = P2PGroup(rank, world, dev)
-        kw = group.alloc_lora_buffers(cfg, B, P, T)
+        group, kw = P2PGroup.from_torch_distributed(cfg, B, P, T, dev)
     pol = Policy.random_init(cfg, dev, B, P, T, seed=1234, **kw)   # same base + LoRA on every learner
     if group is not None:
         group.attach(pol)
@@ -228,6 +227,7 @@ def main():
     from distrl_llm_b200.trainer_prep import synthetic_candidates
     cands, flat = synthetic_candidates(cfg.vocab, N, P, T, args.group_size, seed=1234 + rank)
     prompts, answers, adv = flat
+    assert np.all(np.asarray(adv) != 0), "synthetic advantages must be non-zero (quirk Q1 would skip work)"
     nb = (N + B - 1) // B
     # device-resident copy for the `value` measurement
     ids_h, am_h, ansm_h = learner._encode(prompts, answers)

@@ -56,6 +56,27 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* g, long long gstr
   }
 }
 
+// Same tile, asynchronously (cp.async 16 B, zero-fill for rows >= nrows_valid); pair with cp_async_commit /
+// cp_async_wait<N> + __syncthreads.  Streams the K/V (or Q/dO) tiles one iteration ahead of the math.
+template <int HD, int ROWS>
+__device__ __forceinline__ void load_tile_async(bf16* s, const bf16* g, long long gstride, int nrows_valid) {
+  constexpr int LD = HD + 8;
+  constexpr int VPR = HD / 8;
+  for (int v = threadIdx.x; v < ROWS * VPR; v += blockDim.x) {
+    const int r = v / VPR, c = (v % VPR) * 8;
+    const bool ok = r < nrows_valid;
+    const bf16* src = ok ? g + (long long)r * gstride + c : g;
+    const uint32_t dst = smem_u32(s + r * LD + c);
+    const int nbytes = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // A-operand fragment (16 rows x 16 k) from a row-major padded tile: rows r0.., k columns k0..
 template <int LD>
 __device__ __forceinline__ void load_a_frag(const bf16* s, int r0, int k0, uint32_t* a) {
@@ -93,9 +114,9 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ key_mask,
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
-  bf16* sK = sQ + 64 * LD;
-  bf16* sV = sK + 64 * LD;
-  int* sMask = reinterpret_cast<int*>(sV + 64 * LD);
+  bf16* sKb = sQ + 64 * LD;            // [2][64][LD]
+  bf16* sVb = sKb + 2 * 64 * LD;       // [2][64][LD]
+  int* sMaskb = reinterpret_cast<int*>(sVb + 2 * 64 * LD);  // [2][64]
 
   const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
   const int g = h / (nq / nkv);
@@ -117,14 +138,27 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ key_mask,
   const int row_a = q0 + warp * 16 + gq, row_b = row_a + 8;
 
   const int kb_end = min((q0 + 63) / 64, (L - 1) / 64);
+  auto prefetch = [&](int kb) {
+    const int k0p = kb * 64, buf = kb & 1;
+    load_tile_async<HD, 64>(sKb + buf * 64 * LD, base + (long long)k0p * stride + (nq + g) * HD, stride, min(64, L - k0p));
+    load_tile_async<HD, 64>(sVb + buf * 64 * LD, base + (long long)k0p * stride + (nq + nkv + g) * HD, stride, min(64, L - k0p));
+    if (threadIdx.x < 64)
+      sMaskb[buf * 64 + threadIdx.x] = (k0p + threadIdx.x < L) ? key_mask[(long long)b * L + k0p + threadIdx.x] : 0;
+    cp_async_commit();
+  };
+  prefetch(0);
   for (int kb = 0; kb <= kb_end; ++kb) {
     const int k0 = kb * 64;
-    __syncthreads();  // previous iteration's readers of sK/sV are done
-    load_tile<HD, 64>(sK, base + (long long)k0 * stride + (nq + g) * HD, stride, min(64, L - k0));
-    load_tile<HD, 64>(sV, base + (long long)k0 * stride + (nq + nkv + g) * HD, stride, min(64, L - k0));
-    if (threadIdx.x < 64)
-      sMask[threadIdx.x] = (k0 + threadIdx.x < L) ? key_mask[(long long)b * L + k0 + threadIdx.x] : 0;
+    if (kb < kb_end) {
+      prefetch(kb + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
+    const bf16* sK = sKb + (kb & 1) * 64 * LD;
+    const bf16* sV = sVb + (kb & 1) * 64 * LD;
+    const int* sMask = sMaskb + (kb & 1) * 64;
 
     float s[8][4];
 #pragma unroll
@@ -198,6 +232,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ key_mask,
         mma16816(o[2 * dp + 1], pa, bfr[2], bfr[3]);
       }
     }
+    __syncthreads();  // everyone is done with this buffer before the next prefetch overwrites it
   }
   // finalize
   float inv[2];
@@ -270,9 +305,9 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const int* __restrict__ key_mas
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
   bf16* sdO = sQ + 64 * LD;
-  bf16* sK = sdO + 64 * LD;
-  bf16* sV = sK + 64 * LD;
-  int* sMask = reinterpret_cast<int*>(sV + 64 * LD);
+  bf16* sKb = sdO + 64 * LD;           // [2][64][LD]
+  bf16* sVb = sKb + 2 * 64 * LD;       // [2][64][LD]
+  int* sMaskb = reinterpret_cast<int*>(sVb + 2 * 64 * LD);
 
   const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
   const int g = h / (nq / nkv);
@@ -297,14 +332,27 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const int* __restrict__ key_mas
   for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
 
   const int kb_end = min((q0 + 63) / 64, (L - 1) / 64);
+  auto prefetch = [&](int kb) {
+    const int k0p = kb * 64, buf = kb & 1;
+    load_tile_async<HD, 64>(sKb + buf * 64 * LD, base + (long long)k0p * stride + (nq + g) * HD, stride, min(64, L - k0p));
+    load_tile_async<HD, 64>(sVb + buf * 64 * LD, base + (long long)k0p * stride + (nq + nkv + g) * HD, stride, min(64, L - k0p));
+    if (threadIdx.x < 64)
+      sMaskb[buf * 64 + threadIdx.x] = (k0p + threadIdx.x < L) ? key_mask[(long long)b * L + k0p + threadIdx.x] : 0;
+    cp_async_commit();
+  };
+  prefetch(0);
   for (int kb = 0; kb <= kb_end; ++kb) {
     const int k0 = kb * 64;
-    __syncthreads();
-    load_tile<HD, 64>(sK, base + (long long)k0 * stride + (nq + g) * HD, stride, min(64, L - k0));
-    load_tile<HD, 64>(sV, base + (long long)k0 * stride + (nq + nkv + g) * HD, stride, min(64, L - k0));
-    if (threadIdx.x < 64)
-      sMask[threadIdx.x] = (k0 + threadIdx.x < L) ? key_mask[(long long)b * L + k0 + threadIdx.x] : 0;
-    __syncthreads();
+    if (kb < kb_end) {
+      prefetch(kb + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();  // also publishes the sQ / sdO tiles on the first iteration
+    const bf16* sK = sKb + (kb & 1) * 64 * LD;
+    const bf16* sV = sVb + (kb & 1) * 64 * LD;
+    const int* sMask = sMaskb + (kb & 1) * 64;
 
     float s[8][4], dp[8][4];
 #pragma unroll
@@ -356,6 +404,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const int* __restrict__ key_mas
         mma16816(dq[2 * d2 + 1], pa, bfr[2], bfr[3]);
       }
     }
+    __syncthreads();  // buffer free for the next prefetch
   }
   __syncthreads();  // everyone is done with sQ as an operand
 #pragma unroll
@@ -388,10 +437,10 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const int* __restrict__ key_ma
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sK = reinterpret_cast<bf16*>(smem_attn);
   bf16* sV = sK + 64 * LD;
-  bf16* sQ = sV + 64 * LD;
-  bf16* sdO = sQ + BQ * LD;
-  float* sLse = reinterpret_cast<float*>(sdO + BQ * LD);
-  float* sDel = sLse + BQ;
+  bf16* sQb = sV + 64 * LD;            // [2][BQ][LD]
+  bf16* sdOb = sQb + 2 * BQ * LD;      // [2][BQ][LD]
+  float* sLseb = reinterpret_cast<float*>(sdOb + 2 * BQ * LD);  // [2][BQ]
+  float* sDelb = sLseb + 2 * BQ;                                 // [2][BQ]
 
   const int k0 = blockIdx.x * 64, g = blockIdx.y, b = blockIdx.z;
   const int group = nq / nkv;
@@ -414,21 +463,41 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const int* __restrict__ key_ma
     dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
   }
 
-  for (int hh = 0; hh < group; ++hh) {
-    const int h = g * group + hh;
-    const long long sidx = ((long long)b * nq + h) * L;
-    for (int qb = k0 / BQ; qb * BQ < L; ++qb) {
-      const int q0 = qb * BQ;
-      const int nvalid_q = min(BQ, L - q0);
-      __syncthreads();
-      load_tile<HD, BQ>(sQ, base + (long long)q0 * stride + h * HD, stride, nvalid_q);
-      load_tile<HD, BQ>(sdO, dout + ((long long)b * L + q0) * nq * HD + h * HD, (long long)nq * HD, nvalid_q);
-      if (threadIdx.x < BQ) {
-        const int qi = q0 + threadIdx.x;
-        sLse[threadIdx.x] = qi < L ? lse2[sidx + qi] : INFINITY;
-        sDel[threadIdx.x] = qi < L ? delta[sidx + qi] : 0.f;
+  // flattened (q head of the group, 32-query block at or after the key block) iteration space,
+  // Q / dO / lse / delta tiles streamed one iteration ahead with cp.async
+  const int qb0 = k0 / BQ;
+  const int nqb = (L - qb0 * BQ + BQ - 1) / BQ;
+  const int n_it = group * nqb;
+  auto prefetch = [&](int it) {
+    const int h = g * group + it / nqb;
+    const int q0p = (qb0 + it % nqb) * BQ;
+    const int buf = it & 1;
+    const int nv = min(BQ, L - q0p);
+    load_tile_async<HD, BQ>(sQb + buf * BQ * LD, base + (long long)q0p * stride + h * HD, stride, nv);
+    load_tile_async<HD, BQ>(sdOb + buf * BQ * LD, dout + ((long long)b * L + q0p) * nq * HD + h * HD, (long long)nq * HD, nv);
+    if (threadIdx.x < BQ) {
+      const int qi = q0p + threadIdx.x;
+      const long long sidx = ((long long)b * nq + h) * L;
+      sLseb[buf * BQ + threadIdx.x] = qi < L ? lse2[sidx + qi] : INFINITY;
+      sDelb[buf * BQ + threadIdx.x] = qi < L ? delta[sidx + qi] : 0.f;
+    }
+    cp_async_commit();
+  };
+  prefetch(0);
+  for (int it = 0; it < n_it; ++it) {
+    {
+      const int q0 = (qb0 + it % nqb) * BQ;
+      if (it + 1 < n_it) {
+        prefetch(it + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
-      __syncthreads();
+      __syncthreads();  // also publishes sK / sV on the first iteration
+      const bf16* sQ = sQb + (it & 1) * BQ * LD;
+      const bf16* sdO = sdOb + (it & 1) * BQ * LD;
+      const float* sLse = sLseb + (it & 1) * BQ;
+      const float* sDel = sDelb + (it & 1) * BQ;
 
       // S^T = K . Q^T and dP^T = V . dO^T : [16 keys x 32 queries] per warp
       float st[4][4], dpt[4][4];
@@ -491,6 +560,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const int* __restrict__ key_ma
           mma16816(dk[2 * d2 + 1], sa, bq[2], bq[3]);
         }
       }
+      __syncthreads();  // buffer free for the next prefetch
     }
   }
   // write dK, dV through smem (reuse sK / sV: all operand reads are finished after this barrier)
@@ -518,7 +588,7 @@ template <int HD>
 static int attn_fwd_launch(const void* qkv, const int* key_mask, void* out, float* lse, int B, int L,
                            int nq, int nkv, float scale, cudaStream_t stream) {
   constexpr int LD = HD + 8;
-  const int smem = 3 * 64 * LD * 2 + 64 * 4;
+  const int smem = 5 * 64 * LD * 2 + 2 * 64 * 4;
   auto kern = attn_fwd_kernel<HD>;
   B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((L + 63) / 64, nq, B);
@@ -541,7 +611,7 @@ static int attn_bwd_launch(const void* qkv, const int* key_mask, const void* out
     B200RL_LAUNCH_OK();
   }
   {
-    const int smem = 4 * 64 * LD * 2 + 64 * 4;
+    const int smem = 6 * 64 * LD * 2 + 2 * 64 * 4;
     auto kern = attn_bwd_dq_kernel<HD>;
     B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid((L + 63) / 64, nq, B);
@@ -550,7 +620,7 @@ static int attn_bwd_launch(const void* qkv, const int* key_mask, const void* out
     B200RL_LAUNCH_OK();
   }
   {
-    const int smem = (2 * 64 + 2 * 32) * LD * 2 + 2 * 32 * 4;
+    const int smem = (2 * 64 + 4 * 32) * LD * 2 + 4 * 32 * 4;
     auto kern = attn_bwd_dkv_kernel<HD>;
     B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid((L + 63) / 64, nkv, B);

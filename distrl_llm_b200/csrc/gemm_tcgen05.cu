@@ -276,26 +276,10 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
     return set_error(B200RL_ERR_UNSUPPORTED, "gemm(dW form): BN=%d not instantiated", bn);
   }
   // CTA-pair kernel (cta_group::2, 256-row tiles) for the large activation x weight GEMMs
-  if (gemm_pair_enabled() && a.splits <= 1 && a.M > BM && a.N >= 128 &&
+  if (gemm_pair_enabled() && a.splits <= 1 && a.M > BM && a.N >= 256 &&
       (a.force_bn == 0 || a.force_bn == 128 || a.force_bn == 256)) {
-    int pbn = a.force_bn;
-    if (pbn == 0) {
-      const int clusters = num_sms() / 2;
-      const int mb = (a.M + 2 * BM - 1) / (2 * BM);
-      double best = -1;
-      const int cands[2] = {256, 128};
-      for (int i = 0; i < 2; ++i) {
-        const int c = cands[i];
-        const long long tiles = (long long)mb * ((a.N + c - 1) / c);
-        const long long waves = (tiles + clusters - 1) / clusters;
-        double eff = ((double)a.M * a.N) / ((double)waves * clusters * 2 * BM * c);
-        eff *= (c == 256 ? 1.0 : 0.94);
-        if (eff > best) {
-          best = eff;
-          pbn = c;
-        }
-      }
-    }
+    // pair tiles are 256 x 256: the 128-wide pair tile is smem-bound again (measured 630-750 TFLOP/s)
+    const int pbn = a.force_bn ? a.force_bn : 256;
     return gemm_pair_dispatch(a, pbn, stream);
   }
   if (bn == 0) {

@@ -74,7 +74,9 @@ class BaseLearner:
         self.lora_save_path = config.get("lora_save_path", "lora_request_math")
         self.reference_quirks = reference_quirks
         self.generator = generator
-        self.p2p = None  # set by enable_p2p()
+        self.p2p = None  # set by enable_p2p() / p2p_open_handles()
+        self._p2p_group = None
+        self._p2p_handles = None
         self._pinned = {}
 
     # ---- tokenise + pad (:217-239) ------------------------------------------------------------
@@ -160,6 +162,16 @@ class BaseLearner:
 
     def enable_p2p(self, group):
         self.p2p = group
+
+    # Ray flow: the policy was built on buffers from P2PGroup.alloc_local(); the driver
+    # gathers every learner's handles with p2p_export_handles() and broadcasts them to p2p_open_handles().
+    def p2p_export_handles(self):
+        return self._p2p_handles
+
+    def p2p_open_handles(self, all_handles):
+        self._p2p_group.open_peers(all_handles)
+        self._p2p_group.attach(self.policy)
+        self.p2p = self._p2p_group
 
     # ---- misc actor surface --------------------------------------------------------------------------
     def generate(self, messages, sampling_params=None):

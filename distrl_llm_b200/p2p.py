@@ -3,8 +3,8 @@
 Replaces the reference's exchange (distributed_trainer.py:325-342 driver hop; distributed_actor.py:289-293
 D2H export, :311-328 CPU merge + H2D, :331-333 step on learner 0 only).  Each learner allocates its flat
 LoRA parameter / gradient buffers and a flag array with b200rl_p2p_alloc (cudaMalloc + cudaIpcGetMemHandle),
-the 64-byte IPC handles are exchanged ONCE (torch.distributed here; Ray RPC in the reference's process model,
-see INTEGRATION.md), and every peer maps them with cudaIpcOpenMemHandle.  One step then is:
+the 64-byte IPC handles are exchanged ONCE (torch.distributed under torchrun; two Ray RPCs in the reference's
+process model), and every peer maps them with cudaIpcOpenMemHandle.  One step then is:
     barrier kernel (all gradients complete)  ->  reduce_adam kernel: each learner reads its 1/N slice of
     every peer's gradient over NVLink, averages, applies Adam(W) and stores the updated slice into every
     peer's parameter buffer  ->  barrier kernel (all stores landed)  ->  local bf16 operand refresh.
@@ -19,57 +19,73 @@ from . import _capi
 from ._capi import check, lib, stream
 from .policy import Policy, tensor_from_ptr
 
+_NAMES = ("params", "grads", "flags")
+
+
+def lora_numel(cfg, max_batch, P, T) -> int:
+    ccfg = _capi.ModelConfig(cfg.vocab, cfg.hidden, cfg.inter, cfg.n_layers, cfg.n_q_heads, cfg.n_kv_heads,
+                             cfg.head_dim, cfg.lora_r, cfg.lora_scale, cfg.rms_eps, cfg.rope_theta,
+                             max_batch * (P + T), max_batch, P + T, max_batch * T)
+    n = int(_capi.lib().b200rl_model_lora_numel(C.byref(ccfg)))
+    if n <= 0:
+        raise RuntimeError("libb200rl: " + _capi.lib().b200rl_last_error().decode())
+    return n
+
 
 class P2PGroup:
-    def __init__(self, rank, world, device, exchange=None):
-        """exchange(obj) -> list of every rank's obj (default: torch.distributed.all_gather_object)."""
+    """Two-phase setup: alloc_local() -> handles (send them to every peer) ; open_peers(all handles)."""
+
+    def __init__(self, rank, world, device):
         _capi.load_library()
         self.rank, self.world, self.device = rank, world, torch.device(device)
-        self.exchange = exchange or self._dist_exchange
         self.epoch = 0
         self.local = {}    # name -> local device pointer
         self.peers = {}    # name -> [pointer on every rank]
         self._opened = []
+        self.numel = 0
 
-    @staticmethod
-    def _dist_exchange(obj):
+    # ---- phase 1 ---------------------------------------------------------------------------------
+    def alloc_local(self, numel):
+        """Allocate the IPC-exportable buffers; returns ({name: 64-byte handle}, kwargs for Policy(...))."""
+        self.numel = numel
+        handles = {}
+        for name, nbytes in (("params", numel * 4), ("grads", numel * 4), ("flags", 64 * 4)):
+            p = C.c_void_p()
+            h = (C.c_ubyte * 64)()
+            check(lib().b200rl_p2p_alloc(nbytes, C.byref(p), h), "p2p_alloc")
+            self.local[name] = p.value
+            handles[name] = bytes(h)
+        kw = {"lora_flat": tensor_from_ptr(self.local["params"], numel, torch.float32, self.device),
+              "lora_grad": tensor_from_ptr(self.local["grads"], numel, torch.float32, self.device)}
+        return handles, kw
+
+    # ---- phase 2 ---------------------------------------------------------------------------------
+    def open_peers(self, all_handles):
+        """all_handles[r] = the dict returned by rank r's alloc_local()."""
+        assert len(all_handles) == self.world
+        for name in _NAMES:
+            ptrs = []
+            for r, hd in enumerate(all_handles):
+                if r == self.rank:
+                    ptrs.append(self.local[name])
+                else:
+                    q = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(hd[name])
+                    check(lib().b200rl_p2p_open(buf, C.byref(q)), "p2p_open")
+                    self._opened.append(q.value)
+                    ptrs.append(q.value)
+            self.peers[name] = ptrs
+
+    @classmethod
+    def from_torch_distributed(cls, cfg, max_batch, P, T, device):
+        """torchrun path (bench.py): exchange the handles with all_gather_object."""
         import torch.distributed as dist
-        out = [None] * dist.get_world_size()
-        dist.all_gather_object(out, obj)
-        return out
-
-    def _alloc_shared(self, name, nbytes):
-        p = C.c_void_p()
-        h = (C.c_ubyte * 64)()
-        check(lib().b200rl_p2p_alloc(nbytes, C.byref(p), h), "p2p_alloc")
-        self.local[name] = p.value
-        handles = self.exchange(bytes(h))
-        ptrs = []
-        for r, hb in enumerate(handles):
-            if r == self.rank:
-                ptrs.append(p.value)
-            else:
-                q = C.c_void_p()
-                buf = (C.c_ubyte * 64).from_buffer_copy(hb)
-                check(lib().b200rl_p2p_open(buf, C.byref(q)), "p2p_open")
-                self._opened.append(q.value)
-                ptrs.append(q.value)
-        self.peers[name] = ptrs
-        return p.value
-
-    def alloc_lora_buffers(self, cfg, max_batch, P, T):
-        """Allocate IPC-exportable flat parameter / gradient buffers; returns kwargs for Policy(...)."""
-        probe = Policy.__new__(Policy)  # only to size the buffer
-        ccfg = _capi.ModelConfig(cfg.vocab, cfg.hidden, cfg.inter, cfg.n_layers, cfg.n_q_heads, cfg.n_kv_heads,
-                                 cfg.head_dim, cfg.lora_r, cfg.lora_scale, cfg.rms_eps, cfg.rope_theta,
-                                 max_batch * (P + T), max_batch, P + T, max_batch * T)
-        n = int(lib().b200rl_model_lora_numel(C.byref(ccfg)))
-        self.numel = n
-        pp = self._alloc_shared("params", n * 4)
-        gp = self._alloc_shared("grads", n * 4)
-        self._alloc_shared("flags", 64 * 4)
-        return {"lora_flat": tensor_from_ptr(pp, n, torch.float32, self.device),
-                "lora_grad": tensor_from_ptr(gp, n, torch.float32, self.device)}
+        g = cls(dist.get_rank(), dist.get_world_size(), device)
+        handles, kw = g.alloc_local(lora_numel(cfg, max_batch, P, T))
+        allh = [None] * g.world
+        dist.all_gather_object(allh, handles)
+        g.open_peers(allh)
+        return g, kw
 
     def attach(self, policy: Policy):
         assert policy.lora_flat.data_ptr() == self.local["params"]

@@ -63,8 +63,12 @@ def synthetic_candidates(vocab, n_seq, P, T, group_size, seed=1234, device=None)
             fmt = rng.choice([0.0, 0.1, 0.2], size=group_size, p=[0.5, 0.3, 0.2])
             acc = (rng.random(group_size) < 0.25).astype(np.float64)
             s = fmt + acc
-            if np.std(s) > 0:
+            adv = (s - np.mean(s)) / (np.std(s) + 1e-8)   # distributed_trainer.py:273
+            # redraw degenerate groups AND groups with an exactly-zero advantage: the reference skips every
+            # micro-batch that contains one (quirk Q1, distributed_actor.py:459), which would silently
+            # remove work from a benchmark step
+            if np.std(s) > 0 and np.all(adv != 0):
                 break
-        cand["rewards"].append((s - np.mean(s)) / (np.std(s) + 1e-8))   # distributed_trainer.py:273
+        cand["rewards"].append(adv)
     problems, answers, rewards = merge_candidates([cand])
     return [cand], (problems, answers, np.asarray(rewards, dtype=np.float64))
