@@ -115,3 +115,13 @@ class P2PGroup:
         for p in self._opened:
             lib().b200rl_p2p_close(p)
         self._opened = []
+
+
+def owned_slice(n, world, rank):
+    """[lo, hi) of the flat buffer that `rank` reduces and updates — mirrors b200rl_lora_reduce_adamw
+    (csrc/optim.cu): contiguous, 4-element aligned, remainder absorbed by the last ranks' clamping."""
+    n4 = n // 4
+    per = (n4 + world - 1) // world
+    lo = 4 * min(per * rank, n4)
+    hi = 4 * min(per * (rank + 1), n4)
+    return lo, hi

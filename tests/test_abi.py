@@ -1,0 +1,70 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/b200rl.h declares, and the ctypes table mirrors the header (no compute calls: no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b200rl.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200rl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from distrl_llm_b200 import _capi
+    assert os.path.exists(_capi.LIB_PATH), "build with `python __graft_entry__.py` first"
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in b200rl.h but not exported: {missing}"
+
+
+def test_ctypes_table_matches_header():
+    from distrl_llm_b200 import _capi
+    declared = set(_declared())
+    bound = set(_capi.SIGNATURES)
+    assert bound <= declared, f"bound but not declared: {sorted(bound - declared)}"
+    assert declared <= bound, f"declared but not bound: {sorted(declared - bound)}"
+
+
+def test_header_cites_reference_lines():
+    src = open(HEADER).read()
+    for needle in ("distributed_actor.py:241-243", "distributed_actor.py:252-260", "distributed_trainer.py:262-294",
+                   "distributed_actor.py:283-294", ":302-333"):
+        assert needle in src
+
+
+def test_error_convention_without_gpu():
+    """Argument validation happens before any CUDA call: a bad call returns a negative code and a message."""
+    from distrl_llm_b200 import _capi
+    lib = _capi.load_library()
+    rc = lib.b200rl_logprob(None, 0, None, None, None, 0, 0, 0, None)
+    assert rc < 0
+    assert b"logprob" in lib.b200rl_last_error()
+    cfg = _capi.ModelConfig(1001, 128, 256, 2, 4, 2, 32, 16, 1.0, 1e-6, 1e6, 64, 2, 32, 32)  # vocab % 8 != 0
+    assert lib.b200rl_model_workspace_bytes(ctypes.byref(cfg)) < 0
+    with pytest.raises(RuntimeError):
+        _capi.check(rc, "logprob")
+
+
+def test_no_fallback_when_library_missing(monkeypatch, tmp_path):
+    from distrl_llm_b200 import _capi
+    monkeypatch.setattr(_capi, "_lib", None)
+    monkeypatch.setattr(_capi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or torch fallback"):
+        _capi.load_library()
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "distrl_llm_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py") and fn != "_smoke.py":   # smoke() is allowed to use the oracle as a checker
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
