@@ -281,6 +281,14 @@ def main():
 
     for _ in range(args.warmup):
         device_step()
+    if os.environ.get("B200RL_PROFILE_ONE_STEP"):
+        # ncu --profile-from-start off: exactly one learner step between cudaProfilerStart/Stop
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        device_step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     ms_dev, clocks, launches = timed(device_step, args.steps, sample_clocks=True)
     for _ in range(2):
         e2e_step()
