@@ -60,6 +60,9 @@ SIGNATURES = {
     "b200rl_logprob": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200rl_loss_coef": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200rl_loss_value": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200rl_logprob_kl": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200rl_loss_coef_kl": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_double, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200rl_loss_value_kl": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_double, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200rl_group_advantage_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200rl_nf4_quantize": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "b200rl_nf4_dequant": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -81,6 +84,8 @@ SIGNATURES = {
     "b200rl_model_destroy": (c_int, [c_void_p]),
     "b200rl_model_sync_lora": (c_int, [c_void_p, c_void_p]),
     "b200rl_model_debug_ptr": (c_void_p, [c_void_p, C.c_char_p, c_int]),
+    "b200rl_model_microbatch_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, C.c_double, c_void_p]),
     "b200rl_model_profile": (c_int, [c_void_p, c_int]),
     "b200rl_model_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200rl_launch_count": (c_ll, []),

@@ -22,7 +22,8 @@ static constexpr float LN2 = 0.6931471805599453f;
 // one CTA per row
 __global__ void __launch_bounds__(1024)
 logprob_kernel(bf16* __restrict__ logits, long long ld, const int* __restrict__ targets,
-               const float* __restrict__ coef, float* __restrict__ lp_out, int V, int write_grad) {
+               const float* __restrict__ coef, const float* __restrict__ klw,
+               const float* __restrict__ ref_lp, float* __restrict__ lp_out, int V, int write_grad) {
   __shared__ float red_m[32], red_s[32];
   __shared__ float s_lse2, s_max2;
   const size_t row = blockIdx.x;
@@ -80,11 +81,13 @@ logprob_kernel(bf16* __restrict__ logits, long long ld, const int* __restrict__ 
   __syncthreads();
   const float lse2 = s_lse2;
   const int y = targets[row];
-  const float c = coef ? coef[row] : 0.f;
-  if (threadIdx.x == 0 && lp_out) {
-    const float zy = (y >= 0 && y < V) ? __bfloat162float(z[y]) : 0.f;
-    lp_out[row] = (y >= 0 && y < V) ? (zy * LOG2E - lse2) * LN2 : 0.f;
-  }
+  const float zy = (y >= 0 && y < V) ? __bfloat162float(z[y]) : 0.f;
+  const float lp = (y >= 0 && y < V) ? (zy * LOG2E - lse2) * LN2 : 0.f;
+  float c = coef ? coef[row] : 0.f;
+  // optional KL(pi || pi_ref) term, k3 estimator exp(q-p) - (q-p) - 1 per token:
+  // d k3 / d lp = 1 - exp(q - p); klw carries beta * mask / (len * Bm * nb)   (not in the reference: beta = 0)
+  if (klw && ref_lp && klw[row] != 0.f) c += klw[row] * (1.f - __expf(ref_lp[row] - lp));
+  if (threadIdx.x == 0 && lp_out) lp_out[row] = lp;
   if (!write_grad) return;
   __syncthreads();  // z[y] read above must precede the in-place overwrite
   // ---- pass 2: dz = coef * (onehot - softmax), in place ----
@@ -115,8 +118,8 @@ logprob_kernel(bf16* __restrict__ logits, long long ld, const int* __restrict__ 
 //   len_i = sum_t mask[i,t];  coef[i,t] = -A_i * mask[i,t] / (len_i * Bm * nb)   (0 when len_i = 0)
 // ------------------------------------------------------------------------------------------
 __global__ void loss_coef_kernel(const int* __restrict__ mask, const double* __restrict__ adv,
-                                 float* __restrict__ coef, int* __restrict__ lens, int T, int Bm,
-                                 int nb) {
+                                 float* __restrict__ coef, float* __restrict__ klw, double beta,
+                                 int* __restrict__ lens, int T, int Bm, int nb) {
   __shared__ int red[32];
   const int i = blockIdx.x;
   int cnt = 0;
@@ -135,8 +138,12 @@ __global__ void loss_coef_kernel(const int* __restrict__ mask, const double* __r
   const int len = red[0];
   if (threadIdx.x == 0 && lens) lens[i] = len;
   const double base = len > 0 ? -adv[i] / ((double)len * (double)Bm * (double)nb) : 0.0;
-  for (int t = threadIdx.x; t < T; t += blockDim.x)
-    coef[(size_t)i * T + t] = mask[(size_t)i * T + t] != 0 ? (float)base : 0.f;
+  const double kbase = len > 0 ? beta / ((double)len * (double)Bm * (double)nb) : 0.0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const bool on = mask[(size_t)i * T + t] != 0;
+    coef[(size_t)i * T + t] = on ? (float)base : 0.f;
+    if (klw) klw[(size_t)i * T + t] = on ? (float)kbase : 0.f;
+  }
 }
 
 // loss value of one micro-batch, accumulated on the device (no per-micro-batch .item() sync):
@@ -144,37 +151,46 @@ __global__ void loss_coef_kernel(const int* __restrict__ mask, const double* __r
 //   GRPO (:467-470): importance = exp(lp - lp.detach()) == 1  =>  loss_m = -(1/Bm) sum_i A_i * [len_i>0]
 // The reference's returned scalar is the SUM of loss_m over micro-batches (quirk Q2) -> *accum += loss_m.
 __global__ void loss_value_kernel(const float* __restrict__ lp, const int* __restrict__ mask,
-                                  const double* __restrict__ adv, double* __restrict__ accum, int Bm,
-                                  int T, int grpo) {
+                                  const double* __restrict__ adv, const float* __restrict__ ref_lp,
+                                  double beta, double* __restrict__ accum, int Bm, int T, int grpo) {
   __shared__ double red[32];
   double total = 0.0;
   for (int i = 0; i < Bm; ++i) {
-    double s = 0.0;
+    double s = 0.0, kl = 0.0;
     int cnt = 0;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
       if (mask[(size_t)i * T + t] != 0) {
-        s += (double)lp[(size_t)i * T + t];
+        const double p = (double)lp[(size_t)i * T + t];
+        s += p;
         cnt += 1;
+        if (ref_lp) {
+          const double d = (double)ref_lp[(size_t)i * T + t] - p;
+          kl += exp(d) - d - 1.0;
+        }
       }
     }
     s = warp_sum_d(s);
+    kl = warp_sum_d(kl);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     __syncthreads();
+    __shared__ double redk[32];
     if ((threadIdx.x & 31) == 0) {
       red[threadIdx.x >> 5] = s;
+      redk[threadIdx.x >> 5] = kl;
     }
     __shared__ int redc[32];
     if ((threadIdx.x & 31) == 0) redc[threadIdx.x >> 5] = cnt;
     __syncthreads();
     if (threadIdx.x == 0) {
-      double ss = 0.0;
+      double ss = 0.0, kk = 0.0;
       int cc = 0;
       for (int w = 0; w < (blockDim.x >> 5); ++w) {
         ss += red[w];
+        kk += redk[w];
         cc += redc[w];
       }
-      if (cc > 0) total += grpo ? adv[i] : adv[i] * (ss / (double)cc);
+      if (cc > 0) total += (grpo ? adv[i] : adv[i] * (ss / (double)cc)) - beta * (kk / (double)cc);
     }
     __syncthreads();
   }
@@ -186,14 +202,35 @@ __global__ void loss_value_kernel(const float* __restrict__ lp, const int* __res
 using namespace b200rl;
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
 
+extern "C" int b200rl_logprob_kl(void* logits, long long ld, const int* targets, const float* coef,
+                                 const float* klw, const float* ref_lp, float* lp_out, int rows, int V,
+                                 int write_grad, void* stream) {
+  B200RL_REQUIRE(logits && targets && rows > 0 && V > 0 && V % 8 == 0 && ld % 8 == 0,
+                 "logprob: bad args (rows=%d V=%d ld=%lld)", rows, V, ld);
+  B200RL_REQUIRE(!write_grad || coef, "logprob: write_grad needs coef");
+  const int threads = V >= 8192 ? 1024 : 256;
+  logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, klw, ref_lp, lp_out, V,
+                                               write_grad);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int b200rl_logprob(void* logits, long long ld, const int* targets, const float* coef,
                               float* lp_out, int rows, int V, int write_grad, void* stream) {
   B200RL_REQUIRE(logits && targets && rows > 0 && V > 0 && V % 8 == 0 && ld % 8 == 0,
                  "logprob: bad args (rows=%d V=%d ld=%lld)", rows, V, ld);
   B200RL_REQUIRE(!write_grad || coef, "logprob: write_grad needs coef");
   const int threads = V >= 8192 ? 1024 : 256;
-  logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, lp_out, V,
+  logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, nullptr, nullptr, lp_out, V,
                                                write_grad);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200rl_loss_coef_kl(const int* mask, const double* adv, float* coef, float* klw, double beta,
+                                   int* lens, int Bm, int T, int nb, void* stream) {
+  B200RL_REQUIRE(mask && adv && coef && Bm > 0 && T > 0 && nb > 0, "loss_coef: bad args");
+  loss_coef_kernel<<<Bm, 256, 0, STREAM>>>(mask, adv, coef, klw, beta, lens, T, Bm, nb);
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -201,7 +238,15 @@ extern "C" int b200rl_logprob(void* logits, long long ld, const int* targets, co
 extern "C" int b200rl_loss_coef(const int* mask, const double* adv, float* coef, int* lens, int Bm,
                                 int T, int nb, void* stream) {
   B200RL_REQUIRE(mask && adv && coef && Bm > 0 && T > 0 && nb > 0, "loss_coef: bad args");
-  loss_coef_kernel<<<Bm, 256, 0, STREAM>>>(mask, adv, coef, lens, T, Bm, nb);
+  loss_coef_kernel<<<Bm, 256, 0, STREAM>>>(mask, adv, coef, nullptr, 0.0, lens, T, Bm, nb);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200rl_loss_value_kl(const float* lp, const int* mask, const double* adv, const float* ref_lp,
+                                    double beta, double* accum, int Bm, int T, int grpo, void* stream) {
+  B200RL_REQUIRE(lp && mask && adv && accum && Bm > 0 && T > 0, "loss_value: bad args");
+  loss_value_kernel<<<1, 256, 0, STREAM>>>(lp, mask, adv, ref_lp, beta, accum, Bm, T, grpo);
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -209,7 +254,7 @@ extern "C" int b200rl_loss_coef(const int* mask, const double* adv, float* coef,
 extern "C" int b200rl_loss_value(const float* lp, const int* mask, const double* adv, double* accum,
                                  int Bm, int T, int grpo, void* stream) {
   B200RL_REQUIRE(lp && mask && adv && accum && Bm > 0 && T > 0, "loss_value: bad args");
-  loss_value_kernel<<<1, 256, 0, STREAM>>>(lp, mask, adv, accum, Bm, T, grpo);
+  loss_value_kernel<<<1, 256, 0, STREAM>>>(lp, mask, adv, nullptr, 0.0, accum, Bm, T, grpo);
   B200RL_LAUNCH_OK();
   return 0;
 }

@@ -65,6 +65,9 @@ int b200rl_attn_bwd(const void*, const int*, const void*, const void*, const flo
 int b200rl_logprob(void*, long long, const int*, const float*, float*, int, int, int, void*);
 int b200rl_loss_coef(const int*, const double*, float*, int*, int, int, int, void*);
 int b200rl_loss_value(const float*, const int*, const double*, double*, int, int, int, void*);
+int b200rl_logprob_kl(void*, long long, const int*, const float*, const float*, const float*, float*, int, int, int, void*);
+int b200rl_loss_coef_kl(const int*, const double*, float*, float*, double, int*, int, int, int, void*);
+int b200rl_loss_value_kl(const float*, const int*, const double*, const float*, double, double*, int, int, int, void*);
 int b200rl_nf4_dequant(const void*, const float*, void*, int, int, int, void*);
 int b200rl_lora_pack(const float*, void*, const void*, int, int, void*);
 }
@@ -106,6 +109,21 @@ __global__ void grad_accum_kernel(float* __restrict__ flat, const AccumArgs a) {
     for (int s = 0; s < a.splits; ++s) acc += a.slabs[(long long)s * a.slab_stride + o];  // fixed order
     flat[d.dst_off + idx] += acc;
   }
+}
+
+// out[i] = bf16(sum_s slabs[s][i])  (fixed order; alpha was applied per slab by the GEMM epilogue)
+__global__ void reduce_slabs_bf16_kernel(const float* __restrict__ slabs, long long slab_stride, int splits,
+                                         bf16* __restrict__ out, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < splits; ++s) {
+    const float4 a = *reinterpret_cast<const float4*>(slabs + (long long)s * slab_stride + i * 8);
+    const float4 b = *reinterpret_cast<const float4*>(slabs + (long long)s * slab_stride + i * 8 + 4);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+  reinterpret_cast<bf16x8*>(out)[i] = pack8(acc);
 }
 
 __global__ void targets_kernel(const int* __restrict__ ids, int* __restrict__ targets, int L, int P,
@@ -153,7 +171,7 @@ struct b200rl_model {
   };
   std::vector<LayerAct> act;
   bf16 *wbuf, *xsel, *hsel, *logits, *dhsel, *dx, *dh, *dact, *dgu, *dattn, *dqkv, *du;
-  float *rstd_f, *lp, *coef, *delta, *slabs, *rope_cs;
+  float *rstd_f, *lp, *coef, *klw, *delta, *slabs, *rope_cs;
   int *targets, *lens;
   long long slab_elems;
   int rope_L;
@@ -241,7 +259,7 @@ static int dw_splits(int tokens, int Ny, int bn_cols) {
 struct WsPlan {
   long long total;
   long long off_arena, off_pack, off_X, off_wbuf, off_xsel, off_hsel, off_logits, off_dhsel, off_dx,
-      off_dh, off_dact, off_dgu, off_dattn, off_dqkv, off_du, off_rstd_f, off_lp, off_coef, off_delta,
+      off_dh, off_dact, off_dgu, off_dattn, off_dqkv, off_du, off_rstd_f, off_lp, off_coef, off_klw, off_delta,
       off_slabs, off_rope, off_targets, off_lens, off_layers;
   long long per_layer;
   long long slab_elems;
@@ -278,6 +296,7 @@ static WsPlan plan_ws(const b200rl_model* m) {
   p.off_rstd_f = take(R * 4);
   p.off_lp = take(R * 4);
   p.off_coef = take(R * 4);
+  p.off_klw = take(R * 4);
   p.off_delta = take((long long)c.max_batch * c.n_q_heads * c.max_seq * 4);
   long long nmax = std::max(std::max(QKV, 2 * I), std::max(H, I));
   p.slab_elems = 16 * std::max(nmax, (long long)128) * m->K2max;  // generous: <=16 splits
@@ -385,6 +404,7 @@ extern "C" int b200rl_model_create(const b200rl_model_config* cfg, const b200rl_
   m->rstd_f = (float*)(w + p.off_rstd_f);
   m->lp = (float*)(w + p.off_lp);
   m->coef = (float*)(w + p.off_coef);
+  m->klw = (float*)(w + p.off_klw);
   m->delta = (float*)(w + p.off_delta);
   m->slabs = (float*)(w + p.off_slabs);
   m->slab_elems = p.slab_elems;
@@ -503,6 +523,34 @@ int gemm_l(b200rl_model* m, int cat, int layout, cudaStream_t st, const bf16* A1
   a.M = M; a.N = N; a.mn_major = layout; a.splits = 1; a.c_split_stride = 0;
   a.force_bn = 0; a.max_ctas = 0;
   PM(cat, 2.0 * M * N * K1 + (K2 ? 2.0 * M * N * m->cfg.lora_r : 0.0));
+  if (cat == CAT_GEMM_SKINNY) {
+    // rank-r LoRA intermediates (N = K2 <= 192): only ceil(M/128) output tiles, so split K across CTAs
+    // into fp32 slabs (deterministic order) and reduce to bf16 in a second, tiny kernel
+    const int tiles = ((M + 127) / 128) * ((N + 127) / 128 > 1 ? (N + 127) / 128 : 1);
+    const int kb = (K1 + 63) / 64;
+    const int sms = num_sms();
+    int best_s = 1;
+    double best = 1e30;
+    for (int sp = 1; sp <= 8 && sp <= kb; ++sp) {
+      const double t = (double)((tiles * sp + sms - 1) / sms) / sp;
+      if (t < best - 1e-9) {
+        best = t;
+        best_s = sp;
+      }
+    }
+    const int per = (kb + best_s - 1) / best_s;
+    const int splits = (kb + per - 1) / per;
+    const long long stride = (long long)M * N;
+    if (splits > 1 && K2 == 0 && ldc == N && splits * stride <= m->slab_elems) {
+      a.C = m->slabs; a.c_fp32 = 1; a.splits = splits; a.c_split_stride = stride;
+      int rc = gemm_dispatch(a, st);
+      if (rc) return rc;
+      const long long n8 = stride / 8;
+      reduce_slabs_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(m->slabs, stride, splits, C, n8);
+      B200RL_LAUNCH_OK();
+      return 0;
+    }
+  }
   return gemm_dispatch(a, st);
 }
 
@@ -559,10 +607,11 @@ int lora_dw(b200rl_model* m, cudaStream_t st, const Group& g, const bf16* dY, lo
 
 }  // namespace
 
-extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const int* attn_mask,
-                                       const int* answer_mask, const double* adv, float* lp_out,
-                                       double* loss_accum, int B, int P, int T, int nb, int grpo,
-                                       int backward, void* stream) {
+extern "C" int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const int* attn_mask,
+                                          const int* answer_mask, const double* adv, float* lp_out,
+                                          double* loss_accum, int B, int P, int T, int nb, int grpo,
+                                          int backward, int lora_off, const float* ref_lp, double kl_beta,
+                                          void* stream) {
   B200RL_REQUIRE(m && ids && attn_mask && answer_mask, "model_microbatch: null pointer");
   const b200rl_model_config& c = m->cfg;
   const int L = P + T, M = B * L, R = B * T;
@@ -570,6 +619,9 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
   B200RL_REQUIRE(M <= c.max_tokens && B <= c.max_batch && L <= c.max_seq && R <= c.max_score_rows,
                  "model_microbatch: batch exceeds the workspace (B=%d L=%d)", B, L);
   B200RL_REQUIRE(!backward || (adv && nb >= 1), "model_microbatch: backward needs adv and nb");
+  B200RL_REQUIRE(!(backward && lora_off), "model_microbatch: the adapter-off (reference policy) pass is forward only");
+  B200RL_REQUIRE(kl_beta == 0.0 || ref_lp, "model_microbatch: kl_beta != 0 needs ref_lp");
+  const bool use_kl = backward && kl_beta != 0.0 && ref_lp;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int H = c.hidden, I = c.inter, QKV = m->QKV, QD = m->QD, V = c.vocab;
   const long long Mt = c.max_tokens;
@@ -581,6 +633,7 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
     m->rope_L = L;
   }
   // ---------------- forward ----------------
+  const bool lora = !lora_off;  // adapter-disabled pass = reference policy pi_ref (KL term)
   PM(CAT_ROW, 2.0 * M * H * 2);
   RC(b200rl_embed(ids, m->embed, m->X, M, H, V, stream));
   for (int l = 0; l < c.n_layers; ++l) {
@@ -595,33 +648,33 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
     bf16* xn = m->X + (long long)(l + 1) * Mt * H;
     PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(x, w.ln1_w, a.h1, a.rstd1, M, H, c.rms_eps, stream));
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
     PM(CAT_DEQUANT, 2.5625 * (QKV) * (H));
     RC(b200rl_nf4_dequant(w.qkv_packed, w.qkv_absmax, m->wbuf, QKV, H, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 0, st, a.h1, H, m->wbuf, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, gq.K2, a.qkv, QKV,
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.h1, H, m->wbuf, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, lora ? gq.K2 : 0, a.qkv, QKV,
                (const bf16*)w.qkv_bias, nullptr, 0, 1.f, M, QKV));
     PM(CAT_ROW, 2.0 * M * (c.n_q_heads + c.n_kv_heads) * c.head_dim * 2);
     RC(b200rl_rope(a.qkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 0, stream));
     PM(CAT_ATTN_FWD, 2.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
     RC(b200rl_attn_fwd(a.qkv, attn_mask, a.attn_o, a.lse, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
     PM(CAT_DEQUANT, 2.5625 * (H) * (QD));
     RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 0, st, a.attn_o, QD, m->wbuf, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, go.K2, a.x_mid, H,
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.attn_o, QD, m->wbuf, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, lora ? go.K2 : 0, a.x_mid, H,
                nullptr, x, H, 1.f, M, H));
     PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(a.x_mid, w.ln2_w, a.h2, a.rstd2, M, H, c.rms_eps, stream));
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
     PM(CAT_DEQUANT, 2.5625 * (2 * I) * (H));
     RC(b200rl_nf4_dequant(w.gu_packed, w.gu_absmax, m->wbuf, 2 * I, H, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, m->wbuf, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, gg.K2, a.gu, 2 * I,
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, m->wbuf, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, lora ? gg.K2 : 0, a.gu, 2 * I,
                nullptr, nullptr, 0, 1.f, M, 2 * I));
     PM(CAT_ROW, 3.0 * M * I * 2);
     RC(b200rl_swiglu_fwd(a.gu, a.act, M, I, stream));
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
     PM(CAT_DEQUANT, 2.5625 * (H) * (I));
     RC(b200rl_nf4_dequant(w.down_packed, w.down_absmax, m->wbuf, H, I, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 0, st, a.act, I, m->wbuf, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, gd.K2, xn, H, nullptr,
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.act, I, m->wbuf, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, lora ? gd.K2 : 0, xn, H, nullptr,
                a.x_mid, H, 1.f, M, H));
   }
   // head: only the T scored positions (rows P-1 .. L-2) go through the final norm and lm_head
@@ -635,12 +688,14 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
   targets_kernel<<<(R + 255) / 256, 256, 0, st>>>(ids, m->targets, L, P, T, R);
   B200RL_LAUNCH_OK();
   PM(CAT_MISC, 0);
-  if (backward) RC(b200rl_loss_coef(answer_mask, adv, m->coef, m->lens, B, T, nb, stream));
+  if (backward) RC(b200rl_loss_coef_kl(answer_mask, adv, m->coef, use_kl ? m->klw : nullptr, kl_beta, m->lens, B, T, nb, stream));
   float* lp = lp_out ? lp_out : m->lp;
   PM(CAT_LOGPROB, (backward ? 2.0 : 1.0) * R * V * 2);
-  RC(b200rl_logprob(m->logits, V, m->targets, backward ? m->coef : nullptr, lp, R, V, backward ? 1 : 0, stream));
+  RC(b200rl_logprob_kl(m->logits, V, m->targets, backward ? m->coef : nullptr, use_kl ? m->klw : nullptr,
+                       use_kl ? ref_lp : nullptr, lp, R, V, backward ? 1 : 0, stream));
   PM(CAT_MISC, 0);
-  if (loss_accum && adv) RC(b200rl_loss_value(lp, answer_mask, adv, loss_accum, B, T, grpo, stream));
+  if (loss_accum && adv)
+    RC(b200rl_loss_value_kl(lp, answer_mask, adv, use_kl ? ref_lp : nullptr, use_kl ? kl_beta : 0.0, loss_accum, B, T, grpo, stream));
   if (!backward) {
     PM(CAT_END, 0);
     return 0;
@@ -733,4 +788,12 @@ extern "C" int b200rl_model_profile_read(b200rl_model* m, double* ms, double* wo
   }
   m->prof_n = 0;
   return 0;
+}
+
+extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const int* attn_mask,
+                                       const int* answer_mask, const double* adv, float* lp_out,
+                                       double* loss_accum, int B, int P, int T, int nb, int grpo,
+                                       int backward, void* stream) {
+  return b200rl_model_microbatch_ex(m, ids, attn_mask, answer_mask, adv, lp_out, loss_accum, B, P, T, nb, grpo,
+                                    backward, 0, nullptr, 0.0, stream);
 }

@@ -71,6 +71,7 @@ class BaseLearner:
         self.max_prompt_tokens = config["max_prompt_tokens"]      # :213
         self.lr = config["lr"]                                    # :210
         self.weight_decay = config.get("weight_decay", 0.0)       # commented out in the reference (:210)
+        self.kl_beta = float(config.get("kl_beta", 0.0))          # KL-to-reference weight; 0 = reference behaviour
         self.lora_save_path = config.get("lora_save_path", "lora_request_math")
         self.reference_quirks = reference_quirks
         self.generator = generator
@@ -119,8 +120,15 @@ class BaseLearner:
             if self.reference_quirks and not bool(np.all(r != 0)):
                 continue
             ids, am, ansm = self._encode(messages[s:e], answers[s:e])
-            pol.microbatch(self._h2d(ids), self._h2d(am), self._h2d(ansm), self._h2d(torch.from_numpy(r)),
-                           self.max_prompt_tokens, self.max_new_tokens, nb, grpo, backward=True)
+            d_ids, d_am, d_ansm = self._h2d(ids), self._h2d(am), self._h2d(ansm)
+            ref_lp = None
+            if self.kl_beta != 0.0:
+                # reference policy = the frozen base with the adapter disabled (one extra forward, no backward)
+                ref_lp = torch.empty(e - s, self.max_new_tokens, device=pol.device, dtype=torch.float32)
+                pol.microbatch(d_ids, d_am, d_ansm, None, self.max_prompt_tokens, self.max_new_tokens, 1, False,
+                               backward=False, lp_out=ref_lp, lora_off=True)
+            pol.microbatch(d_ids, d_am, d_ansm, self._h2d(torch.from_numpy(r)), self.max_prompt_tokens,
+                           self.max_new_tokens, nb, grpo, backward=True, ref_lp=ref_lp, kl_beta=self.kl_beta)
         return float(pol.loss_accum.item())   # sum of per-micro-batch losses (quirk Q2), one sync
 
     # ---- gradient export / merge (:283-333) --------------------------------------------------------

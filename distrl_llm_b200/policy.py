@@ -222,13 +222,16 @@ class Policy:
     def sync_lora(self):
         check(lib().b200rl_model_sync_lora(self.handle, stream()), "model_sync_lora")
 
-    def microbatch(self, ids, attn_mask, answer_mask, adv, P, T, nb, grpo, backward, lp_out=None):
+    def microbatch(self, ids, attn_mask, answer_mask, adv, P, T, nb, grpo, backward, lp_out=None,
+                   lora_off=False, ref_lp=None, kl_beta=0.0):
         """One micro-batch through the C++ driver. ids/attn_mask [B, P+T] int32, answer_mask [B,T] int32,
-        adv [B] float64 (all on this device). Accumulates into lora_grad and self.loss_accum."""
+        adv [B] float64 (all on this device). Accumulates into lora_grad and self.loss_accum.
+        lora_off: adapter-disabled scoring pass (reference policy); ref_lp + kl_beta: optional KL term."""
         B = ids.shape[0]
-        check(lib().b200rl_model_microbatch(self.handle, ptr(ids), ptr(attn_mask), ptr(answer_mask), ptr(adv),
-                                            ptr(lp_out), ptr(self.loss_accum), B, P, T, nb, 1 if grpo else 0,
-                                            1 if backward else 0, stream()), "model_microbatch")
+        check(lib().b200rl_model_microbatch_ex(self.handle, ptr(ids), ptr(attn_mask), ptr(answer_mask), ptr(adv),
+                                               ptr(lp_out), ptr(self.loss_accum), B, P, T, nb, 1 if grpo else 0,
+                                               1 if backward else 0, 1 if lora_off else 0, ptr(ref_lp),
+                                               float(kl_beta), stream()), "model_microbatch")
 
     def debug_tensor(self, name, layer, shape, dtype=torch.bfloat16):
         p = lib().b200rl_model_debug_ptr(self.handle, name.encode(), layer)

@@ -74,6 +74,15 @@ int b200rl_loss_coef(const int* mask, const double* adv, float* coef, int* lens,
                      int nb, void* stream);
 int b200rl_loss_value(const float* lp, const int* mask, const double* adv, double* accum, int Bm,
                       int T, int grpo, void* stream);
+/* variants with the optional KL(pi || pi_ref) term (k3 estimator exp(q-p)-(q-p)-1 per token, weight beta, same
+ * mask / length / batch normalisation as the policy term).  NOT in the reference (its GRPO loss has no KL,
+ * distributed_actor.py:467-470): beta = 0 reproduces it exactly; "parity unpinned". */
+int b200rl_logprob_kl(void* logits, long long ld, const int* targets, const float* coef, const float* klw,
+                      const float* ref_lp, float* lp_out, int rows, int V, int write_grad, void* stream);
+int b200rl_loss_coef_kl(const int* mask, const double* adv, float* coef, float* klw, double beta, int* lens,
+                        int Bm, int T, int nb, void* stream);
+int b200rl_loss_value_kl(const float* lp, const int* mask, const double* adv, const float* ref_lp, double beta,
+                         double* accum, int Bm, int T, int grpo, void* stream);
 
 /* ---- G9: group-relative advantages + top-k (distributed_trainer.py:262-294) ---------------- */
 int b200rl_group_advantage_topk(const double* rewards, double* values, double* baselines,
@@ -150,6 +159,13 @@ int b200rl_model_microbatch(b200rl_model* m, const int* ids, const int* attn_mas
                             const int* answer_mask, const double* adv, float* lp_out,
                             double* loss_accum, int B, int P, int T, int nb, int grpo, int backward,
                             void* stream);
+
+/* extended form: lora_off=1 runs the adapter-disabled forward (reference policy pi_ref, scoring only);
+ * ref_lp [B,T] + kl_beta add the KL term to the loss and its gradient. */
+int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const int* attn_mask,
+                               const int* answer_mask, const double* adv, float* lp_out,
+                               double* loss_accum, int B, int P, int T, int nb, int grpo, int backward,
+                               int lora_off, const float* ref_lp, double kl_beta, void* stream);
 
 /* per-op CUDA-event profiling of the driver (categories: 0 gemm, 1 skinny LoRA gemm, 2 dW gemm, 3 nf4
  * dequant, 4 attn fwd, 5 attn bwd, 6 row kernels, 7 logprob, 8 misc); read() returns sums since the last

@@ -106,14 +106,14 @@ def _lora_linear(x, W, b, A, B, s):
 
 
 def model_forward(params: dict, cfg: OracleConfig, ids: torch.Tensor, attn_mask: torch.Tensor,
-                  dtype=torch.float32) -> torch.Tensor:
+                  dtype=torch.float32, lora_off=False) -> torch.Tensor:
     """Logits [B, L, V].  `params`: base tensors ('embed','final_norm','lm_head', 'l{i}.wq' ...,
     'l{i}.bq'/bk/bv, 'l{i}.ln1/ln2') and LoRA tensors 'l{i}.{mod}.A' [r,in] / '.B' [out,r].
     position_ids = arange(L) even under left padding (reference passes none, distributed_actor.py:241-243;
     transformers Qwen2Model.forward builds arange)."""
     B, L = ids.shape
     dev = ids.device
-    s = cfg.lora_scale
+    s = 0.0 if lora_off else cfg.lora_scale  # lora_off: adapter disabled = reference policy of the KL term
     hd, nq, nkv = cfg.head_dim, cfg.n_q_heads, cfg.n_kv_heads
     p = lambda name: params[name].to(dtype) if params[name].dtype.is_floating_point else params[name]
     x = p("embed")[ids]
@@ -167,11 +167,11 @@ def pad_batch(prompt_ids, answer_ids, P, T, pad_id=0):
     return torch.from_numpy(ids), torch.from_numpy(mask), torch.from_numpy(mask[:, P:].copy())
 
 
-def compute_current_policy_probs(params, cfg, ids, attn_mask, P, dtype=torch.float32):
+def compute_current_policy_probs(params, cfg, ids, attn_mask, P, dtype=torch.float32, lora_off=False):
     """distributed_actor.py:241-261: logits -> shift (:245-246) -> slice to the answer (:248-249) ->
     per-row log_softmax + gather (:252-259).  Returns action_log_probs [B, T] (fp32 like autocast's
     log_softmax)."""
-    logits = model_forward(params, cfg, ids, attn_mask, dtype)
+    logits = model_forward(params, cfg, ids, attn_mask, dtype, lora_off)
     logits = logits[:, :-1, :]
     targets = ids[:, 1:]
     logits = logits[:, P - 1:]
@@ -181,7 +181,7 @@ def compute_current_policy_probs(params, cfg, ids, attn_mask, P, dtype=torch.flo
 
 
 def compute_loss(params, cfg, ids, attn_mask, answer_mask, rewards, P, train_batch_size, learner="pg",
-                 dtype=torch.float32, reference_quirks=True):
+                 dtype=torch.float32, reference_quirks=True, kl_beta=0.0):
     """Learner.compute_loss (distributed_actor.py:349-395) / GRPOLearner.compute_loss (:440-493).
     Accumulates .grad on the LoRA tensors of `params` (those with requires_grad) and returns the float
     the reference returns: the SUM over micro-batches of the per-micro-batch mean loss (quirk Q2)."""
@@ -201,7 +201,15 @@ def compute_loss(params, cfg, ids, attn_mask, answer_mask, rewards, P, train_bat
         else:
             imp = torch.exp(lp - lp.detach())  # :467
             per_seq = (imp * m).sum(-1) / m.sum(-1)  # :470
-        loss = -(per_seq * r).mean() / nb  # :375+:382 / :470+:479
+        loss = -(per_seq * r).mean()
+        if kl_beta:
+            # NOT in the reference (parity unpinned): KL(pi||pi_ref) with the k3 estimator, pi_ref = adapter off,
+            # normalised exactly like the policy term (mask, /len, mean over the micro-batch)
+            with torch.no_grad():
+                q = compute_current_policy_probs(params, cfg, ids[sl], attn_mask[sl], P, dtype, lora_off=True)
+            d = q - lp
+            loss = loss + kl_beta * (((torch.exp(d) - d - 1) * m).sum(-1) / m.sum(-1)).mean()
+        loss = loss / nb  # :375+:382 / :470+:479
         loss.backward()  # :385 / :483
         total += loss.item() * nb  # :387-389 / :485-487
     return total

@@ -179,3 +179,28 @@ def test_train_step_updates_like_adam(cuda):
     assert torch.allclose(ln.policy.lora_flat, refp.data, rtol=1e-6, atol=1e-9)
     lp1, mask = ln.compute_current_policy_probs(ln.policy, prompts, answers)
     assert (lp1 - lp0)[mask.bool()].abs().max() > 1e-4  # adapter change is visible to the next forward
+
+
+def test_kl_term_vs_oracle(cuda):
+    """Optional KL(pi || pi_ref) term (north_star; absent from the reference => oracle restates OUR definition,
+    'parity unpinned'): pi_ref = adapter-disabled forward, k3 estimator, beta = 0.2."""
+    ocfg = lo.OracleConfig(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=64,
+                           lora_r=16, lora_alpha=32)
+    params, nf4 = lo.make_params(ocfg, seed=21, lora_b_std=0.05)   # larger B so that pi differs visibly from pi_ref
+    N, P, T, B, beta = 6, 12, 36, 3, 0.2
+    prompts, answers, rewards = lo.make_batch(ocfg, N, P, T, seed=5, ragged=True, group_size=N, learner="grpo")
+    dparams = {k: (v.detach().to(cuda).requires_grad_(v.requires_grad)) for k, v in params.items()}
+    ids, am, ansm = lo.pad_batch(prompts, answers, P, T)
+    ref_grads, ref_loss = lo.compute_gradients(dparams, ocfg, ids.to(cuda), am.to(cuda), ansm.to(cuda), rewards, P, B,
+                                               "grpo", kl_beta=beta)
+    g0, loss0 = lo.compute_gradients(dparams, ocfg, ids.to(cuda), am.to(cuda), ansm.to(cuda), rewards, P, B, "grpo")
+    assert abs(ref_loss - loss0) > 1e-5, "the KL term must be active in this test"
+    ln = _mk_learner("grpo", ocfg, params, nf4, P, T, B, cuda)
+    ln.kl_beta = beta
+    grads, loss = ln._compute_gradients(prompts, answers, list(rewards))
+    assert abs(loss - ref_loss) <= 5e-2 * abs(ref_loss - loss0) + 2e-3, (loss, ref_loss, loss0)
+    _compare_grads(grads, ref_grads, ocfg, ln.policy)
+    # and beta = 0 falls back to the reference loss exactly (GRPO loss value = -mean(adv))
+    ln.kl_beta = 0.0
+    _, loss_b0 = ln._compute_gradients(prompts, answers, list(rewards))
+    assert abs(loss_b0 - loss0) < 1e-9
