@@ -13,6 +13,7 @@
 // out/dout [B*L, nq*hd] bf16, lse2 [B, nq, L] fp32 = log2-sum-exp2 of the scaled scores
 // (+inf for rows with no visible key, which makes every probability of that row exactly 0).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b200rl {
 
@@ -631,9 +632,38 @@ static int attn_bwd_launch(const void* qkv, const int* key_mask, const void* out
   return 0;
 }
 
+// tcgen05 forward (attention_tc.cu), head_dim 128
+int attn_fwd_tc_launch(const void* qkv, const int* key_mask, void* out, float* lse, int B, int L, int nq, int nkv,
+                       float scale, cudaStream_t stream);
+int attn_bwd_tc_launch(const void* qkv, const int* key_mask, const void* dout, const float* lse, const float* delta,
+                       void* dqkv, int B, int L, int nq, int nkv, float scale, cudaStream_t stream);
+static int attn_bwd_tc(const void* qkv, const int* key_mask, const void* out, const void* dout, const float* lse,
+                       float* delta, void* dqkv, int B, int L, int nq, int nkv, float scale, cudaStream_t stream) {
+  const long long rows = (long long)B * L;
+  const long long warps = rows * nq;
+  attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, L, nq,
+                                                                      128, rows);
+  B200RL_LAUNCH_OK();
+  return attn_bwd_tc_launch(qkv, key_mask, dout, lse, delta, dqkv, B, L, nq, nkv, scale, stream);
+}
+static int g_attn_tc = -1;
+static bool attn_tc_enabled() {
+  if (g_attn_tc < 0) {
+    const char* e = getenv("B200RL_ATTN_TC");
+    g_attn_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_attn_tc != 0;
+}
+
 }  // namespace b200rl
 
 using namespace b200rl;
+
+// bisection switch: 1 (default) = tcgen05 attention kernels where available (head_dim 128), 0 = mma.sync kernels
+extern "C" int b200rl_attn_set_tc(int enable) {
+  b200rl::g_attn_tc = enable ? 1 : 0;
+  return 0;
+}
 
 extern "C" int b200rl_attn_fwd(const void* qkv, const int* key_mask, void* out, float* lse, int B,
                                int L, int n_q_heads, int n_kv_heads, int head_dim, float scale,
@@ -644,7 +674,9 @@ extern "C" int b200rl_attn_fwd(const void* qkv, const int* key_mask, void* out, 
   switch (head_dim) {
     case 32: return attn_fwd_launch<32>(qkv, key_mask, out, lse, B, L, n_q_heads, n_kv_heads, scale, st);
     case 64: return attn_fwd_launch<64>(qkv, key_mask, out, lse, B, L, n_q_heads, n_kv_heads, scale, st);
-    case 128: return attn_fwd_launch<128>(qkv, key_mask, out, lse, B, L, n_q_heads, n_kv_heads, scale, st);
+    case 128:
+      if (attn_tc_enabled()) return attn_fwd_tc_launch(qkv, key_mask, out, lse, B, L, n_q_heads, n_kv_heads, scale, st);
+      return attn_fwd_launch<128>(qkv, key_mask, out, lse, B, L, n_q_heads, n_kv_heads, scale, st);
     default: return set_error(B200RL_ERR_UNSUPPORTED, "attn: head_dim %d not in {32,64,128}", head_dim);
   }
 }
@@ -659,7 +691,9 @@ extern "C" int b200rl_attn_bwd(const void* qkv, const int* key_mask, const void*
   switch (head_dim) {
     case 32: return attn_bwd_launch<32>(qkv, key_mask, out, dout, lse, delta, dqkv, B, L, n_q_heads, n_kv_heads, scale, st);
     case 64: return attn_bwd_launch<64>(qkv, key_mask, out, dout, lse, delta, dqkv, B, L, n_q_heads, n_kv_heads, scale, st);
-    case 128: return attn_bwd_launch<128>(qkv, key_mask, out, dout, lse, delta, dqkv, B, L, n_q_heads, n_kv_heads, scale, st);
+    case 128:
+      if (attn_tc_enabled()) return attn_bwd_tc(qkv, key_mask, out, dout, lse, delta, dqkv, B, L, n_q_heads, n_kv_heads, scale, st);
+      return attn_bwd_launch<128>(qkv, key_mask, out, dout, lse, delta, dqkv, B, L, n_q_heads, n_kv_heads, scale, st);
     default: return set_error(B200RL_ERR_UNSUPPORTED, "attn: head_dim %d not in {32,64,128}", head_dim);
   }
 }

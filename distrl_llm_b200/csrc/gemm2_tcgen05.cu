@@ -144,8 +144,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+      int m_blk, n_blk;
+      tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
       const int row0 = m_blk * BM2 + (int)rank * BM;
       const int col0 = n_blk * BN + (int)rank * C::BH;
       for (int kb = 0; kb < kb_total; ++kb) {
@@ -211,8 +211,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const int quad = warp & 3;
     int local = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+      int m_blk, n_blk;
+      tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);

@@ -47,6 +47,20 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 }
 
 
+// Tile rasterisation: groups of GM m-blocks sweep all n-blocks before the next group, so the ~74-148 tiles in
+// flight form a compact (GM x ~9..18) patch of C and share both A and B tiles through L2 (ncu on the m-fastest
+// order: 3.2-4.4x DRAM read amplification on the MLP GEMMs, A = 261 MB does not fit the 126 MB L2).
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+  constexpr int GM = 8;
+  const int per_group = GM * num_n;
+  const int group = tile / per_group;
+  const int first_m = group * GM;
+  const int gm = min(num_m - first_m, GM);
+  const int in_group = tile - group * per_group;
+  m_blk = first_m + in_group % gm;
+  n_blk = in_group / gm;
+}
+
 // epilogue shared by both kernels: 32 accumulator columns of one row -> alpha / bias / residual -> global
 __device__ __forceinline__ void epilogue_store32(const GemmParams& p, const uint32_t* r, int row, int col0,
                                                  int split) {

@@ -85,10 +85,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int rest = tile / p.num_m_blocks;
-      const int n_blk = rest % p.num_n_blocks;
-      const int split = rest / p.num_n_blocks;
+      const int mn = p.num_m_blocks * p.num_n_blocks;
+      const int split = tile / mn;
+      int m_blk, n_blk;
+      tile_coords(tile - split * mn, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
       const int kb_begin = split * p.kb_per_split;
       const int kb_end = min(kb_begin + p.kb_per_split, kb_total);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -129,8 +129,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     uint32_t phase = 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const int rest = tile / p.num_m_blocks;
-      const int split = rest / p.num_n_blocks;
+      const int split = tile / (p.num_m_blocks * p.num_n_blocks);
       const int kb_begin = split * p.kb_per_split;
       const int kb_end = min(kb_begin + p.kb_per_split, kb_total);
       const int acc = local & 1;
@@ -167,10 +166,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int rest = tile / p.num_m_blocks;
-      const int n_blk = rest % p.num_n_blocks;
-      const int split = rest / p.num_n_blocks;
+      const int mn = p.num_m_blocks * p.num_n_blocks;
+      const int split = tile / mn;
+      int m_blk, n_blk;
+      tile_coords(tile - split * mn, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);

@@ -344,9 +344,18 @@ def _attn_ref(qkv, key_mask, B, L, nq, nkv, hd):
     return o.permute(0, 2, 1, 3).reshape(B * L, nq * hd)
 
 
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "mma_sync"])
+def attn_mode(request, cuda):
+    from distrl_llm_b200 import _capi
+    _capi.lib().b200rl_attn_set_tc(request.param)
+    yield request.param
+    _capi.lib().b200rl_attn_set_tc(1)
+
+
 @pytest.mark.parametrize("B,L,nq,nkv,hd", [(2, 48, 4, 2, 32), (2, 200, 4, 2, 64), (1, 333, 14, 2, 128),
-                                            (3, 64, 4, 4, 128), (2, 130, 7, 1, 128)])
-def test_attention(cuda, B, L, nq, nkv, hd):
+                                            (3, 64, 4, 4, 128), (2, 130, 7, 1, 128), (2, 862, 4, 2, 128),
+                                            (1, 1024, 2, 1, 128)])
+def test_attention(cuda, attn_mode, B, L, nq, nkv, hd):
     from distrl_llm_b200 import ops
     qkv = _rand((B * L, (nq + 2 * nkv) * hd), cuda, seed=1)
     key_mask = torch.ones(B, L, dtype=torch.int32, device=cuda)
