@@ -57,12 +57,14 @@ struct FwdParams {
   float scale_log2;
 };
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], s_empty[2], o_full[2], o_empty[2], p_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ int s_mask[2][BKV];
+  __shared__ uint32_t s_maskw[2][4];     // key-padding bitmask of the 128 keys of a block
+  __shared__ float s_mx[2][2][BQ];       // [stage][warpgroup][row] partial row max
+  __shared__ float s_l[2][BQ];           // [warpgroup][row] partial row sums (final combine)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -83,11 +85,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 128);
+      mbar_init(&s_empty[s], 256);
       mbar_init(&o_full[s], 1);
-      mbar_init(&o_empty[s], 128);
+      mbar_init(&o_empty[s], 256);
     }
-    mbar_init(&p_full, 128);
+    mbar_init(&p_full, 256);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tm);
@@ -158,28 +160,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
     }
     issue_pv(n_kb - 1);
   } else if (warp >= 4) {
-    // ===================== softmax / output (one query row per thread) =====================
+    // ===================== softmax / output =====================
+    // two warpgroups share every query row: warpgroup wg owns keys [64 wg, 64 wg + 64) of each block (one
+    // swizzle atom of the P tile) and output columns d in [64 wg, 64 wg + 64); TMEM lane = row for both
+    const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
-    const int r = quad * 32 + lane;       // row in the tile == TMEM lane
-    const int t = threadIdx.x - 128;      // 0..127 among the softmax threads
+    const int r = quad * 32 + lane;
     const int q = q0 + r;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    float o[HD];
+    float o[64];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
 
-    auto absorb = [&](int j, float corr) {  // O_reg = O_reg * corr + O_j
+    auto absorb = [&](int j, float corr) {  // O_reg = O_reg * corr + O_j   (own 64 columns)
       const int st = j & 1;
       mbar_wait(&o_full[st], (j >> 1) & 1);
       tc_fence_after();
+      uint32_t a0[32], a1[32];
+      const uint32_t to = tmem_base + 256 + st * 128 + lane_addr + wg * 64;
+      tmem_ld_32x32(to, a0);
+      tmem_ld_32x32(to + 32, a1);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + 256 + st * 128 + lane_addr + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * corr + __uint_as_float(v[i]);
+      for (int i = 0; i < 32; ++i) {
+        o[i] = o[i] * corr + __uint_as_float(a0[i]);
+        o[32 + i] = o[32 + i] * corr + __uint_as_float(a1[i]);
       }
       tc_fence_before();
       mbar_arrive(&o_empty[st]);
@@ -188,54 +194,70 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
       const int k0 = j * BKV;
-      // key-padding mask of this block (shared by the 128 rows)
-      s_mask[st][t] = (k0 + t < p.L) ? p.key_mask[(long long)b * p.L + k0 + t] : 0;
-      named_bar_sync(1, 128);
+      if (wg == 0) {  // key-padding bitmask of this block
+        const int mk = (k0 + r < p.L) ? p.key_mask[(long long)b * p.L + k0 + r] : 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, mk != 0);
+        if (lane == 0) s_maskw[st][quad] = bal;
+      }
+      named_bar_sync(1, 256);
+      const uint32_t w0 = s_maskw[st][2 * wg], w1 = s_maskw[st][2 * wg + 1];
+      const bool diag = (j == qb);                                   // only the diagonal block needs key <= q
+      const bool plain = !diag && (w0 & w1) == 0xFFFFFFFFu;          // no masking at all (the common case)
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t ts = tmem_base + st * 128 + lane_addr;
-      // ---- pass 1: row max ----
+      const uint32_t ts = tmem_base + st * 128 + lane_addr + wg * 64;
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(ts, v0);
+      tmem_ld_32x32(ts + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[st]);  // scores are in registers: S[st] may be overwritten by QK_{j+2}
+      const int kbase = k0 + wg * 64;
+      // ---- row max over the own 64 keys, then exchange with the other warpgroup ----
       float mx = -INFINITY;
+      if (plain) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(ts + c * 32, v);
-        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+        mx *= p.scale_log2;  // scale > 0
+      } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int key = k0 + c * 32 + i;
-          const bool ok = key <= q && s_mask[st][c * 32 + i] != 0;
-          mx = fmaxf(mx, ok ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY);
+          const bool ok0 = ((w0 >> i) & 1u) && (!diag || kbase + i <= q);
+          const bool ok1 = ((w1 >> i) & 1u) && (!diag || kbase + 32 + i <= q);
+          const float a = ok0 ? __uint_as_float(v0[i]) * p.scale_log2 : -INFINITY;
+          const float c = ok1 ? __uint_as_float(v1[i]) * p.scale_log2 : -INFINITY;
+          v0[i] = __float_as_uint(a);  // keep the masked, scaled score
+          v1[i] = __float_as_uint(c);
+          mx = fmaxf(mx, fmaxf(a, c));
         }
       }
+      s_mx[st][wg][r] = mx;
+      named_bar_sync(2, 256);
+      mx = fmaxf(mx, s_mx[st][wg ^ 1][r]);
       const float m_new = fmaxf(m_run, mx);
       const float mu = (m_new == -INFINITY) ? 0.f : m_new;
       const float corr = exp2f(m_run - mu);
       // fold the previous block's P.V into the register accumulator (also guarantees the previous P.V has
       // finished reading the P tile before it is overwritten below)
       if (j > 0) absorb(j - 1, corr_prev);
-      // ---- pass 2: p = exp2(s - m) -> bf16 P tile (K-major, 128B swizzle) ----
+      // ---- p = exp2(s - m) -> bf16 into this warpgroup's 64-key atom of the P tile ----
       float rs = 0.f;
+      const uint32_t prow = sP + wg * (TILE_BYTES / 2) + r * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(ts + c * 32, v);
-        tmem_ld_wait();
+      for (int half = 0; half < 2; ++half) {
         float pf[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int key = k0 + c * 32 + i;
-          const bool ok = key <= q && s_mask[st][c * 32 + i] != 0;
-          const float pv = ok ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - mu) : 0.f;
+          const float sv = __uint_as_float(half == 0 ? v0[i] : v1[i]);
+          const float pv = plain ? exp2f(sv * p.scale_log2 - mu) : exp2f(sv - mu);  // masked -> exp2(-inf) = 0
           pf[i] = pv;
           rs += pv;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int cc = c * 4 + u;  // 16-byte chunk index along the 128 keys (0..15)
-          const uint32_t addr = sP + (cc >> 3) * (TILE_BYTES / 2) + r * 128 + (((cc & 7) ^ (r & 7)) << 4);
+          const int cc = half * 4 + u;  // 16-byte chunk 0..7 within the 128-byte row of the atom
           const bf16x8 pk = pack8(&pf[u * 8]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((cc ^ (r & 7)) << 4)),
                        "r"(*reinterpret_cast<const uint32_t*>(&pk.v[0])),
                        "r"(*reinterpret_cast<const uint32_t*>(&pk.v[1])),
                        "r"(*reinterpret_cast<const uint32_t*>(&pk.v[2])),
@@ -246,20 +268,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
       l_run = l_run * corr + rs;
       m_run = m_new;
       corr_prev = corr;
-      tc_fence_before();
-      mbar_arrive(&s_empty[st]);      // S[st] may be overwritten by QK_{j+2}
-      fence_proxy_async_smem();       // P tile visible to the tensor core (async proxy)
+      fence_proxy_async_smem();  // P tile visible to the tensor core (async proxy)
       mbar_arrive(&p_full);
     }
     // corr bookkeeping: O_reg before absorbing block j is relative to m_{j-1}; corr_j = exp2(m_{j-1} - m_j) was
     // computed when block j's scores were processed and O_j (from P_j) is relative to m_j.
     absorb(n_kb - 1, corr_prev);
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    s_l[wg][r] = l_run;
+    named_bar_sync(3, 256);
+    const float l_tot = l_run + s_l[wg ^ 1][r];
+    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
     if (q < p.L) {
-      p.lse2[((long long)b * p.nq + h) * p.L + q] = l_run > 0.f ? m_run + log2f(l_run) : INFINITY;
-      bf16* dst = p.out + ((long long)b * p.L + q) * p.nq * HD + h * HD;
+      if (wg == 0) p.lse2[((long long)b * p.nq + h) * p.L + q] = l_tot > 0.f ? m_run + log2f(l_tot) : INFINITY;
+      bf16* dst = p.out + ((long long)b * p.L + q) * p.nq * HD + h * HD + wg * 64;
 #pragma unroll
-      for (int i = 0; i < HD; i += 8) {
+      for (int i = 0; i < 64; i += 8) {
         float f[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) f[u] = o[i + u] * inv;
@@ -275,7 +298,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
     tmem_dealloc(tmem_base, 512);
   }
 }
-
 
 // ==================================================================================================
 // BACKWARD on tcgen05.  Deterministic two-kernel split like the mma.sync version:
@@ -321,7 +343,7 @@ __device__ __forceinline__ void store_row32_sw128(uint32_t tile, int r, int col0
 // ---------------------------------------------------------------------------------------------------
 // dQ
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_do128,
                       const __grid_constant__ CUtensorMap tm_kv64, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -346,8 +368,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
       mbar_init(&sp_full[s], 1);
-      mbar_init(&sp_empty[s], 128);
-      mbar_init(&ds_full[s], 128);
+      mbar_init(&sp_empty[s], 256);
+      mbar_init(&ds_full[s], 256);
       mbar_init(&ds_empty[s], 1);
     }
     fence_barrier_init();
@@ -427,7 +449,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     issue_dq(n_kb - 1);
     umma_commit(&dq_full);
   } else if (warp >= 4) {
-    // ===================== dS producer: one query row per thread =====================
+    // ===================== dS producer: two warpgroups, each 32 of the 64 keys of a block =====================
+    const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const int t = threadIdx.x - 128;
@@ -440,16 +463,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
       const int st = j & 1;
       const int k0 = j * 64;
       if (t < 64) s_mask[st][t] = (k0 + t < p.L) ? p.key_mask[(long long)b * p.L + k0 + t] : 0;
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(&sp_full[st], (j >> 1) & 1);
       mbar_wait(&ds_empty[st], ((j >> 1) & 1) ^ 1u);  // dQ MMA of block j-2 finished reading dS[st]
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = wg;
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tmem_base + st * 64 + lane_addr + c * 32, sv);
         tmem_ld_32x32(tmem_base + 128 + st * 64 + lane_addr + c * 32, dv);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&sp_empty[st]);
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -460,36 +485,29 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
         }
         store_row32_sw128(sDS + st * HALF_TILE, r, c * 32, f);
       }
-      tc_fence_before();
-      mbar_arrive(&sp_empty[st]);
       fence_proxy_async_smem();
       mbar_arrive(&ds_full[st]);
     }
     // ---- write dQ ----
     mbar_wait(&dq_full, 0);
     tc_fence_after();
-    if (q < p.L) {
-      bf16* dst = p.dqkv + ((long long)b * p.L + q) * (long long)(p.nq + 2 * p.nkv) * HD + h * HD;
+    {
+      // the TMEM loads are .sync.aligned: every lane executes them, only the stores are predicated
+      bf16* dst = p.dqkv + ((long long)b * p.L + (q < p.L ? q : 0)) * (long long)(p.nq + 2 * p.nkv) * HD + h * HD;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * wg; c < 2 * wg + 2; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + 256 + lane_addr + c * 32, v);
         tmem_ld_wait();
+        if (q < p.L) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float f[8];
+          for (int u = 0; u < 4; ++u) {
+            float f[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[u * 8 + i]);
-          *reinterpret_cast<bf16x8*>(dst + c * 32 + u * 8) = pack8(f);
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[u * 8 + i]);
+            *reinterpret_cast<bf16x8*>(dst + c * 32 + u * 8) = pack8(f);
+          }
         }
-      }
-    } else {
-      // keep the warp converged on the .sync.aligned TMEM loads
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + 256 + lane_addr + c * 32, v);
-        tmem_ld_wait();
       }
     }
   }
@@ -504,7 +522,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
 // ---------------------------------------------------------------------------------------------------
 // dK, dV
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_constant__ CUtensorMap tm_q64,
                        const __grid_constant__ CUtensorMap tm_do64, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -530,8 +548,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       mbar_init(&qd_full[s], 1);
       mbar_init(&qd_empty[s], 1);
       mbar_init(&sp_full[s], 1);
-      mbar_init(&sp_empty[s], 128);
-      mbar_init(&ds_full[s], 128);
+      mbar_init(&sp_empty[s], 256);
+      mbar_init(&ds_full[s], 256);
       mbar_init(&ds_empty[s], 1);
     }
     fence_barrier_init();
@@ -617,7 +635,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     if (n_it > 0) issue_grad(n_it - 1);
     umma_commit(&out_full);
   } else if (warp >= 4) {
-    // ===================== P^T / dS^T producer: one KEY row per thread =====================
+    // ===================== P^T / dS^T producer: one KEY row per thread, two warpgroups x 32 queries =====================
+    const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const int t = threadIdx.x - 128;
@@ -634,17 +653,19 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
         s_lse[st][t] = qi < p.L ? p.lse2[sidx + qi] : INFINITY;
         s_del[st][t] = qi < p.L ? p.delta[sidx + qi] : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(&sp_full[st], (it >> 1) & 1);
       mbar_wait(&ds_empty[st], ((it >> 1) & 1) ^ 1u);
       tc_fence_after();
       const uint32_t pt = sPD + st * 2 * HALF_TILE, dst = pt + HALF_TILE;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = wg;
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tmem_base + st * 64 + lane_addr + c * 32, sv);
         tmem_ld_32x32(tmem_base + 128 + st * 64 + lane_addr + c * 32, dv);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&sp_empty[st]);
         float fp[32], fs[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -658,8 +679,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
         store_row32_sw128(pt, r, c * 32, fp);
         store_row32_sw128(dst, r, c * 32, fs);
       }
-      tc_fence_before();
-      mbar_arrive(&sp_empty[st]);
       fence_proxy_async_smem();
       mbar_arrive(&ds_full[st]);
     }
@@ -668,8 +687,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     tc_fence_after();
     const long long stride = (long long)(p.nq + 2 * p.nkv) * HD;
     bf16* drow = p.dqkv + ((long long)b * p.L + (key < p.L ? key : 0)) * stride;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
+    {
+      const int which = wg;
       bf16* dst = drow + (which == 0 ? (p.nq + g) : (p.nq + p.nkv + g)) * HD;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -748,7 +767,7 @@ int attn_fwd_tc_launch(const void* qkv, const int* key_mask, void* out, float* l
     attr_set = true;
   }
   dim3 grid((L + BQ - 1) / BQ, nq, B);
-  attn_fwd_tc_kernel<<<grid, 256, smem, stream>>>(tm, p);
+  attn_fwd_tc_kernel<<<grid, 384, smem, stream>>>(tm, p);
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -783,12 +802,12 @@ int attn_bwd_tc_launch(const void* qkv, const int* key_mask, const void* dout, c
   }
   {
     dim3 grid((L + BQ - 1) / BQ, nq, B);
-    attn_bwd_dq_tc_kernel<<<grid, 256, smem_dq, stream>>>(q128, d128, q64, p);
+    attn_bwd_dq_tc_kernel<<<grid, 384, smem_dq, stream>>>(q128, d128, q64, p);
     B200RL_LAUNCH_OK();
   }
   {
     dim3 grid((L + BKV - 1) / BKV, nkv, B);
-    attn_bwd_dkv_tc_kernel<<<grid, 256, smem_dkv, stream>>>(q128, q64, d64, p);
+    attn_bwd_dkv_tc_kernel<<<grid, 384, smem_dkv, stream>>>(q128, q64, d64, p);
     B200RL_LAUNCH_OK();
   }
   return 0;
