@@ -60,7 +60,7 @@ struct FwdParams {
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], s_empty[2], o_full[2], o_empty[2], p_full;
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], o_full[2], o_empty[2], p_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ uint32_t s_maskw[2][4];     // key-padding bitmask of the 128 keys of a block
   __shared__ float s_mx[2][2][BQ];       // [stage][warpgroup][row] partial row max
@@ -82,8 +82,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 256);
       mbar_init(&o_full[s], 1);
@@ -103,21 +105,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: Q, then the K ring (a K slot is free as soon as QK_j retired) ====
     mbar_arrive_expect_tx(&q_full, TILE_BYTES);
     tma_load_3d(smem_gen, &tm, &q_full, h * HD, q0, b);
     tma_load_3d(smem_gen + TILE_BYTES / 2, &tm, &q_full, h * HD + 64, q0, b);
+    const int kcol = (p.nq + g) * HD;
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
-      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1u);
+      mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1u);
       uint8_t* k_dst = smem_gen + TILE_BYTES * (1 + 2 * st);
-      uint8_t* v_dst = k_dst + TILE_BYTES;
-      mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-      const int kcol = (p.nq + g) * HD, vcol = (p.nq + p.nkv + g) * HD;
-      tma_load_3d(k_dst, &tm, &kv_full[st], kcol, j * BKV, b);
-      tma_load_3d(k_dst + TILE_BYTES / 2, &tm, &kv_full[st], kcol + 64, j * BKV, b);
-      tma_load_3d(v_dst, &tm, &kv_full[st], vcol, j * BKV, b);
-      tma_load_3d(v_dst + TILE_BYTES / 2, &tm, &kv_full[st], vcol + 64, j * BKV, b);
+      mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+      tma_load_3d(k_dst, &tm, &k_full[st], kcol, j * BKV, b);
+      tma_load_3d(k_dst + TILE_BYTES / 2, &tm, &k_full[st], kcol + 64, j * BKV, b);
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===================== TMA producer: V ring (a V slot is free when P.V_j retired) =====================
+    const int vcol = (p.nq + p.nkv + g) * HD;
+    for (int j = 0; j < n_kb; ++j) {
+      const int st = j & 1;
+      mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1u);
+      uint8_t* v_dst = smem_gen + TILE_BYTES * (2 + 2 * st);
+      mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+      tma_load_3d(v_dst, &tm, &v_full[st], vcol, j * BKV, b);
+      tma_load_3d(v_dst + TILE_BYTES / 2, &tm, &v_full[st], vcol + 64, j * BKV, b);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
@@ -127,6 +137,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
     auto issue_pv = [&](int j) {
       const int st = j & 1;
       mbar_wait(&p_full, j & 1);
+      mbar_wait(&v_full[st], (j >> 1) & 1);
       mbar_wait(&o_empty[st], ((j >> 1) & 1) ^ 1u);
       tc_fence_after();
       const uint32_t v = sKV + TILE_BYTES * (2 * st + 1);
@@ -140,11 +151,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
         umma_bf16(tmem_o, da, db, idesc_pv, kk > 0 ? 1u : 0u);
       }
       umma_commit(&o_full[st]);
-      umma_commit(&kv_empty[st]);
+      umma_commit(&v_empty[st]);
     };
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
-      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      mbar_wait(&k_full[st], (j >> 1) & 1);
       mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1u);
       tc_fence_after();
       const uint32_t k = sKV + TILE_BYTES * (2 * st);
@@ -156,6 +167,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
         umma_bf16(tmem_s, da, db, idesc_qk, kk > 0 ? 1u : 0u);
       }
       umma_commit(&s_full[st]);
+      umma_commit(&k_empty[st]);
       if (j > 0) issue_pv(j - 1);
     }
     issue_pv(n_kb - 1);
@@ -347,14 +359,14 @@ __global__ void __launch_bounds__(384, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_do128,
                       const __grid_constant__ CUtensorMap tm_kv64, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t qdo_full, kv_full[2], kv_empty[2], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], dq_full;
+  __shared__ uint64_t qdo_full, kv_full[3], kv_empty[3], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], dq_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ int s_mask[2][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // [Q 32K][dO 32K][K0 16K][V0 16K][K1 16K][V1 16K][dS0 16K][dS1 16K]  = 160 KB
-  const uint32_t sQ = smem_base, sdO = sQ + TILE_BYTES, sKV = sdO + TILE_BYTES, sDS = sKV + 4 * HALF_TILE;
+  // [Q 32K][dO 32K][3 x (K 16K, V 16K)][dS0 16K][dS1 16K]  = 192 KB
+  const uint32_t sQ = smem_base, sdO = sQ + TILE_BYTES, sKV = sdO + TILE_BYTES, sDS = sKV + 6 * HALF_TILE;
   const int qb = (int)gridDim.x - 1 - (int)blockIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
   const int g = h / (p.nq / p.nkv);
@@ -364,9 +376,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
   if (threadIdx.x == 0) {
     mbar_init(&qdo_full, 1);
     mbar_init(&dq_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&sp_full[s], 1);
       mbar_init(&sp_empty[s], 256);
       mbar_init(&ds_full[s], 256);
@@ -393,8 +407,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     tma_load_3d(smem_gen + TILE_BYTES + TILE_BYTES / 2, &tm_do128, &qdo_full, h * HD + 64, q0, b);
     const int kcol = (p.nq + g) * HD, vcol = (p.nq + p.nkv + g) * HD;
     for (int j = 0; j < n_kb; ++j) {
-      const int st = j & 1;
-      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1u);
+      const int st = j % 3;
+      mbar_wait(&kv_empty[st], ((j / 3) & 1) ^ 1u);
       uint8_t* kd = smem_gen + 2 * TILE_BYTES + st * 2 * HALF_TILE;
       uint8_t* vd = kd + HALF_TILE;
       mbar_arrive_expect_tx(&kv_full[st], 2 * HALF_TILE);
@@ -409,10 +423,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     constexpr uint32_t id_dq = idesc_n(128, true);   // [128 q] x [128 d], B = K_j MN-major (k = keys)
     mbar_wait(&qdo_full, 0);
     auto issue_dq = [&](int j) {
-      const int st = j & 1;
+      const int st = j & 1, k3 = j % 3;
       mbar_wait(&ds_full[st], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t kt = sKV + st * 2 * HALF_TILE;
+      const uint32_t kt = sKV + k3 * 2 * HALF_TILE;
       const uint32_t ds = sDS + st * HALF_TILE;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {  // 64 keys = 4 x K16
@@ -420,15 +434,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
         const uint64_t db = smem_desc_sw128(kt + kk * 2048, HALF_TILE / 2, 1024);
         umma_bf16(tmem_base + 256, da, db, id_dq, (j > 0 || kk > 0) ? 1u : 0u);
       }
-      umma_commit(&kv_empty[st]);
+      umma_commit(&kv_empty[k3]);
       umma_commit(&ds_empty[st]);
     };
     for (int j = 0; j < n_kb; ++j) {
-      const int st = j & 1;
-      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      const int st = j & 1, k3 = j % 3;
+      mbar_wait(&kv_full[k3], (j / 3) & 1);
       mbar_wait(&sp_empty[st], ((j >> 1) & 1) ^ 1u);
       tc_fence_after();
-      const uint32_t kt = sKV + st * 2 * HALF_TILE, vt = kt + HALF_TILE;
+      const uint32_t kt = sKV + k3 * 2 * HALF_TILE, vt = kt + HALF_TILE;
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {  // d = 128 = 8 x K16, two d-halves
         const uint32_t aoff = (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32;
@@ -526,14 +540,14 @@ __global__ void __launch_bounds__(384, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_constant__ CUtensorMap tm_q64,
                        const __grid_constant__ CUtensorMap tm_do64, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t kv_full, qd_full[2], qd_empty[2], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], out_full;
+  __shared__ uint64_t kv_full, qd_full[3], qd_empty[3], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], out_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_lse[2][64], s_del[2][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // [K 32K][V 32K][Q0 16K][dO0 16K][Q1 16K][dO1 16K][PT0 16K][dST0 16K][PT1 16K][dST1 16K] = 192 KB
-  const uint32_t sK = smem_base, sV = sK + TILE_BYTES, sQD = sV + TILE_BYTES, sPD = sQD + 4 * HALF_TILE;
+  // [K 32K][V 32K][3 x (Q 16K, dO 16K)][PT0 16K][dST0 16K][PT1 16K][dST1 16K] = 224 KB
+  const uint32_t sK = smem_base, sV = sK + TILE_BYTES, sQD = sV + TILE_BYTES, sPD = sQD + 6 * HALF_TILE;
   const int kb = blockIdx.x, g = blockIdx.y, b = blockIdx.z;   // key block 0 (most work) is scheduled first
   const int group = p.nq / p.nkv;
   const int k0 = kb * BKV;
@@ -544,9 +558,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
   if (threadIdx.x == 0) {
     mbar_init(&kv_full, 1);
     mbar_init(&out_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       mbar_init(&qd_full[s], 1);
       mbar_init(&qd_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&sp_full[s], 1);
       mbar_init(&sp_empty[s], 256);
       mbar_init(&ds_full[s], 256);
@@ -573,10 +589,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     tma_load_3d(smem_gen + TILE_BYTES, &tm_kv128, &kv_full, vcol, k0, b);
     tma_load_3d(smem_gen + TILE_BYTES + TILE_BYTES / 2, &tm_kv128, &kv_full, vcol + 64, k0, b);
     for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1;
+      const int st = it % 3;
       const int h = g * group + it / nqb;
       const int qs = (qb0 + it % nqb) * 64;
-      mbar_wait(&qd_empty[st], ((it >> 1) & 1) ^ 1u);
+      mbar_wait(&qd_empty[st], ((it / 3) & 1) ^ 1u);
       uint8_t* qd = smem_gen + 2 * TILE_BYTES + st * 2 * HALF_TILE;
       uint8_t* dd = qd + HALF_TILE;
       mbar_arrive_expect_tx(&qd_full[st], 2 * HALF_TILE);
@@ -591,10 +607,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     constexpr uint32_t id_g = idesc_n(128, true);    // [128 keys] x [128 d], B = dO / Q MN-major (k = queries)
     mbar_wait(&kv_full, 0);
     auto issue_grad = [&](int it) {
-      const int st = it & 1;
+      const int st = it & 1, q3 = it % 3;
       mbar_wait(&ds_full[st], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t qt = sQD + st * 2 * HALF_TILE, dt = qt + HALF_TILE;
+      const uint32_t qt = sQD + q3 * 2 * HALF_TILE, dt = qt + HALF_TILE;
       const uint32_t pt = sPD + st * 2 * HALF_TILE, dst = pt + HALF_TILE;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {  // 64 queries = 4 x K16
@@ -606,15 +622,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
         umma_bf16(tmem_base + 256, smem_desc_sw128(dst + kk * 32, 16, 1024),
                   smem_desc_sw128(qt + kk * 2048, HALF_TILE / 2, 1024), id_g, (it > 0 || kk > 0) ? 1u : 0u);
       }
-      umma_commit(&qd_empty[st]);
+      umma_commit(&qd_empty[q3]);
       umma_commit(&ds_empty[st]);
     };
     for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1;
-      mbar_wait(&qd_full[st], (it >> 1) & 1);
+      const int st = it & 1, q3 = it % 3;
+      mbar_wait(&qd_full[q3], (it / 3) & 1);
       mbar_wait(&sp_empty[st], ((it >> 1) & 1) ^ 1u);
       tc_fence_after();
-      const uint32_t qt = sQD + st * 2 * HALF_TILE, dt = qt + HALF_TILE;
+      const uint32_t qt = sQD + q3 * 2 * HALF_TILE, dt = qt + HALF_TILE;
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         const uint32_t aoff = (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32;
@@ -793,8 +809,8 @@ int attn_bwd_tc_launch(const void* qkv, const int* key_mask, const void* dout, c
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   static bool attr_set = false;
-  const int smem_dq = 2 * TILE_BYTES + 6 * HALF_TILE + 1024;
-  const int smem_dkv = 2 * TILE_BYTES + 8 * HALF_TILE + 1024;
+  const int smem_dq = 2 * TILE_BYTES + 8 * HALF_TILE + 1024;
+  const int smem_dkv = 2 * TILE_BYTES + 10 * HALF_TILE + 1024;
   if (!attr_set) {
     B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
     B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv));
