@@ -270,10 +270,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
           const int cc = half * 4 + u;  // 16-byte chunk 0..7 within the 128-byte row of the atom
           const bf16x8 pk = pack8(&pf[u * 8]);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((cc ^ (r & 7)) << 4)),
-                       "r"(*reinterpret_cast<const uint32_t*>(&pk.v[0])),
-                       "r"(*reinterpret_cast<const uint32_t*>(&pk.v[1])),
-                       "r"(*reinterpret_cast<const uint32_t*>(&pk.v[2])),
-                       "r"(*reinterpret_cast<const uint32_t*>(&pk.v[3]))
+                       "r"(pk.u.x), "r"(pk.u.y), "r"(pk.u.z), "r"(pk.u.w)
                        : "memory");
         }
       }
@@ -346,8 +343,7 @@ __device__ __forceinline__ void store_row32_sw128(uint32_t tile, int r, int col0
     const uint32_t addr = tile + r * 128 + ((cc ^ (r & 7)) << 4);
     const bf16x8 pk = pack8(&f[u * 8]);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                 "r"(*reinterpret_cast<const uint32_t*>(&pk.v[0])), "r"(*reinterpret_cast<const uint32_t*>(&pk.v[1])),
-                 "r"(*reinterpret_cast<const uint32_t*>(&pk.v[2])), "r"(*reinterpret_cast<const uint32_t*>(&pk.v[3]))
+                 "r"(pk.u.x), "r"(pk.u.y), "r"(pk.u.z), "r"(pk.u.w)
                  : "memory");
   }
 }

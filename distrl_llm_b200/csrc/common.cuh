@@ -74,22 +74,36 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// 8 x bf16 <-> float[8] through one 16-byte vector
+// 8 x bf16 <-> float[8] through ONE 16-byte transaction.  The payload is a uint4 so that copying a bf16x8
+// (load from / store to global or shared memory) is a single 128-bit LDG/STG/LDS/STS; a struct of four
+// __nv_bfloat162 is copied member-wise and compiles to four 32-bit accesses (seen in SASS / ncu source view).
 struct __align__(16) bf16x8 {
-  __nv_bfloat162 v[4];
+  uint4 u;
+  __device__ __forceinline__ uint32_t& w(int i) { return reinterpret_cast<uint32_t*>(&u)[i]; }
+  __device__ __forceinline__ const uint32_t& w(int i) const { return reinterpret_cast<const uint32_t*>(&u)[i]; }
+  __device__ __forceinline__ void set(int i, __nv_bfloat162 h) { w(i) = *reinterpret_cast<uint32_t*>(&h); }
+  __device__ __forceinline__ __nv_bfloat162 get(int i) const {
+    const uint32_t t = w(i);
+    return *reinterpret_cast<const __nv_bfloat162*>(&t);
+  }
 };
 __device__ __forceinline__ void unpack8(const bf16x8& in, float* f) {
+  const uint32_t r[4] = {in.u.x, in.u.y, in.u.z, in.u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(in.v[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
+    // bf16 -> fp32 is a 16-bit shift
+    f[2 * i] = __uint_as_float(r[i] << 16);
+    f[2 * i + 1] = __uint_as_float(r[i] & 0xFFFF0000u);
   }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
   bf16x8 o;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) o.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  o.u = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                   pack_bf16x2(f[6], f[7]));
   return o;
 }
 

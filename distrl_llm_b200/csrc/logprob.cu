@@ -94,8 +94,7 @@ logprob_kernel(bf16* __restrict__ logits, long long ld, const int* __restrict__ 
   bf16x8* zw = reinterpret_cast<bf16x8*>(z);
   if (c == 0.f) {
     bf16x8 zero;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) zero.v[j] = __floats2bfloat162_rn(0.f, 0.f);
+    zero.u = make_uint4(0u, 0u, 0u, 0u);
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) zw[i] = zero;
     return;
   }

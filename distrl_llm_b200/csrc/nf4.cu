@@ -82,7 +82,7 @@ nf4_dequant_kernel(const uint8_t* __restrict__ packed, const float* __restrict__
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const float2 v = lut[(q[u] >> (8 * b)) & 0xFFu];
-          o.v[b] = __floats2bfloat162_rn(v.x * am[u], v.y * am[u]);
+          o.w(b) = pack_bf16x2(v.x * am[u], v.y * am[u]);
         }
         reinterpret_cast<bf16x8*>(out)[i] = o;
       }
@@ -125,8 +125,10 @@ __global__ void nf4_dequant_t_kernel(const uint8_t* __restrict__ packed,
       bf16x8 o;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        o.v[j].x = tile[rv + 2 * j][c];
-        o.v[j].y = tile[rv + 2 * j + 1][c];
+        __nv_bfloat162 h;
+        h.x = tile[rv + 2 * j][c];
+        h.y = tile[rv + 2 * j + 1][c];
+        o.set(j, h);
       }
       *reinterpret_cast<bf16x8*>(out + (long long)(c0 + c) * rows + r0 + rv) = o;
     }
