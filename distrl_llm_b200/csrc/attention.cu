@@ -281,12 +281,13 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
   const bf16* po = out + row * nq * hd + h * hd;
   const bf16* pd = dout + row * nq * hd + h * hd;
   float acc = 0.f;
-  for (int c = lane * 8; c < hd; c += 256) {
-    float a[8], d[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(po + c), a);
-    unpack8(*reinterpret_cast<const bf16x8*>(pd + c), d);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc += a[j] * d[j];
+  for (int c = lane * 4; c < hd; c += 128) {  // 8-byte loads: every lane is active for hd = 128
+    const uint2 a2 = *reinterpret_cast<const uint2*>(po + c);
+    const uint2 d2 = *reinterpret_cast<const uint2*>(pd + c);
+    acc += __uint_as_float(a2.x << 16) * __uint_as_float(d2.x << 16) +
+           __uint_as_float(a2.x & 0xFFFF0000u) * __uint_as_float(d2.x & 0xFFFF0000u) +
+           __uint_as_float(a2.y << 16) * __uint_as_float(d2.y << 16) +
+           __uint_as_float(a2.y & 0xFFFF0000u) * __uint_as_float(d2.y & 0xFFFF0000u);
   }
   acc = warp_sum(acc);
   const long long b = row / L, i = row % L;

@@ -248,7 +248,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
       mx = fmaxf(mx, s_mx[st][wg ^ 1][r]);
       const float m_new = fmaxf(m_run, mx);
       const float mu = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = exp2f(m_run - mu);
+      const float corr = ex2_approx(m_run - mu);
       // fold the previous block's P.V into the register accumulator (also guarantees the previous P.V has
       // finished reading the P tile before it is overwritten below)
       if (j > 0) absorb(j - 1, corr_prev);
@@ -261,7 +261,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float sv = __uint_as_float(half == 0 ? v0[i] : v1[i]);
-          const float pv = plain ? exp2f(sv * p.scale_log2 - mu) : exp2f(sv - mu);  // masked -> exp2(-inf) = 0
+          const float pv = plain ? ex2_approx(sv * p.scale_log2 - mu) : ex2_approx(sv - mu);  // masked -> 2^-inf = 0
           pf[i] = pv;
           rs += pv;
         }
@@ -472,13 +472,21 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
       const int k0 = j * 64;
-      if (t < 64) s_mask[st][t] = (k0 + t < p.L) ? p.key_mask[(long long)b * p.L + k0 + t] : 0;
+      if (t < 64) {  // warps 4 and 5: key-padding bitmask of the block's two 32-key chunks
+        const int mk = (k0 + t < p.L) ? p.key_mask[(long long)b * p.L + k0 + t] : 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, mk != 0);
+        if (lane == 0) s_mask[st][t >> 5] = (int)bal;
+      }
       named_bar_sync(1, 256);
+      const int c = wg;
+      const uint32_t mw = (uint32_t)s_mask[st][c];
+      const int kc0 = k0 + c * 32;
+      // no masking at all when every key of the chunk is real and at or before the tile's first query
+      const bool plain = (mw == 0xFFFFFFFFu) && (kc0 + 31 <= q0);
       mbar_wait(&sp_full[st], (j >> 1) & 1);
       mbar_wait(&ds_empty[st], ((j >> 1) & 1) ^ 1u);  // dQ MMA of block j-2 finished reading dS[st]
       tc_fence_after();
       {
-        const int c = wg;
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tmem_base + st * 64 + lane_addr + c * 32, sv);
         tmem_ld_32x32(tmem_base + 128 + st * 64 + lane_addr + c * 32, dv);
@@ -486,12 +494,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
         tc_fence_before();
         mbar_arrive(&sp_empty[st]);
         float f[32];
+        if (plain) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int key = k0 + c * 32 + i;
-          const bool ok = key <= q && s_mask[st][c * 32 + i] != 0;
-          const float pr = ok ? exp2f(__uint_as_float(sv[i]) * p.scale_log2 - lse) : 0.f;
-          f[i] = p.scale * pr * (__uint_as_float(dv[i]) - del);
+          for (int i = 0; i < 32; ++i) {
+            const float pr = ex2_approx(__uint_as_float(sv[i]) * p.scale_log2 - lse);
+            f[i] = p.scale * pr * (__uint_as_float(dv[i]) - del);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = ((mw >> i) & 1u) && (kc0 + i <= q);
+            const float pr = ok ? ex2_approx(__uint_as_float(sv[i]) * p.scale_log2 - lse) : 0.f;
+            f[i] = p.scale * pr * (__uint_as_float(dv[i]) - del);
+          }
         }
         store_row32_sw128(sDS + st * HALF_TILE, r, c * 32, f);
       }
@@ -538,7 +553,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t kv_full, qd_full[3], qd_empty[3], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], out_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_lse[2][64], s_del[2][64];
+  __shared__ __align__(16) float s_lse[2][64], s_del[2][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -662,16 +677,18 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       if (t < 64) {
         const int qi = qs + t;
         const long long sidx = ((long long)b * p.nq + h) * p.L;
-        s_lse[st][t] = qi < p.L ? p.lse2[sidx + qi] : INFINITY;
+        s_lse[st][t] = qi < p.L ? p.lse2[sidx + qi] : INFINITY;   // +inf -> probability 0 for queries past the end
         s_del[st][t] = qi < p.L ? p.delta[sidx + qi] : 0.f;
       }
       named_bar_sync(1, 256);
+      const int c = wg;
+      const int qc0 = qs + c * 32;
+      const bool need_cmp = qc0 < k0 + BKV - 1;   // some (key, query) pair of this chunk may violate key <= query
       mbar_wait(&sp_full[st], (it >> 1) & 1);
       mbar_wait(&ds_empty[st], ((it >> 1) & 1) ^ 1u);
       tc_fence_after();
       const uint32_t pt = sPD + st * 2 * HALF_TILE, dst = pt + HALF_TILE;
       {
-        const int c = wg;
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tmem_base + st * 64 + lane_addr + c * 32, sv);
         tmem_ld_32x32(tmem_base + 128 + st * 64 + lane_addr + c * 32, dv);
@@ -679,14 +696,20 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
         tc_fence_before();
         mbar_arrive(&sp_empty[st]);
         float fp[32], fs[32];
+        const float4* l4 = reinterpret_cast<const float4*>(&s_lse[st][c * 32]);
+        const float4* d4 = reinterpret_cast<const float4*>(&s_del[st][c * 32]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int ql = c * 32 + i;
-          const int qi = qs + ql;
-          const bool ok = key_ok && key <= qi && qi < p.L;
-          const float pr = ok ? exp2f(__uint_as_float(sv[i]) * p.scale_log2 - s_lse[st][ql]) : 0.f;
-          fp[i] = pr;
-          fs[i] = p.scale * pr * (__uint_as_float(dv[i]) - s_del[st][ql]);
+        for (int v4 = 0; v4 < 8; ++v4) {
+          const float4 lv = l4[v4], dl = d4[v4];
+          const float ls[4] = {lv.x, lv.y, lv.z, lv.w}, ds4[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = v4 * 4 + u;
+            float pr = ex2_approx(__uint_as_float(sv[i]) * p.scale_log2 - ls[u]);
+            if (!key_ok || (need_cmp && key > qc0 + i)) pr = 0.f;  // select, never 0 * inf
+            fp[i] = pr;
+            fs[i] = p.scale * pr * (__uint_as_float(dv[i]) - ds4[u]);
+          }
         }
         store_row32_sw128(pt, r, c * 32, fp);
         store_row32_sw128(dst, r, c * 32, fs);

@@ -107,6 +107,13 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   return o;
 }
 
+// single-instruction 2^x (MUFU.EX2, rel. error ~2^-22, flushes denormals); exp2f() adds ~4 range-handling instrs
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---- mbarrier ----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
