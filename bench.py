@@ -166,6 +166,8 @@ def config_dict(args):
                         f"(P={args.prompt_len}, micro-batch {args.micro_batch})",
             "global_batch": args.seqs * args.gpus, "seq_len": args.prompt_len + args.new_tokens,
             "parallelism": f"dp{args.gpus}" if args.gpus > 1 else "single learner",
+            "layout": "classic [B, P+T] rows" if getattr(args, "no_share_prompts", False) else
+                      "packed shared-prompt rows (each group's prompt processed once; identical gradients)",
             "l2": "per-step activations and weights (>30 GB) far exceed the 126 MB L2; no flush needed"}
 
 
@@ -185,6 +187,7 @@ def main():
     ap.add_argument("--layers", type=int, default=28, help="debug only: anything but 28 is not the benchmark")
     ap.add_argument("--cpu_rows", type=int, default=2, help="sequences in the CPU sample micro-batch")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_share_prompts", action="store_true", help="classic [B, P+T] layout (every prompt recomputed per completion)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: W >= 3
@@ -234,12 +237,25 @@ def main():
     d_ids, d_am, d_ansm = ids_h.to(dev), am_h.to(dev), ansm_h.to(dev)
     d_adv = torch.from_numpy(np.asarray(adv, dtype=np.float64)).to(dev)
 
+    share = learner.share_prompts and not args.no_share_prompts
+    learner.share_prompts = share
+    packed = []
+    if share:  # packed shared-prompt layout, device-resident for the `value` measurement
+        from distrl_llm_b200 import packing
+        for i in range(nb):
+            s_, e_ = i * B, min((i + 1) * B, N)
+            packed.append(packing.PackedDevice(packing.pack_microbatch(ids_h[s_:e_].numpy(), am_h[s_:e_].numpy(), P, T), dev))
+        torch.cuda.synchronize()
+
     def device_step():
         pol.zero_grad()
         pol.loss_accum.zero_()
         for i in range(nb):
             s, e = i * B, min((i + 1) * B, N)
-            pol.microbatch(d_ids[s:e], d_am[s:e], d_ansm[s:e], d_adv[s:e], P, T, nb, True, backward=True)
+            if share:
+                pol.microbatch_packed(packed[i], d_adv[s:e], nb, True, backward=True)
+            else:
+                pol.microbatch(d_ids[s:e], d_am[s:e], d_ansm[s:e], d_adv[s:e], P, T, nb, True, backward=True)
         if group is not None:
             group.reduce_adam_step(pol, learner.lr, 0.0)
         else:
@@ -325,7 +341,7 @@ def main():
                 "flops_per_launch": gemm["work"] / max(gemm["launches"], 1),
                 "step_model_tflops": round(step_flops * world / (ms_dev / 1e3) / 1e12 / world, 1),
                 "how": "CUDA events between consecutive launches on the launching stream, one profiled step after the timed region"}
-    h2d = int(ids_h.numel() * 4 + am_h.numel() * 4 + ansm_h.numel() * 4 + N * 8)
+    h2d = int(sum(pk.h2d_bytes for pk in packed) + N * 8) if share else int(ids_h.numel() * 4 + am_h.numel() * 4 + ansm_h.numel() * 4 + N * 8)
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and args.layers == 28:

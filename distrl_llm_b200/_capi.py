@@ -58,6 +58,9 @@ SIGNATURES = {
     "b200rl_attn_set_tc": (c_int, [c_int]),
     "b200rl_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "b200rl_attn_seg_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
+    "b200rl_attn_seg_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll,
+                                    c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200rl_logprob": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200rl_loss_coef": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200rl_loss_value": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -87,6 +90,11 @@ SIGNATURES = {
     "b200rl_model_debug_ptr": (c_void_p, [c_void_p, C.c_char_p, c_int]),
     "b200rl_model_microbatch_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, C.c_double, c_void_p]),
+    "b200rl_model_microbatch_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                               c_void_p, C.c_double, c_void_p]),
+    "b200rl_rope_pos": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p]),
+    "b200rl_gather_rows_idx": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "b200rl_scatter_add_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b200rl_model_profile": (c_int, [c_void_p, c_int]),
     "b200rl_model_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200rl_launch_count": (c_ll, []),

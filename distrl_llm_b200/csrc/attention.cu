@@ -13,6 +13,7 @@
 // out/dout [B*L, nq*hd] bf16, lse2 [B, nq, L] fp32 = log2-sum-exp2 of the scaled scores
 // (+inf for rows with no visible key, which makes every probability of that row exactly 0).
 #include "common.cuh"
+#include "b200rl.h"
 #include <stdlib.h>
 
 namespace b200rl {
@@ -647,6 +648,12 @@ static int attn_bwd_tc(const void* qkv, const int* key_mask, const void* out, co
   B200RL_LAUNCH_OK();
   return attn_bwd_tc_launch(qkv, key_mask, dout, lse, delta, dqkv, B, L, nq, nkv, scale, stream);
 }
+int attn_fwd_seg_launch(const void* qkv, const int* key_mask, void* out, float* lse, long long rows, int nq, int nkv,
+                        float scale, const b200rl_attn_qblock* qblocks_dev, int n_qblocks, cudaStream_t stream);
+int attn_bwd_seg_launch(const void* qkv, const int* key_mask, const void* dout, const float* lse, const float* delta,
+                        void* dqkv, float* kv_part, long long rows, int nq, int nkv, float scale,
+                        const b200rl_attn_qblock* qblocks_dev, int n_qblocks, const b200rl_attn_kblock* kblocks_dev,
+                        int n_kblocks, const int* red_start_dev, const int* red_list_dev, cudaStream_t stream);
 static int g_attn_tc = -1;
 static bool attn_tc_enabled() {
   if (g_attn_tc < 0) {
@@ -697,4 +704,32 @@ extern "C" int b200rl_attn_bwd(const void* qkv, const int* key_mask, const void*
       return attn_bwd_launch<128>(qkv, key_mask, out, dout, lse, delta, dqkv, B, L, n_q_heads, n_kv_heads, scale, st);
     default: return set_error(B200RL_ERR_UNSUPPORTED, "attn: head_dim %d not in {32,64,128}", head_dim);
   }
+}
+
+// ---- packed (shared-prompt) layout, head_dim 128 only ----------------------------------------------------------
+extern "C" int b200rl_attn_seg_fwd(const void* qkv, const int* key_mask, void* out, float* lse, long long rows,
+                                   int n_q_heads, int n_kv_heads, float scale,
+                                   const b200rl_attn_qblock* qblocks_dev, int n_qblocks, void* stream) {
+  B200RL_REQUIRE(qkv && key_mask && out && lse && qblocks_dev && rows > 0 && n_qblocks > 0, "attn_seg_fwd: bad args");
+  B200RL_REQUIRE(n_kv_heads > 0 && n_q_heads % n_kv_heads == 0, "attn_seg_fwd: nq %% nkv != 0");
+  return attn_fwd_seg_launch(qkv, key_mask, out, lse, rows, n_q_heads, n_kv_heads, scale, qblocks_dev, n_qblocks,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200rl_attn_seg_bwd(const void* qkv, const int* key_mask, const void* out, const void* dout,
+                                   const float* lse, float* delta, void* dqkv, float* kv_part, long long rows,
+                                   int n_q_heads, int n_kv_heads, float scale,
+                                   const b200rl_attn_qblock* qblocks_dev, int n_qblocks,
+                                   const b200rl_attn_kblock* kblocks_dev, int n_kblocks, const int* red_start_dev,
+                                   const int* red_list_dev, void* stream) {
+  B200RL_REQUIRE(qkv && key_mask && out && dout && lse && delta && dqkv && kv_part && qblocks_dev && kblocks_dev &&
+                     red_start_dev && red_list_dev && rows > 0, "attn_seg_bwd: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // delta[h][row]: the classic kernel with B = 1, L = rows uses exactly that index
+  const long long warps = rows * n_q_heads;
+  attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, (int)rows,
+                                                                  n_q_heads, 128, rows);
+  B200RL_LAUNCH_OK();
+  return attn_bwd_seg_launch(qkv, key_mask, dout, lse, delta, dqkv, kv_part, rows, n_q_heads, n_kv_heads, scale,
+                             qblocks_dev, n_qblocks, kblocks_dev, n_kblocks, red_start_dev, red_list_dev, st);
 }

@@ -1,35 +1,44 @@
-// G4 on the 5th-gen tensor cores: causal GQA flash attention FORWARD with tcgen05.mma, S and the per-block
-// P.V product in TMEM, Q/K/V tiles by TMA (head_dim 128; other head dims use the mma.sync kernels in
-// attention.cu).  Same contract as attn_fwd_kernel: qkv [B*L, (nq+2nkv)*128] bf16 (RoPE applied), key-padding
-// mask, out [B*L, nq*128] bf16, lse2 [B, nq, L] fp32 (log2 domain, +inf for rows without any visible key).
+// G4 on the 5th-gen tensor cores (head_dim 128): causal GQA flash attention forward + backward with tcgen05.mma,
+// accumulators in TMEM, tiles by TMA.  Other head dims use the mma.sync kernels in attention.cu.
 //
-// One CTA per (128-query block, q head, sequence); key blocks of 128:
-//   warp 0  : TMA producer  - Q once, then (K_j, V_j) into a 2-stage ring (3-D tensor map over [B][L][cols] so
-//             rows beyond a sequence's end are zero-filled)
-//   warp 1  : MMA issuer    - S_j = Q.K_j^T  (8 x UMMA 128x128x16, both operands K-major) into TMEM S[j&1];
-//                             O_j = P_j.V_j  (A = P_j from smem, B = V_j MN-major) into TMEM O[j&1]; software
-//                             pipelined: QK_{j+1} is issued before P.V_j so the tensor core overlaps the softmax
-//   warp 2  : TMEM allocator (512 columns: S0 S1 O0 O1)
-//   warps 4-7: softmax, one query row per thread (TMEM lane = row): pass 1 row max, pass 2 p = exp2(s - m) ->
-//             bf16 P tile in the canonical 128B-swizzled K-major layout; running (m, l) and the output row live
-//             in registers, O_reg = O_reg * exp2(m_old - m_new) + O_j (no TMEM read-modify-write).
+// The kernels are driven by small block descriptors so that ONE implementation serves two token layouts:
+//   classic : B sequences of L = P + T rows each (the reference's padded batch, distributed_actor.py:233-239);
+//             descriptors are computed from blockIdx on the device.
+//   packed  : "shared-prompt" layout — every distinct prompt of the micro-batch is stored ONCE (a causal segment),
+//             each completion is its own segment whose queries additionally see the whole prompt segment as a
+//             prefix.  In GRPO all completions of a group share the prompt (distributed_actor.py:169-170 repeats it
+//             n times), so the token-parallel work of the 28 layers drops from B*(P+T) to G*P + B*T rows with the
+//             same attention inputs per query.  Descriptors come from arrays built on the host.
+//
+// Forward (one CTA per <=128-query block and q head):
+//   warp 0 / 3 : TMA producers (Q + K ring / V ring)       warp 1 : MMA issuer      warp 2 : TMEM allocator
+//   warps 4-11 : two softmax warpgroups; thread = query row (TMEM lane); warpgroup wg owns keys [64wg,64wg+64) of
+//                each 128-key block and output columns [64wg, 64wg+64); O_reg = O_reg*corr + P_j.V_j (from TMEM)
+// Backward: dQ kernel per query block (64-key inner blocks, dQ accumulates in TMEM); dK/dV kernel per key block and
+// per query segment that sees it (64-query inner blocks over all q heads of the GQA group, dK/dV accumulate in TMEM;
+// in the packed layout the per-(key block, query segment) partials are fp32 slabs summed in fixed order).
 #include "common.cuh"
+#include "b200rl.h"
+#include <string.h>
 
 namespace b200rl {
 
 namespace {
 
 constexpr int HD = 128;
-constexpr int BQ = 128;   // queries per CTA
-constexpr int BKV = 128;  // keys per block
+constexpr int BQ = 128;   // queries per CTA (fwd, dQ) / keys per CTA (dKV)
+constexpr int BKV = 128;  // keys per block in the forward
 constexpr int TILE_BYTES = 128 * HD * 2;  // 32 KB: [2 halves of 64 cols][128 rows][128 B]
+constexpr int HALF_TILE = 64 * HD * 2;    // 16 KB: [2 d-halves of 8 KB][64 rows][128 B]
 
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
-                                            int c2) {
+typedef b200rl_attn_qblock QBlock;
+typedef b200rl_attn_kblock KBlock;
+
+__device__ __forceinline__ void tma_load_rows(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int col, int row) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(col), "r"(row)
       : "memory");
 }
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
@@ -41,26 +50,86 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo,
   d |= (uint64_t)2 << 61;
   return d;
 }
-constexpr uint32_t idesc_128x128(bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(128 >> 3) << 17) |
+constexpr uint32_t idesc_n(int n, bool b_mn) {  // M = 128, A K-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(128 >> 4) << 24);
 }
+constexpr uint32_t idesc_128x128(bool b_mn) { return idesc_n(128, b_mn); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// this thread's row r of a [128 rows][64 cols] bf16 K-major SW128 tile: store columns col0..col0+31
+__device__ __forceinline__ void store_row32_sw128(uint32_t tile, int r, int col0, const float* f) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int cc = col0 / 8 + u;  // 16-byte chunk 0..7 within the 128-byte row
+    const uint32_t addr = tile + r * 128 + ((cc ^ (r & 7)) << 4);
+    const bf16x8 pk = pack8(&f[u * 8]);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk.u.x), "r"(pk.u.y), "r"(pk.u.z),
+                 "r"(pk.u.w)
+                 : "memory");
+  }
+}
 
-struct FwdParams {
-  const int* key_mask;
-  bf16* out;
-  float* lse2;
-  int L, nq, nkv;
-  float scale_log2;
+struct AttnParams {
+  const int* key_mask;   // [rows] 1 = real token
+  bf16* out;             // fwd: [rows, nq*HD]
+  float* lse2;           // fwd out / bwd in
+  const float* delta;    // bwd in
+  bf16* dqkv;            // bwd out [rows, (nq+2nkv)*HD]
+  float* kv_part;        // packed dKV: fp32 partial slabs [part rows][2*nkv*HD]
+  const QBlock* qblocks; // packed: descriptors (nullptr = classic)
+  const KBlock* kblocks;
+  int L;                 // classic: sequence length
+  int stat_h;            // lse/delta head stride
+  int nq, nkv;
+  float scale, scale_log2;
+};
+
+// classic layout descriptors from the launch grid: grid = (ceil(L/128), heads, B), heavy blocks first
+__device__ __forceinline__ QBlock classic_qblock(const AttnParams& p) {
+  const int qb = (int)gridDim.x - 1 - (int)blockIdx.x, b = blockIdx.z;
+  QBlock d;
+  d.q_row0 = b * p.L + qb * BQ;
+  d.q_rows = min(BQ, p.L - qb * BQ);
+  d.q_local0 = qb * BQ;
+  d.own_row0 = b * p.L;
+  d.own_len = p.L;
+  d.pre_row0 = 0;
+  d.pre_len = 0;
+  d.stat0 = b * p.nq * p.L + qb * BQ;
+  return d;
+}
+
+// key-block iteration shared by fwd (W = 128) and dQ (W = 64): prefix blocks first, then own (causal) blocks
+template <int W>
+struct KeyIter {
+  int n_pre, n_tot;
+  __device__ __forceinline__ KeyIter(const QBlock& d) {
+    n_pre = (d.pre_len + W - 1) / W;
+    const int need = d.q_local0 + d.q_rows;  // own keys with local index < need are visible to some query
+    n_tot = n_pre + (min(need, d.own_len) + W - 1) / W;
+  }
+  // block j -> global row of its first key, number of in-range keys, local index of the first key (-1: prefix)
+  __device__ __forceinline__ void get(const QBlock& d, int j, int& row0, int& valid, int& local0) const {
+    if (j < n_pre) {
+      row0 = d.pre_row0 + j * W;
+      valid = min(W, d.pre_len - j * W);
+      local0 = -1;
+    } else {
+      const int jo = j - n_pre;
+      row0 = d.own_row0 + jo * W;
+      valid = min(W, d.own_len - jo * W);
+      local0 = jo * W;
+    }
+  }
 };
 
 __global__ void __launch_bounds__(384, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], o_full[2], o_empty[2], p_full;
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], o_full[2],
+      o_empty[2], p_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ uint32_t s_maskw[2][4];     // key-padding bitmask of the 128 keys of a block
   __shared__ float s_mx[2][2][BQ];       // [stage][warpgroup][row] partial row max
@@ -72,12 +141,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
   // [Q 32K][K0 32K][V0 32K][K1 32K][V1 32K][P 32K]
   const uint32_t sQ = smem_base, sKV = smem_base + TILE_BYTES, sP = smem_base + 5 * TILE_BYTES;
 
-  // heavy (late) query blocks first: causal work per CTA grows with the block index
-  const int qb = (int)gridDim.x - 1 - (int)blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const QBlock d = p.qblocks ? p.qblocks[blockIdx.x] : classic_qblock(p);
+  const int h = blockIdx.y;
   const int g = h / (p.nq / p.nkv);
-  const int q0 = qb * BQ;
-  const int n_kb = min(qb + 1, (p.L + BKV - 1) / BKV);  // causal: key blocks 0..qb
+  const KeyIter<BKV> kit(d);
+  const int n_kb = kit.n_tot;
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
@@ -107,27 +175,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer: Q, then the K ring (a K slot is free as soon as QK_j retired) ====
     mbar_arrive_expect_tx(&q_full, TILE_BYTES);
-    tma_load_3d(smem_gen, &tm, &q_full, h * HD, q0, b);
-    tma_load_3d(smem_gen + TILE_BYTES / 2, &tm, &q_full, h * HD + 64, q0, b);
+    tma_load_rows(smem_gen, &tm, &q_full, h * HD, d.q_row0);
+    tma_load_rows(smem_gen + TILE_BYTES / 2, &tm, &q_full, h * HD + 64, d.q_row0);
     const int kcol = (p.nq + g) * HD;
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
+      int row0, valid, local0;
+      kit.get(d, j, row0, valid, local0);
       mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1u);
       uint8_t* k_dst = smem_gen + TILE_BYTES * (1 + 2 * st);
       mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
-      tma_load_3d(k_dst, &tm, &k_full[st], kcol, j * BKV, b);
-      tma_load_3d(k_dst + TILE_BYTES / 2, &tm, &k_full[st], kcol + 64, j * BKV, b);
+      tma_load_rows(k_dst, &tm, &k_full[st], kcol, row0);
+      tma_load_rows(k_dst + TILE_BYTES / 2, &tm, &k_full[st], kcol + 64, row0);
     }
   } else if (warp == 3 && lane == 0) {
     // ===================== TMA producer: V ring (a V slot is free when P.V_j retired) =====================
     const int vcol = (p.nq + p.nkv + g) * HD;
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
+      int row0, valid, local0;
+      kit.get(d, j, row0, valid, local0);
       mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1u);
       uint8_t* v_dst = smem_gen + TILE_BYTES * (2 + 2 * st);
       mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
-      tma_load_3d(v_dst, &tm, &v_full[st], vcol, j * BKV, b);
-      tma_load_3d(v_dst + TILE_BYTES / 2, &tm, &v_full[st], vcol + 64, j * BKV, b);
+      tma_load_rows(v_dst, &tm, &v_full[st], vcol, row0);
+      tma_load_rows(v_dst + TILE_BYTES / 2, &tm, &v_full[st], vcol + 64, row0);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
@@ -178,7 +250,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
     const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    const int q = q0 + r;
+    const int ql = d.q_local0 + r;  // query index inside its segment
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     float o[64];
 #pragma unroll
@@ -205,15 +277,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
 
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
-      const int k0 = j * BKV;
-      if (wg == 0) {  // key-padding bitmask of this block
-        const int mk = (k0 + r < p.L) ? p.key_mask[(long long)b * p.L + k0 + r] : 0;
+      int row0, valid, local0;
+      kit.get(d, j, row0, valid, local0);
+      if (wg == 0) {  // validity bitmask of this block's 128 keys: inside the segment AND a real token
+        const int mk = (r < valid) ? p.key_mask[row0 + r] : 0;
         const uint32_t bal = __ballot_sync(0xffffffffu, mk != 0);
         if (lane == 0) s_maskw[st][quad] = bal;
       }
       named_bar_sync(1, 256);
       const uint32_t w0 = s_maskw[st][2 * wg], w1 = s_maskw[st][2 * wg + 1];
-      const bool diag = (j == qb);                                   // only the diagonal block needs key <= q
+      // causal clipping is needed only when an own key of the block can lie after the tile's first query
+      const bool diag = local0 >= 0 && (local0 + BKV - 1 > d.q_local0);
       const bool plain = !diag && (w0 & w1) == 0xFFFFFFFFu;          // no masking at all (the common case)
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
@@ -224,7 +298,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_empty[st]);  // scores are in registers: S[st] may be overwritten by QK_{j+2}
-      const int kbase = k0 + wg * 64;
+      const int kbase = local0 + wg * 64;  // local index of this warpgroup's first key (own blocks)
       // ---- row max over the own 64 keys, then exchange with the other warpgroup ----
       float mx = -INFINITY;
       if (plain) {
@@ -234,8 +308,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const bool ok0 = ((w0 >> i) & 1u) && (!diag || kbase + i <= q);
-          const bool ok1 = ((w1 >> i) & 1u) && (!diag || kbase + 32 + i <= q);
+          const bool ok0 = ((w0 >> i) & 1u) && (!diag || kbase + i <= ql);
+          const bool ok1 = ((w1 >> i) & 1u) && (!diag || kbase + 32 + i <= ql);
           const float a = ok0 ? __uint_as_float(v0[i]) * p.scale_log2 : -INFINITY;
           const float c = ok1 ? __uint_as_float(v1[i]) * p.scale_log2 : -INFINITY;
           v0[i] = __float_as_uint(a);  // keep the masked, scaled score
@@ -287,9 +361,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
     named_bar_sync(3, 256);
     const float l_tot = l_run + s_l[wg ^ 1][r];
     const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-    if (q < p.L) {
-      if (wg == 0) p.lse2[((long long)b * p.nq + h) * p.L + q] = l_tot > 0.f ? m_run + log2f(l_tot) : INFINITY;
-      bf16* dst = p.out + ((long long)b * p.L + q) * p.nq * HD + h * HD + wg * 64;
+    if (r < d.q_rows) {
+      if (wg == 0)
+        p.lse2[(long long)d.stat0 + (long long)h * p.stat_h + r] = l_tot > 0.f ? m_run + log2f(l_tot) : INFINITY;
+      bf16* dst = p.out + (long long)(d.q_row0 + r) * p.nq * HD + h * HD + wg * 64;
 #pragma unroll
       for (int i = 0; i < 64; i += 8) {
         float f[8];
@@ -319,55 +394,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const FwdParams p) {
 // The 64-row streamed tiles are stored [d-half][64 rows][128 B]; the SAME smem tile is read K-major (rows = N)
 // by the score MMAs and MN-major (rows = K) by the gradient MMAs.
 // ==================================================================================================
-constexpr int HALF_TILE = 64 * HD * 2;  // 16 KB: [2 d-halves of 8 KB][64 rows][128 B]
-
-constexpr uint32_t idesc_n(int n, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(128 >> 4) << 24);
-}
-
-struct BwdParams {
-  const int* key_mask;
-  const float* lse2;
-  const float* delta;
-  bf16* dqkv;
-  int L, nq, nkv;
-  float scale, scale_log2;
-};
-
-// this thread's row r of a [128 rows][64 cols] bf16 K-major SW128 tile: store columns col0..col0+31
-__device__ __forceinline__ void store_row32_sw128(uint32_t tile, int r, int col0, const float* f) {
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int cc = col0 / 8 + u;  // 16-byte chunk 0..7 within the 128-byte row
-    const uint32_t addr = tile + r * 128 + ((cc ^ (r & 7)) << 4);
-    const bf16x8 pk = pack8(&f[u * 8]);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                 "r"(pk.u.x), "r"(pk.u.y), "r"(pk.u.z), "r"(pk.u.w)
-                 : "memory");
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // dQ
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(384, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_do128,
-                      const __grid_constant__ CUtensorMap tm_kv64, const BwdParams p) {
+                      const __grid_constant__ CUtensorMap tm_kv64, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t qdo_full, kv_full[3], kv_empty[3], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], dq_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ int s_mask[2][64];
+  __shared__ uint32_t s_maskw[2][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   // [Q 32K][dO 32K][3 x (K 16K, V 16K)][dS0 16K][dS1 16K]  = 192 KB
   const uint32_t sQ = smem_base, sdO = sQ + TILE_BYTES, sKV = sdO + TILE_BYTES, sDS = sKV + 6 * HALF_TILE;
-  const int qb = (int)gridDim.x - 1 - (int)blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const QBlock d = p.qblocks ? p.qblocks[blockIdx.x] : classic_qblock(p);
+  const int h = blockIdx.y;
   const int g = h / (p.nq / p.nkv);
-  const int q0 = qb * BQ;
-  const int n_kb = min((q0 + BQ + 63) / 64, (p.L + 63) / 64);  // 64-key blocks that intersect keys <= q0+127
+  const KeyIter<64> kit(d);
+  const int n_kb = kit.n_tot;
 
   if (threadIdx.x == 0) {
     mbar_init(&qdo_full, 1);
@@ -397,21 +443,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     mbar_arrive_expect_tx(&qdo_full, 2 * TILE_BYTES);
-    tma_load_3d(smem_gen, &tm_q128, &qdo_full, h * HD, q0, b);
-    tma_load_3d(smem_gen + TILE_BYTES / 2, &tm_q128, &qdo_full, h * HD + 64, q0, b);
-    tma_load_3d(smem_gen + TILE_BYTES, &tm_do128, &qdo_full, h * HD, q0, b);
-    tma_load_3d(smem_gen + TILE_BYTES + TILE_BYTES / 2, &tm_do128, &qdo_full, h * HD + 64, q0, b);
+    tma_load_rows(smem_gen, &tm_q128, &qdo_full, h * HD, d.q_row0);
+    tma_load_rows(smem_gen + TILE_BYTES / 2, &tm_q128, &qdo_full, h * HD + 64, d.q_row0);
+    tma_load_rows(smem_gen + TILE_BYTES, &tm_do128, &qdo_full, h * HD, d.q_row0);
+    tma_load_rows(smem_gen + TILE_BYTES + TILE_BYTES / 2, &tm_do128, &qdo_full, h * HD + 64, d.q_row0);
     const int kcol = (p.nq + g) * HD, vcol = (p.nq + p.nkv + g) * HD;
     for (int j = 0; j < n_kb; ++j) {
       const int st = j % 3;
+      int row0, valid, local0;
+      kit.get(d, j, row0, valid, local0);
       mbar_wait(&kv_empty[st], ((j / 3) & 1) ^ 1u);
       uint8_t* kd = smem_gen + 2 * TILE_BYTES + st * 2 * HALF_TILE;
       uint8_t* vd = kd + HALF_TILE;
       mbar_arrive_expect_tx(&kv_full[st], 2 * HALF_TILE);
-      tma_load_3d(kd, &tm_kv64, &kv_full[st], kcol, j * 64, b);
-      tma_load_3d(kd + HALF_TILE / 2, &tm_kv64, &kv_full[st], kcol + 64, j * 64, b);
-      tma_load_3d(vd, &tm_kv64, &kv_full[st], vcol, j * 64, b);
-      tma_load_3d(vd + HALF_TILE / 2, &tm_kv64, &kv_full[st], vcol + 64, j * 64, b);
+      tma_load_rows(kd, &tm_kv64, &kv_full[st], kcol, row0);
+      tma_load_rows(kd + HALF_TILE / 2, &tm_kv64, &kv_full[st], kcol + 64, row0);
+      tma_load_rows(vd, &tm_kv64, &kv_full[st], vcol, row0);
+      tma_load_rows(vd + HALF_TILE / 2, &tm_kv64, &kv_full[st], vcol + 64, row0);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
@@ -464,25 +512,28 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const int t = threadIdx.x - 128;
-    const int q = q0 + r;
+    const int ql = d.q_local0 + r;
+    const bool q_ok = r < d.q_rows;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const long long sidx = ((long long)b * p.nq + h) * p.L;
-    const float lse = q < p.L ? p.lse2[sidx + q] : INFINITY;
-    const float del = q < p.L ? p.delta[sidx + q] : 0.f;
+    const long long sidx = (long long)d.stat0 + (long long)h * p.stat_h + r;
+    const float lse = q_ok ? p.lse2[sidx] : INFINITY;
+    const float del = q_ok ? p.delta[sidx] : 0.f;
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
-      const int k0 = j * 64;
-      if (t < 64) {  // warps 4 and 5: key-padding bitmask of the block's two 32-key chunks
-        const int mk = (k0 + t < p.L) ? p.key_mask[(long long)b * p.L + k0 + t] : 0;
+      int row0, valid, local0;
+      kit.get(d, j, row0, valid, local0);
+      if (t < 64) {  // warps 4 and 5: validity bitmask of the block's two 32-key chunks
+        const int mk = (t < valid) ? p.key_mask[row0 + t] : 0;
         const uint32_t bal = __ballot_sync(0xffffffffu, mk != 0);
-        if (lane == 0) s_mask[st][t >> 5] = (int)bal;
+        if (lane == 0) s_maskw[st][t >> 5] = bal;
       }
       named_bar_sync(1, 256);
       const int c = wg;
-      const uint32_t mw = (uint32_t)s_mask[st][c];
-      const int kc0 = k0 + c * 32;
-      // no masking at all when every key of the chunk is real and at or before the tile's first query
-      const bool plain = (mw == 0xFFFFFFFFu) && (kc0 + 31 <= q0);
+      const uint32_t mw = s_maskw[st][c];
+      const int kc0 = local0 + c * 32;  // local index of the chunk's first key (own blocks)
+      // causal clipping only when an own key of the chunk can lie after the tile's first query
+      const bool diag = local0 >= 0 && (kc0 + 31 > d.q_local0);
+      const bool plain = !diag && mw == 0xFFFFFFFFu;
       mbar_wait(&sp_full[st], (j >> 1) & 1);
       mbar_wait(&ds_empty[st], ((j >> 1) & 1) ^ 1u);  // dQ MMA of block j-2 finished reading dS[st]
       tc_fence_after();
@@ -503,7 +554,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const bool ok = ((mw >> i) & 1u) && (kc0 + i <= q);
+            const bool ok = ((mw >> i) & 1u) && (!diag || kc0 + i <= ql);
             const float pr = ok ? ex2_approx(__uint_as_float(sv[i]) * p.scale_log2 - lse) : 0.f;
             f[i] = p.scale * pr * (__uint_as_float(dv[i]) - del);
           }
@@ -518,13 +569,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     tc_fence_after();
     {
       // the TMEM loads are .sync.aligned: every lane executes them, only the stores are predicated
-      bf16* dst = p.dqkv + ((long long)b * p.L + (q < p.L ? q : 0)) * (long long)(p.nq + 2 * p.nkv) * HD + h * HD;
+      bf16* dst = p.dqkv + (long long)(d.q_row0 + (q_ok ? r : 0)) * (long long)(p.nq + 2 * p.nkv) * HD + h * HD;
 #pragma unroll
       for (int c = 2 * wg; c < 2 * wg + 2; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + 256 + lane_addr + c * 32, v);
         tmem_ld_wait();
-        if (q < p.L) {
+        if (q_ok) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             float f[8];
@@ -549,7 +600,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(384, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_constant__ CUtensorMap tm_q64,
-                       const __grid_constant__ CUtensorMap tm_do64, const BwdParams p) {
+                       const __grid_constant__ CUtensorMap tm_do64, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t kv_full, qd_full[3], qd_empty[3], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], out_full;
   __shared__ uint32_t tmem_base_smem;
@@ -559,11 +610,24 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   // [K 32K][V 32K][3 x (Q 16K, dO 16K)][PT0 16K][dST0 16K][PT1 16K][dST1 16K] = 224 KB
   const uint32_t sK = smem_base, sV = sK + TILE_BYTES, sQD = sV + TILE_BYTES, sPD = sQD + 6 * HALF_TILE;
-  const int kb = blockIdx.x, g = blockIdx.y, b = blockIdx.z;   // key block 0 (most work) is scheduled first
+  KBlock d;
+  if (p.kblocks) {
+    d = p.kblocks[blockIdx.x];
+  } else {  // classic: grid = (ceil(L/128), nkv, B); key block 0 (most work) first
+    const int kb = blockIdx.x, b = blockIdx.z;
+    d.k_row0 = b * p.L + kb * BQ;
+    d.k_rows = min(BQ, p.L - kb * BQ);
+    d.k_local0 = kb * BQ;
+    d.q_row0 = b * p.L;
+    d.q_len = p.L;
+    d.causal = 1;
+    d.stat0 = b * p.nq * p.L;
+    d.out_row0 = 0;
+  }
+  const int g = blockIdx.y;
   const int group = p.nq / p.nkv;
-  const int k0 = kb * BKV;
-  const int qb0 = k0 / 64;                         // first 64-query block that can see these keys
-  const int nqb = (p.L + 63) / 64 - qb0;           // 64-query blocks per head
+  const int qb0 = d.causal ? d.k_local0 / 64 : 0;   // first 64-query block that can see these keys
+  const int nqb = (d.q_len + 63) / 64 - qb0;        // 64-query blocks per head
   const int n_it = group * nqb;
 
   if (threadIdx.x == 0) {
@@ -595,22 +659,22 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     // ===================== TMA producer =====================
     const int kcol = (p.nq + g) * HD, vcol = (p.nq + p.nkv + g) * HD;
     mbar_arrive_expect_tx(&kv_full, 2 * TILE_BYTES);
-    tma_load_3d(smem_gen, &tm_kv128, &kv_full, kcol, k0, b);
-    tma_load_3d(smem_gen + TILE_BYTES / 2, &tm_kv128, &kv_full, kcol + 64, k0, b);
-    tma_load_3d(smem_gen + TILE_BYTES, &tm_kv128, &kv_full, vcol, k0, b);
-    tma_load_3d(smem_gen + TILE_BYTES + TILE_BYTES / 2, &tm_kv128, &kv_full, vcol + 64, k0, b);
+    tma_load_rows(smem_gen, &tm_kv128, &kv_full, kcol, d.k_row0);
+    tma_load_rows(smem_gen + TILE_BYTES / 2, &tm_kv128, &kv_full, kcol + 64, d.k_row0);
+    tma_load_rows(smem_gen + TILE_BYTES, &tm_kv128, &kv_full, vcol, d.k_row0);
+    tma_load_rows(smem_gen + TILE_BYTES + TILE_BYTES / 2, &tm_kv128, &kv_full, vcol + 64, d.k_row0);
     for (int it = 0; it < n_it; ++it) {
       const int st = it % 3;
       const int h = g * group + it / nqb;
-      const int qs = (qb0 + it % nqb) * 64;
+      const int qrow = d.q_row0 + (qb0 + it % nqb) * 64;
       mbar_wait(&qd_empty[st], ((it / 3) & 1) ^ 1u);
       uint8_t* qd = smem_gen + 2 * TILE_BYTES + st * 2 * HALF_TILE;
       uint8_t* dd = qd + HALF_TILE;
       mbar_arrive_expect_tx(&qd_full[st], 2 * HALF_TILE);
-      tma_load_3d(qd, &tm_q64, &qd_full[st], h * HD, qs, b);
-      tma_load_3d(qd + HALF_TILE / 2, &tm_q64, &qd_full[st], h * HD + 64, qs, b);
-      tma_load_3d(dd, &tm_do64, &qd_full[st], h * HD, qs, b);
-      tma_load_3d(dd + HALF_TILE / 2, &tm_do64, &qd_full[st], h * HD + 64, qs, b);
+      tma_load_rows(qd, &tm_q64, &qd_full[st], h * HD, qrow);
+      tma_load_rows(qd + HALF_TILE / 2, &tm_q64, &qd_full[st], h * HD + 64, qrow);
+      tma_load_rows(dd, &tm_do64, &qd_full[st], h * HD, qrow);
+      tma_load_rows(dd + HALF_TILE / 2, &tm_do64, &qd_full[st], h * HD + 64, qrow);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
@@ -667,23 +731,24 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const int t = threadIdx.x - 128;
-    const int key = k0 + r;
-    const bool key_ok = key < p.L && p.key_mask[(long long)b * p.L + key] != 0;
+    const int kl = d.k_local0 + r;  // local key index (meaningful when causal)
+    const bool row_ok = r < d.k_rows;
+    const bool key_ok = row_ok && p.key_mask[d.k_row0 + (row_ok ? r : 0)] != 0;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
       const int h = g * group + it / nqb;
-      const int qs = (qb0 + it % nqb) * 64;
+      const int qs = (qb0 + it % nqb) * 64;  // local index of the block's first query
       if (t < 64) {
         const int qi = qs + t;
-        const long long sidx = ((long long)b * p.nq + h) * p.L;
-        s_lse[st][t] = qi < p.L ? p.lse2[sidx + qi] : INFINITY;   // +inf -> probability 0 for queries past the end
-        s_del[st][t] = qi < p.L ? p.delta[sidx + qi] : 0.f;
+        const long long sidx = (long long)d.stat0 + (long long)h * p.stat_h + qi;
+        s_lse[st][t] = qi < d.q_len ? p.lse2[sidx] : INFINITY;   // +inf -> probability 0 for queries past the end
+        s_del[st][t] = qi < d.q_len ? p.delta[sidx] : 0.f;
       }
       named_bar_sync(1, 256);
       const int c = wg;
       const int qc0 = qs + c * 32;
-      const bool need_cmp = qc0 < k0 + BKV - 1;   // some (key, query) pair of this chunk may violate key <= query
+      const bool need_cmp = d.causal && (qc0 < d.k_local0 + BQ - 1);  // some (key, query) pair may violate key <= query
       mbar_wait(&sp_full[st], (it >> 1) & 1);
       mbar_wait(&ds_empty[st], ((it >> 1) & 1) ^ 1u);
       tc_fence_after();
@@ -706,7 +771,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
           for (int u = 0; u < 4; ++u) {
             const int i = v4 * 4 + u;
             float pr = ex2_approx(__uint_as_float(sv[i]) * p.scale_log2 - ls[u]);
-            if (!key_ok || (need_cmp && key > qc0 + i)) pr = 0.f;  // select, never 0 * inf
+            if (!key_ok || (need_cmp && kl > qc0 + i)) pr = 0.f;  // select, never 0 * inf
             fp[i] = pr;
             fs[i] = p.scale * pr * (__uint_as_float(dv[i]) - ds4[u]);
           }
@@ -717,26 +782,31 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       fence_proxy_async_smem();
       mbar_arrive(&ds_full[st]);
     }
-    // ---- write dK, dV ----
+    // ---- write dK (warpgroup 0) / dV (warpgroup 1): bf16 into dqkv (classic) or an fp32 partial slab (packed) ----
     mbar_wait(&out_full, 0);
     tc_fence_after();
+    const int which = wg;
     const long long stride = (long long)(p.nq + 2 * p.nkv) * HD;
-    bf16* drow = p.dqkv + ((long long)b * p.L + (key < p.L ? key : 0)) * stride;
-    {
-      const int which = wg;
-      bf16* dst = drow + (which == 0 ? (p.nq + g) : (p.nq + p.nkv + g)) * HD;
+    bf16* dst16 = p.dqkv + (long long)(d.k_row0 + (row_ok ? r : 0)) * stride +
+                  (which == 0 ? (p.nq + g) : (p.nq + p.nkv + g)) * HD;
+    float* dst32 = p.kv_part ? p.kv_part + ((long long)(d.out_row0 + (row_ok ? r : 0)) * 2 * p.nkv + which * p.nkv + g) * HD
+                             : nullptr;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + 256 + which * 128 + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        if (key < p.L) {
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + 256 + which * 128 + lane_addr + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float f[8];
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = n_it > 0 ? __uint_as_float(v[u * 8 + i]) : 0.f;
-            *reinterpret_cast<bf16x8*>(dst + c * 32 + u * 8) = pack8(f);
+          for (int i = 0; i < 8; ++i) f[i] = n_it > 0 ? __uint_as_float(v[u * 8 + i]) : 0.f;
+          if (dst32) {
+            *reinterpret_cast<float4*>(dst32 + c * 32 + u * 8) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(dst32 + c * 32 + u * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            *reinterpret_cast<bf16x8*>(dst16 + c * 32 + u * 8) = pack8(f);
           }
         }
       }
@@ -747,6 +817,26 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// packed layout: dK/dV of key row m = sum (fixed order) of its fp32 partial rows -> bf16 into dqkv
+__global__ void kv_reduce_kernel(const float* __restrict__ part, const int* __restrict__ row_start,
+                                 const int* __restrict__ row_list, bf16* __restrict__ dqkv, int nq, int nkv) {
+  const int m = blockIdx.x;
+  const int s0 = row_start[m], s1 = row_start[m + 1];
+  const int width = 2 * nkv * HD;
+  const long long stride = (long long)(nq + 2 * nkv) * HD;
+  for (int c = threadIdx.x * 8; c < width; c += blockDim.x * 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = s0; s < s1; ++s) {
+      const float* src = part + (long long)row_list[s] * width + c;
+      const float4 a = *reinterpret_cast<const float4*>(src), b2 = *reinterpret_cast<const float4*>(src + 4);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b2.x; acc[5] += b2.y; acc[6] += b2.z; acc[7] += b2.w;
+    }
+    // partial row layout [which][g][HD] == dqkv columns (nq + which*nkv + g)*HD + d
+    *reinterpret_cast<bf16x8*>(dqkv + (long long)m * stride + (long long)nq * HD + c) = pack8(acc);
   }
 }
 
@@ -765,86 +855,149 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-}  // namespace
-
-// 3-D map over x[B][L][cols] bf16, box = 64 cols x 128 rows x 1 sequence, 128B swizzle
-int make_seq_map(CUtensorMap* tm, const void* base, int B, int L, long long cols, int box_rows) {
+// 2-D map over x[rows][cols] bf16, box = 64 cols x box_rows rows, 128B swizzle (rows past the end are zero-filled;
+// rows of a neighbouring segment that fall into a box are masked by index in the kernels)
+int make_rows_map(CUtensorMap* tm, const void* base, long long rows, long long cols, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(B200RL_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * 2 * (cuuint64_t)L};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error(B200RL_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: CUresult %d", (int)r);
+  if (r != CUDA_SUCCESS) return set_error(B200RL_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
   return 0;
 }
 
-int attn_fwd_tc_launch(const void* qkv, const int* key_mask, void* out, float* lse, int B, int L, int nq, int nkv,
-                       float scale, cudaStream_t stream) {
-  CUtensorMap tm;
-  int rc = make_seq_map(&tm, qkv, B, L, (long long)(nq + 2 * nkv) * HD, 128);
-  if (rc) return rc;
-  FwdParams p;
-  p.key_mask = key_mask;
-  p.out = (bf16*)out;
-  p.lse2 = lse;
-  p.L = L;
-  p.nq = nq;
-  p.nkv = nkv;
-  p.scale_log2 = scale * 1.4426950408889634f;
-  const int smem = 6 * TILE_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200RL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  dim3 grid((L + BQ - 1) / BQ, nq, B);
-  attn_fwd_tc_kernel<<<grid, 384, smem, stream>>>(tm, p);
-  B200RL_LAUNCH_OK();
+constexpr int SMEM_FWD = 6 * TILE_BYTES + 1024;
+constexpr int SMEM_DQ = 2 * TILE_BYTES + 8 * HALF_TILE + 1024;
+constexpr int SMEM_DKV = 2 * TILE_BYTES + 10 * HALF_TILE + 1024;
+
+int set_attrs() {
+  static bool done = false;
+  if (done) return 0;
+  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
+  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
+  done = true;
   return 0;
 }
 
-
-int attn_bwd_tc_launch(const void* qkv, const int* key_mask, const void* dout, const float* lse, const float* delta,
-                       void* dqkv, int B, int L, int nq, int nkv, float scale, cudaStream_t stream) {
-  const long long qcols = (long long)(nq + 2 * nkv) * HD, ocols = (long long)nq * HD;
-  CUtensorMap q128, q64, d128, d64;
-  int rc;
-  if ((rc = make_seq_map(&q128, qkv, B, L, qcols, 128))) return rc;
-  if ((rc = make_seq_map(&q64, qkv, B, L, qcols, 64))) return rc;
-  if ((rc = make_seq_map(&d128, dout, B, L, ocols, 128))) return rc;
-  if ((rc = make_seq_map(&d64, dout, B, L, ocols, 64))) return rc;
-  BwdParams p;
+AttnParams base_params(const int* key_mask, int nq, int nkv, float scale) {
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
   p.key_mask = key_mask;
-  p.lse2 = lse;
-  p.delta = delta;
-  p.dqkv = (bf16*)dqkv;
-  p.L = L;
   p.nq = nq;
   p.nkv = nkv;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
-  static bool attr_set = false;
-  const int smem_dq = 2 * TILE_BYTES + 8 * HALF_TILE + 1024;
-  const int smem_dkv = 2 * TILE_BYTES + 10 * HALF_TILE + 1024;
-  if (!attr_set) {
-    B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
-    B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv));
-    attr_set = true;
-  }
+  return p;
+}
+
+struct BwdMaps {
+  CUtensorMap q128, q64, d128, d64;
+};
+int make_bwd_maps(BwdMaps& m, const void* qkv, const void* dout, long long rows, int nq, int nkv) {
+  const long long qcols = (long long)(nq + 2 * nkv) * HD, ocols = (long long)nq * HD;
+  int rc;
+  if ((rc = make_rows_map(&m.q128, qkv, rows, qcols, 128))) return rc;
+  if ((rc = make_rows_map(&m.q64, qkv, rows, qcols, 64))) return rc;
+  if ((rc = make_rows_map(&m.d128, dout, rows, ocols, 128))) return rc;
+  if ((rc = make_rows_map(&m.d64, dout, rows, ocols, 64))) return rc;
+  return set_attrs();
+}
+
+}  // namespace
+
+// ---- classic layout -----------------------------------------------------------------------------------
+int attn_fwd_tc_launch(const void* qkv, const int* key_mask, void* out, float* lse, int B, int L, int nq, int nkv,
+                       float scale, cudaStream_t stream) {
+  CUtensorMap tm;
+  int rc = make_rows_map(&tm, qkv, (long long)B * L, (long long)(nq + 2 * nkv) * HD, 128);
+  if (rc) return rc;
+  if ((rc = set_attrs())) return rc;
+  AttnParams p = base_params(key_mask, nq, nkv, scale);
+  p.out = (bf16*)out;
+  p.lse2 = lse;
+  p.L = L;
+  p.stat_h = L;
+  dim3 grid((L + BQ - 1) / BQ, nq, B);
+  attn_fwd_tc_kernel<<<grid, 384, SMEM_FWD, stream>>>(tm, p);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
+int attn_bwd_tc_launch(const void* qkv, const int* key_mask, const void* dout, const float* lse, const float* delta,
+                       void* dqkv, int B, int L, int nq, int nkv, float scale, cudaStream_t stream) {
+  BwdMaps m;
+  int rc = make_bwd_maps(m, qkv, dout, (long long)B * L, nq, nkv);
+  if (rc) return rc;
+  AttnParams p = base_params(key_mask, nq, nkv, scale);
+  p.lse2 = const_cast<float*>(lse);
+  p.delta = delta;
+  p.dqkv = (bf16*)dqkv;
+  p.L = L;
+  p.stat_h = L;
   {
     dim3 grid((L + BQ - 1) / BQ, nq, B);
-    attn_bwd_dq_tc_kernel<<<grid, 384, smem_dq, stream>>>(q128, d128, q64, p);
+    attn_bwd_dq_tc_kernel<<<grid, 384, SMEM_DQ, stream>>>(m.q128, m.d128, m.q64, p);
     B200RL_LAUNCH_OK();
   }
   {
-    dim3 grid((L + BKV - 1) / BKV, nkv, B);
-    attn_bwd_dkv_tc_kernel<<<grid, 384, smem_dkv, stream>>>(q128, q64, d64, p);
+    dim3 grid((L + BQ - 1) / BQ, nkv, B);
+    attn_bwd_dkv_tc_kernel<<<grid, 384, SMEM_DKV, stream>>>(m.q128, m.q64, m.d64, p);
     B200RL_LAUNCH_OK();
   }
+  return 0;
+}
+
+// ---- packed (shared-prompt) layout: lse / delta are indexed [head][row] (stat_h = rows) -------------------------
+int attn_fwd_seg_launch(const void* qkv, const int* key_mask, void* out, float* lse, long long rows, int nq, int nkv,
+                        float scale, const QBlock* qblocks_dev, int n_qblocks, cudaStream_t stream) {
+  CUtensorMap tm;
+  int rc = make_rows_map(&tm, qkv, rows, (long long)(nq + 2 * nkv) * HD, 128);
+  if (rc) return rc;
+  if ((rc = set_attrs())) return rc;
+  AttnParams p = base_params(key_mask, nq, nkv, scale);
+  p.out = (bf16*)out;
+  p.lse2 = lse;
+  p.qblocks = qblocks_dev;
+  p.stat_h = (int)rows;
+  dim3 grid(n_qblocks, nq, 1);
+  attn_fwd_tc_kernel<<<grid, 384, SMEM_FWD, stream>>>(tm, p);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
+int attn_bwd_seg_launch(const void* qkv, const int* key_mask, const void* dout, const float* lse, const float* delta,
+                        void* dqkv, float* kv_part, long long rows, int nq, int nkv, float scale,
+                        const QBlock* qblocks_dev, int n_qblocks, const KBlock* kblocks_dev, int n_kblocks,
+                        const int* red_start_dev, const int* red_list_dev, cudaStream_t stream) {
+  BwdMaps m;
+  int rc = make_bwd_maps(m, qkv, dout, rows, nq, nkv);
+  if (rc) return rc;
+  AttnParams p = base_params(key_mask, nq, nkv, scale);
+  p.lse2 = const_cast<float*>(lse);
+  p.delta = delta;
+  p.dqkv = (bf16*)dqkv;
+  p.kv_part = kv_part;
+  p.qblocks = qblocks_dev;
+  p.kblocks = kblocks_dev;
+  p.stat_h = (int)rows;
+  {
+    dim3 grid(n_qblocks, nq, 1);
+    attn_bwd_dq_tc_kernel<<<grid, 384, SMEM_DQ, stream>>>(m.q128, m.d128, m.q64, p);
+    B200RL_LAUNCH_OK();
+  }
+  {
+    dim3 grid(n_kblocks, nkv, 1);
+    attn_bwd_dkv_tc_kernel<<<grid, 384, SMEM_DKV, stream>>>(m.q128, m.q64, m.d64, p);
+    B200RL_LAUNCH_OK();
+  }
+  kv_reduce_kernel<<<(unsigned)rows, 128, 0, stream>>>(kv_part, red_start_dev, red_list_dev, (bf16*)dqkv, nq, nkv);
+  B200RL_LAUNCH_OK();
   return 0;
 }
 

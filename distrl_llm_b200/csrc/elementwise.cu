@@ -129,9 +129,10 @@ __global__ void rope_table_kernel(float* __restrict__ cs, int L, int half, float
 }
 
 __global__ void rope_kernel(bf16* __restrict__ qkv, const float* __restrict__ cs, int L,
-                            long long row_stride, int n_rot_heads, int D, float sign) {
+                            long long row_stride, int n_rot_heads, int D, float sign,
+                            const int* __restrict__ pos_idx) {
   const size_t m = blockIdx.x;
-  const int pos = (int)(m % L);
+  const int pos = pos_idx ? pos_idx[m] : (int)(m % L);  // packed layout carries explicit positions
   const int half = D / 2;
   bf16* row = qkv + m * row_stride;
   const float2* tab = reinterpret_cast<const float2*>(cs) + (size_t)pos * half;
@@ -210,6 +211,32 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ x, bf16* __restrict_
   uint4* dst = reinterpret_cast<uint4*>(out + (size_t)r * H);
   for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = src[i];
 }
+// packed layout: out[r, :] = x[src[r], :]
+__global__ void gather_rows_idx_kernel(const bf16* __restrict__ x, const int* __restrict__ src,
+                                       bf16* __restrict__ out, int H) {
+  const int r = blockIdx.x;
+  const uint4* s4 = reinterpret_cast<const uint4*>(x + (size_t)src[r] * H);
+  uint4* d4 = reinterpret_cast<uint4*>(out + (size_t)r * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) d4[i] = s4[i];
+}
+// packed layout: dx[m, :] = sum over the scored rows r whose hidden state is row m (CSR start/list, fixed order);
+// rows without a scored position get zeros.  The shared last prompt row collects one term per completion.
+__global__ void scatter_add_rows_kernel(const bf16* __restrict__ d, const int* __restrict__ start,
+                                        const int* __restrict__ list, bf16* __restrict__ dx, int H) {
+  const int m = blockIdx.x;
+  const int s0 = start[m], s1 = start[m + 1];
+  bf16x8* dst = reinterpret_cast<bf16x8*>(dx + (size_t)m * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = s0; s < s1; ++s) {
+      float f[8];
+      unpack8(reinterpret_cast<const bf16x8*>(d + (size_t)list[s] * H)[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    dst[i] = pack8(acc);
+  }
+}
 // scatter back (zero elsewhere): dx[b*L + start + t, :] = d[b*T + t, :], other rows 0
 __global__ void scatter_rows_kernel(const bf16* __restrict__ d, bf16* __restrict__ dx, int H, int L,
                                     int T, int start) {
@@ -269,7 +296,30 @@ extern "C" int b200rl_rope(void* qkv, const float* cs, int M, int L, long long r
   B200RL_REQUIRE(qkv && cs && M > 0 && L > 0 && head_dim % 16 == 0 && row_stride % 8 == 0,
                  "rope: bad args");
   rope_kernel<<<M, 128, 0, STREAM>>>((bf16*)qkv, cs, L, row_stride, n_rot_heads, head_dim,
-                                     backward ? -1.f : 1.f);
+                                     backward ? -1.f : 1.f, nullptr);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200rl_rope_pos(void* qkv, const float* cs, const int* pos, int M, long long row_stride,
+                               int n_rot_heads, int head_dim, int backward, void* stream) {
+  B200RL_REQUIRE(qkv && cs && pos && M > 0 && head_dim % 16 == 0 && row_stride % 8 == 0, "rope_pos: bad args");
+  rope_kernel<<<M, 128, 0, STREAM>>>((bf16*)qkv, cs, 1, row_stride, n_rot_heads, head_dim, backward ? -1.f : 1.f, pos);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200rl_gather_rows_idx(const void* x, const int* src, void* out, int R, int H, void* stream) {
+  B200RL_REQUIRE(x && src && out && R > 0 && H % 8 == 0, "gather_rows_idx: bad args");
+  gather_rows_idx_kernel<<<R, 128, 0, STREAM>>>((const bf16*)x, src, (bf16*)out, H);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200rl_scatter_add_rows(const void* d, const int* start, const int* list, void* dx, int M, int H,
+                                       void* stream) {
+  B200RL_REQUIRE(d && start && list && dx && M > 0 && H % 8 == 0, "scatter_add_rows: bad args");
+  scatter_add_rows_kernel<<<M, 128, 0, STREAM>>>((const bf16*)d, start, list, (bf16*)dx, H);
   B200RL_LAUNCH_OK();
   return 0;
 }

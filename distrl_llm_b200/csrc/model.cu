@@ -70,6 +70,9 @@ int b200rl_loss_coef_kl(const int*, const double*, float*, float*, double, int*,
 int b200rl_loss_value_kl(const float*, const int*, const double*, const float*, double, double*, int, int, int, void*);
 int b200rl_nf4_dequant(const void*, const float*, void*, int, int, int, void*);
 int b200rl_lora_pack(const float*, void*, const void*, int, int, void*);
+int b200rl_rope_pos(void*, const float*, const int*, int, long long, int, int, int, void*);
+int b200rl_gather_rows_idx(const void*, const int*, void*, int, int, void*);
+int b200rl_scatter_add_rows(const void*, const int*, const int*, void*, int, int, void*);
 }
 
 namespace {
@@ -171,7 +174,8 @@ struct b200rl_model {
   };
   std::vector<LayerAct> act;
   bf16 *wbuf, *xsel, *hsel, *logits, *dhsel, *dx, *dh, *dact, *dgu, *dattn, *dqkv, *du;
-  float *rstd_f, *lp, *coef, *klw, *delta, *slabs, *rope_cs;
+  float *rstd_f, *lp, *coef, *klw, *delta, *slabs, *rope_cs, *kvpart;
+  long long kvpart_rows;
   int *targets, *lens;
   long long slab_elems;
   int rope_L;
@@ -259,7 +263,7 @@ static int dw_splits(int tokens, int Ny, int bn_cols) {
 struct WsPlan {
   long long total;
   long long off_arena, off_pack, off_X, off_wbuf, off_xsel, off_hsel, off_logits, off_dhsel, off_dx,
-      off_dh, off_dact, off_dgu, off_dattn, off_dqkv, off_du, off_rstd_f, off_lp, off_coef, off_klw, off_delta,
+      off_dh, off_dact, off_dgu, off_dattn, off_dqkv, off_du, off_rstd_f, off_lp, off_coef, off_klw, off_delta, off_kvpart,
       off_slabs, off_rope, off_targets, off_lens, off_layers;
   long long per_layer;
   long long slab_elems;
@@ -298,6 +302,8 @@ static WsPlan plan_ws(const b200rl_model* m) {
   p.off_coef = take(R * 4);
   p.off_klw = take(R * 4);
   p.off_delta = take((long long)c.max_batch * c.n_q_heads * c.max_seq * 4);
+  // fp32 dK/dV partial slabs of the packed (shared-prompt) attention backward: <= 2*max_tokens rows
+  p.off_kvpart = take(c.head_dim == 128 ? 2 * Mt * 2 * c.n_kv_heads * c.head_dim * 4 : 0);
   long long nmax = std::max(std::max(QKV, 2 * I), std::max(H, I));
   p.slab_elems = 16 * std::max(nmax, (long long)128) * m->K2max;  // generous: <=16 splits
   // tighter: splits * Ny is bounded by ~ (num_sms/tiles+1) * Ny <= 2*128*num_sms for Ny < 128*sms
@@ -406,6 +412,8 @@ extern "C" int b200rl_model_create(const b200rl_model_config* cfg, const b200rl_
   m->coef = (float*)(w + p.off_coef);
   m->klw = (float*)(w + p.off_klw);
   m->delta = (float*)(w + p.off_delta);
+  m->kvpart = (float*)(w + p.off_kvpart);
+  m->kvpart_rows = cfg->head_dim == 128 ? 2LL * cfg->max_tokens : 0;
   m->slabs = (float*)(w + p.off_slabs);
   m->slab_elems = p.slab_elems;
   m->rope_cs = (float*)(w + p.off_rope);
@@ -607,17 +615,26 @@ int lora_dw(b200rl_model* m, cudaStream_t st, const Group& g, const bf16* dY, lo
 
 }  // namespace
 
-extern "C" int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const int* attn_mask,
-                                          const int* answer_mask, const double* adv, float* lp_out,
-                                          double* loss_accum, int B, int P, int T, int nb, int grpo,
-                                          int backward, int lora_off, const float* ref_lp, double kl_beta,
-                                          void* stream) {
-  B200RL_REQUIRE(m && ids && attn_mask && answer_mask, "model_microbatch: null pointer");
+namespace {
+// token layout of one micro-batch: classic [B, L] padded batch, or the packed shared-prompt layout
+struct Layout {
+  int M, B, T, L, P;
+  const int* ids;
+  const int* key_mask;      // classic: attention_mask [B, L]; packed: [rows]
+  const int* answer_mask;
+  const b200rl_packed_batch* pb;  // nullptr = classic
+};
+}  // namespace
+
+static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv, float* lp_out, double* loss_accum,
+                          int nb, int grpo, int backward, int lora_off, const float* ref_lp, double kl_beta,
+                          void* stream) {
   const b200rl_model_config& c = m->cfg;
-  const int L = P + T, M = B * L, R = B * T;
-  B200RL_REQUIRE(B > 0 && P >= 1 && T >= 1, "model_microbatch: need B>0, P>=1, T>=1 (B=%d P=%d T=%d)", B, P, T);
-  B200RL_REQUIRE(M <= c.max_tokens && B <= c.max_batch && L <= c.max_seq && R <= c.max_score_rows,
-                 "model_microbatch: batch exceeds the workspace (B=%d L=%d)", B, L);
+  const b200rl_packed_batch* pb = lay.pb;
+  const int M = lay.M, B = lay.B, T = lay.T, L = lay.L, P = lay.P, R = B * T;
+  const int* ids = lay.ids;
+  const int* attn_mask = lay.key_mask;
+  const int* answer_mask = lay.answer_mask;
   B200RL_REQUIRE(!backward || (adv && nb >= 1), "model_microbatch: backward needs adv and nb");
   B200RL_REQUIRE(!(backward && lora_off), "model_microbatch: the adapter-off (reference policy) pass is forward only");
   B200RL_REQUIRE(kl_beta == 0.0 || ref_lp, "model_microbatch: kl_beta != 0 needs ref_lp");
@@ -654,9 +671,11 @@ extern "C" int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const
     RC(gemm_l(m, CAT_GEMM, 0, st, a.h1, H, m->wbuf, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, lora ? gq.K2 : 0, a.qkv, QKV,
                (const bf16*)w.qkv_bias, nullptr, 0, 1.f, M, QKV));
     PM(CAT_ROW, 2.0 * M * (c.n_q_heads + c.n_kv_heads) * c.head_dim * 2);
-    RC(b200rl_rope(a.qkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 0, stream));
+    if (pb) RC(b200rl_rope_pos(a.qkv, m->rope_cs, pb->pos, M, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 0, stream));
+    else RC(b200rl_rope(a.qkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 0, stream));
     PM(CAT_ATTN_FWD, 2.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
-    RC(b200rl_attn_fwd(a.qkv, attn_mask, a.attn_o, a.lse, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
+    if (pb) RC(b200rl_attn_seg_fwd(a.qkv, attn_mask, a.attn_o, a.lse, M, c.n_q_heads, c.n_kv_heads, attn_scale, pb->qblocks, pb->n_qblocks, stream));
+    else RC(b200rl_attn_fwd(a.qkv, attn_mask, a.attn_o, a.lse, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
     if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
     PM(CAT_DEQUANT, 2.5625 * (H) * (QD));
     RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 0, stream));
@@ -680,18 +699,22 @@ extern "C" int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const
   // head: only the T scored positions (rows P-1 .. L-2) go through the final norm and lm_head
   bf16* xf = m->X + (long long)c.n_layers * Mt * H;
   PM(CAT_ROW, 2.0 * R * H * 2);
-  RC(b200rl_gather_rows(xf, m->xsel, B, L, T, P - 1, H, stream));
+  if (pb) RC(b200rl_gather_rows_idx(xf, pb->score_src, m->xsel, R, H, stream));
+  else RC(b200rl_gather_rows(xf, m->xsel, B, L, T, P - 1, H, stream));
   PM(CAT_ROW, 2.0 * R * H * 2);
   RC(b200rl_rmsnorm_fwd(m->xsel, m->final_norm, m->hsel, m->rstd_f, R, H, c.rms_eps, stream));
   RC(gemm_l(m, CAT_GEMM, 0, st, m->hsel, H, m->lm_head, H, H, nullptr, 0, nullptr, 0, 0, m->logits, V, nullptr, nullptr, 0, 1.f, R, V));
   PM(CAT_MISC, 0);
-  targets_kernel<<<(R + 255) / 256, 256, 0, st>>>(ids, m->targets, L, P, T, R);
-  B200RL_LAUNCH_OK();
+  const int* targets = pb ? pb->targets : m->targets;
+  if (!pb) {
+    targets_kernel<<<(R + 255) / 256, 256, 0, st>>>(ids, m->targets, L, P, T, R);
+    B200RL_LAUNCH_OK();
+  }
   PM(CAT_MISC, 0);
   if (backward) RC(b200rl_loss_coef_kl(answer_mask, adv, m->coef, use_kl ? m->klw : nullptr, kl_beta, m->lens, B, T, nb, stream));
   float* lp = lp_out ? lp_out : m->lp;
   PM(CAT_LOGPROB, (backward ? 2.0 : 1.0) * R * V * 2);
-  RC(b200rl_logprob_kl(m->logits, V, m->targets, backward ? m->coef : nullptr, use_kl ? m->klw : nullptr,
+  RC(b200rl_logprob_kl(m->logits, V, targets, backward ? m->coef : nullptr, use_kl ? m->klw : nullptr,
                        use_kl ? ref_lp : nullptr, lp, R, V, backward ? 1 : 0, stream));
   PM(CAT_MISC, 0);
   if (loss_accum && adv)
@@ -706,7 +729,8 @@ extern "C" int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const
   PM(CAT_ROW, 3.0 * R * H * 2);
   RC(b200rl_rmsnorm_bwd(m->dhsel, m->xsel, m->final_norm, m->rstd_f, nullptr, m->dhsel, R, H, stream));
   PM(CAT_ROW, 1.0 * (R + M) * H * 2);
-  RC(b200rl_scatter_rows(m->dhsel, m->dx, B, L, T, P - 1, H, stream));
+  if (pb) RC(b200rl_scatter_add_rows(m->dhsel, pb->sc_start, pb->sc_list, m->dx, M, H, stream));
+  else RC(b200rl_scatter_rows(m->dhsel, m->dx, B, L, T, P - 1, H, stream));
   for (int l = c.n_layers - 1; l >= 0; --l) {
     const b200rl_layer_weights& w = m->layers[l];
     b200rl_model::LayerAct& a = m->act[l];
@@ -741,9 +765,12 @@ extern "C" int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const
     RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, m->wbuf, QD, H, m->du, go.K2, ar + go.acat, QD, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
     // ---- attention + rope
     PM(CAT_ATTN_BWD, 4.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
-    RC(b200rl_attn_bwd(a.qkv, attn_mask, a.attn_o, m->dattn, a.lse, m->delta, m->dqkv, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
+    if (pb) RC(b200rl_attn_seg_bwd(a.qkv, attn_mask, a.attn_o, m->dattn, a.lse, m->delta, m->dqkv, m->kvpart, M, c.n_q_heads, c.n_kv_heads, attn_scale,
+                                   pb->qblocks, pb->n_qblocks, pb->kblocks, pb->n_kblocks, pb->red_start, pb->red_list, stream));
+    else RC(b200rl_attn_bwd(a.qkv, attn_mask, a.attn_o, m->dattn, a.lse, m->delta, m->dqkv, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
     PM(CAT_ROW, 2.0 * M * (c.n_q_heads + c.n_kv_heads) * c.head_dim * 2);
-    RC(b200rl_rope(m->dqkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 1, stream));
+    if (pb) RC(b200rl_rope_pos(m->dqkv, m->rope_cs, pb->pos, M, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 1, stream));
+    else RC(b200rl_rope(m->dqkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 1, stream));
     // ---- qkv projection:  qkv = h1.Wqkv^T + u_qkv.Bqkv^T + bias
     RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dqkv, QKV, ar + gq.bcat, gq.K2, QKV, nullptr, 0, nullptr, 0, 0, m->du, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
     RC(lora_dw(m, st, gq, m->dqkv, QKV, a.u_qkv, a.h1, H, m->du, M));
@@ -790,10 +817,47 @@ extern "C" int b200rl_model_profile_read(b200rl_model* m, double* ms, double* wo
   return 0;
 }
 
+extern "C" int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const int* attn_mask,
+                                          const int* answer_mask, const double* adv, float* lp_out,
+                                          double* loss_accum, int B, int P, int T, int nb, int grpo,
+                                          int backward, int lora_off, const float* ref_lp, double kl_beta,
+                                          void* stream) {
+  B200RL_REQUIRE(m && ids && attn_mask && answer_mask, "model_microbatch: null pointer");
+  const b200rl_model_config& c = m->cfg;
+  const int L = P + T;
+  B200RL_REQUIRE(B > 0 && P >= 1 && T >= 1, "model_microbatch: need B>0, P>=1, T>=1 (B=%d P=%d T=%d)", B, P, T);
+  B200RL_REQUIRE(B * L <= c.max_tokens && B <= c.max_batch && L <= c.max_seq && B * T <= c.max_score_rows,
+                 "model_microbatch: batch exceeds the workspace (B=%d L=%d)", B, L);
+  Layout lay;
+  lay.M = B * L; lay.B = B; lay.T = T; lay.L = L; lay.P = P;
+  lay.ids = ids; lay.key_mask = attn_mask; lay.answer_mask = answer_mask; lay.pb = nullptr;
+  return run_microbatch(m, lay, adv, lp_out, loss_accum, nb, grpo, backward, lora_off, ref_lp, kl_beta, stream);
+}
+
 extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const int* attn_mask,
                                        const int* answer_mask, const double* adv, float* lp_out,
                                        double* loss_accum, int B, int P, int T, int nb, int grpo,
                                        int backward, void* stream) {
   return b200rl_model_microbatch_ex(m, ids, attn_mask, answer_mask, adv, lp_out, loss_accum, B, P, T, nb, grpo,
                                     backward, 0, nullptr, 0.0, stream);
+}
+
+extern "C" int b200rl_model_microbatch_packed(b200rl_model* m, const b200rl_packed_batch* pb, const double* adv,
+                                              float* lp_out, double* loss_accum, int nb, int grpo, int backward,
+                                              int lora_off, const float* ref_lp, double kl_beta, void* stream) {
+  B200RL_REQUIRE(m && pb, "model_microbatch_packed: null pointer");
+  const b200rl_model_config& c = m->cfg;
+  B200RL_REQUIRE(c.head_dim == 128, "model_microbatch_packed: the packed layout needs head_dim 128 (tcgen05 attention)");
+  B200RL_REQUIRE(pb->ids && pb->pos && pb->key_mask && pb->score_src && pb->targets && pb->answer_mask &&
+                     pb->sc_start && pb->sc_list && pb->qblocks && pb->kblocks && pb->red_start && pb->red_list,
+                 "model_microbatch_packed: null array");
+  B200RL_REQUIRE(pb->rows > 0 && pb->rows <= c.max_tokens && pb->B > 0 && pb->B <= c.max_batch && pb->T >= 1 &&
+                     pb->B * pb->T <= c.max_score_rows && pb->max_pos >= 1 && pb->max_pos <= c.max_seq,
+                 "model_microbatch_packed: batch exceeds the workspace (rows=%d B=%d T=%d)", pb->rows, pb->B, pb->T);
+  B200RL_REQUIRE(pb->part_rows <= m->kvpart_rows, "model_microbatch_packed: %d dK/dV partial rows > capacity %lld",
+                 pb->part_rows, m->kvpart_rows);
+  Layout lay;
+  lay.M = pb->rows; lay.B = pb->B; lay.T = pb->T; lay.L = pb->max_pos; lay.P = 0;
+  lay.ids = pb->ids; lay.key_mask = pb->key_mask; lay.answer_mask = pb->answer_mask; lay.pb = pb;
+  return run_microbatch(m, lay, adv, lp_out, loss_accum, nb, grpo, backward, lora_off, ref_lp, kl_beta, stream);
 }

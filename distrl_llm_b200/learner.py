@@ -17,7 +17,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, packing
 from .policy import LMConfig, Policy
 
 try:  # Ray is the reference's process model; optional here (not installed in the build image)
@@ -72,6 +72,9 @@ class BaseLearner:
         self.lr = config["lr"]                                    # :210
         self.weight_decay = config.get("weight_decay", 0.0)       # commented out in the reference (:210)
         self.kl_beta = float(config.get("kl_beta", 0.0))          # KL-to-reference weight; 0 = reference behaviour
+        # packed shared-prompt layout (packing.py): identical results, each distinct prompt of a micro-batch is
+        # processed once; needs the tcgen05 attention kernels (head_dim 128)
+        self.share_prompts = bool(config.get("share_prompts", policy.cfg.head_dim == 128))
         self.lora_save_path = config.get("lora_save_path", "lora_request_math")
         self.reference_quirks = reference_quirks
         self.generator = generator
@@ -99,10 +102,18 @@ class BaseLearner:
         ids, am, ansm = self._encode(messages, answers)
         B = ids.shape[0]
         lp = torch.empty(B, self.max_new_tokens, device=policy.device, dtype=torch.float32)
+        if self.share_prompts:
+            pk = self._pack(ids, am)
+            policy.microbatch_packed(pk, None, 1, False, backward=False, lp_out=lp)
+            return lp, pk.answer_mask
         d_ansm = self._h2d(ansm)
         policy.microbatch(self._h2d(ids), self._h2d(am), d_ansm, None, self.max_prompt_tokens,
                           self.max_new_tokens, 1, False, backward=False, lp_out=lp)
         return lp, d_ansm
+
+    def _pack(self, ids, am):
+        host = packing.pack_microbatch(ids.numpy(), am.numpy(), self.max_prompt_tokens, self.max_new_tokens)
+        return packing.PackedDevice(host, self.policy.device)
 
     # ---- loss + backward (:349-395 PG, :440-493 GRPO) ---------------------------------------------
     def compute_loss(self, messages, answers, rewards):
@@ -120,6 +131,15 @@ class BaseLearner:
             if self.reference_quirks and not bool(np.all(r != 0)):
                 continue
             ids, am, ansm = self._encode(messages[s:e], answers[s:e])
+            if self.share_prompts:
+                pk = self._pack(ids, am)
+                ref_lp = None
+                if self.kl_beta != 0.0:
+                    ref_lp = torch.empty(e - s, self.max_new_tokens, device=pol.device, dtype=torch.float32)
+                    pol.microbatch_packed(pk, None, 1, False, backward=False, lp_out=ref_lp, lora_off=True)
+                pol.microbatch_packed(pk, self._h2d(torch.from_numpy(r)), nb, grpo, backward=True, ref_lp=ref_lp,
+                                      kl_beta=self.kl_beta)
+                continue
             d_ids, d_am, d_ansm = self._h2d(ids), self._h2d(am), self._h2d(ansm)
             ref_lp = None
             if self.kl_beta != 0.0:

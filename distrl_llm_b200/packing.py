@@ -1,0 +1,166 @@
+"""Host-side construction of the packed ("shared-prompt") micro-batch layout.
+
+The reference pads every (prompt, completion) pair to P + T tokens and runs the model on all B*(P+T) rows
+(distributed_actor.py:217-243).  In its pipeline the n completions of a problem share the prompt verbatim
+(`task["problem"] = [[p for _ in range(n)] for p in ...]`, distributed_actor.py:169-170), and under causal
+attention the prompt positions never see the completion, so their activations are identical for the whole group.
+The packed layout stores each distinct prompt of a micro-batch ONCE:
+
+    rows = [ prompt 0 | prompt 1 | ... | completion 0 | completion 1 | ... ]      G*P + B*T rows
+
+Completion queries attend to the whole prompt segment of their group (prefix) and causally to their own segment.
+Everything here is integer bookkeeping (numpy); the arrays go to the device in one int32 blob and are consumed by
+b200rl_model_microbatch_packed / the tcgen05 attention kernels through block descriptors.
+
+Groups are runs of CONSECUTIVE sequences with identical padded prompt rows (ids and mask); a micro-batch without any
+repeated prompt degenerates to G = B (same code path, no saving).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+QB_FIELDS = 8   # b200rl_attn_qblock: q_row0 q_rows q_local0 own_row0 own_len pre_row0 pre_len stat0
+KB_FIELDS = 8   # b200rl_attn_kblock: k_row0 k_rows k_local0 q_row0 q_len causal stat0 out_row0
+
+
+class PackedBatchC(C.Structure):
+    _fields_ = [("rows", C.c_int), ("B", C.c_int), ("T", C.c_int), ("max_pos", C.c_int),
+                ("n_qblocks", C.c_int), ("n_kblocks", C.c_int), ("part_rows", C.c_int),
+                ("ids", C.c_void_p), ("pos", C.c_void_p), ("key_mask", C.c_void_p), ("score_src", C.c_void_p),
+                ("targets", C.c_void_p), ("answer_mask", C.c_void_p), ("sc_start", C.c_void_p), ("sc_list", C.c_void_p),
+                ("qblocks", C.c_void_p), ("kblocks", C.c_void_p), ("red_start", C.c_void_p), ("red_list", C.c_void_p)]
+
+
+@dataclass
+class PackedHost:
+    """numpy arrays of one packed micro-batch (all int32)."""
+    rows: int
+    B: int
+    P: int
+    T: int
+    n_groups: int
+    part_rows: int
+    arrays: dict          # name -> np.int32 array
+    seq_group: np.ndarray  # [B] group of every sequence
+
+    def blob(self):
+        """Concatenate all arrays into one int32 vector; returns (blob, {name: (offset, length)})."""
+        offs, parts, o = {}, [], 0
+        for k, v in self.arrays.items():
+            v = np.ascontiguousarray(v, dtype=np.int32).reshape(-1)
+            pad = (-o) % 4  # keep every array 16-byte aligned
+            if pad:
+                parts.append(np.zeros(pad, np.int32))
+                o += pad
+            offs[k] = (o, v.size)
+            parts.append(v)
+            o += v.size
+        return np.concatenate(parts), offs
+
+
+def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int) -> PackedHost:
+    """ids / attn_mask: [B, P+T] (prompt left-padded to P, completion right-padded to T, reference layout)."""
+    ids = np.asarray(ids, dtype=np.int32)
+    am = np.asarray(attn_mask, dtype=np.int32)
+    B, L = ids.shape
+    assert L == P + T
+    # ---- groups = runs of identical prompts ----
+    seq_group = np.zeros(B, np.int32)
+    g = 0
+    for i in range(1, B):
+        same = np.array_equal(ids[i, :P], ids[i - 1, :P]) and np.array_equal(am[i, :P], am[i - 1, :P])
+        if not same:
+            g += 1
+        seq_group[i] = g
+    G = g + 1
+    first_of_group = [int(np.argmax(seq_group == k)) for k in range(G)]
+    rows = G * P + B * T
+    comp0 = G * P
+    p_ids = np.empty(rows, np.int32)
+    p_pos = np.empty(rows, np.int32)
+    p_km = np.empty(rows, np.int32)
+    for k in range(G):
+        i = first_of_group[k]
+        p_ids[k * P:(k + 1) * P] = ids[i, :P]
+        p_km[k * P:(k + 1) * P] = am[i, :P]
+        p_pos[k * P:(k + 1) * P] = np.arange(P)
+    for i in range(B):
+        r0 = comp0 + i * T
+        p_ids[r0:r0 + T] = ids[i, P:]
+        p_km[r0:r0 + T] = am[i, P:]
+        p_pos[r0:r0 + T] = P + np.arange(T)
+    # ---- scored rows: the logit at original position P-1+t predicts completion token t (distributed_actor.py:245-249)
+    score_src = np.empty(B * T, np.int32)
+    for i in range(B):
+        score_src[i * T] = seq_group[i] * P + (P - 1)            # last prompt position (shared by the group)
+        score_src[i * T + 1:(i + 1) * T] = comp0 + i * T + np.arange(T - 1)
+    targets = ids[:, P:].reshape(-1).astype(np.int32)
+    answer_mask = am[:, P:].reshape(-1).astype(np.int32)
+    order = np.argsort(score_src, kind="stable")
+    counts = np.bincount(score_src, minlength=rows)
+    sc_start = np.zeros(rows + 1, np.int32)
+    sc_start[1:] = np.cumsum(counts)
+    sc_list = order.astype(np.int32)
+    # ---- attention block descriptors ----
+    segs = [(k * P, P, 0, 0) for k in range(G)]                                   # (row0, len, pre_row0, pre_len)
+    segs += [(comp0 + i * T, T, int(seq_group[i]) * P, P) for i in range(B)]
+    qb = []
+    for (r0, ln, pr0, pl) in segs:
+        for b0 in range(0, ln, 128):
+            work = (pl + 127) // 128 + (min(b0 + 128, ln) + 127) // 128
+            qb.append((work, [r0 + b0, min(128, ln - b0), b0, r0, ln, pr0, pl, r0 + b0]))
+    qb.sort(key=lambda t: -t[0])                                                  # heavy blocks first
+    qblocks = np.array([t[1] for t in qb], np.int32)
+    kb, part_rows = [], 0
+    red = [[] for _ in range(rows)]
+    deps = [[] for _ in range(G)]
+    for i in range(B):
+        deps[int(seq_group[i])].append(i)
+    for si, (r0, ln, pr0, pl) in enumerate(segs):
+        qsegs = [(r0, ln, 1)]                                                     # own queries (causal)
+        if si < G:
+            qsegs += [(comp0 + i * T, T, 0) for i in deps[si]]                    # every completion of the group
+        for b0 in range(0, ln, 128):
+            k_rows = min(128, ln - b0)
+            for (qr0, qlen, causal) in qsegs:
+                nqb = (qlen + 63) // 64 - (b0 // 64 if causal else 0)
+                kb.append((nqb, [r0 + b0, k_rows, b0, qr0, qlen, causal, qr0, part_rows]))
+                for r in range(k_rows):
+                    red[r0 + b0 + r].append(part_rows + r)
+                part_rows += k_rows
+    kb.sort(key=lambda t: -t[0])
+    kblocks = np.array([t[1] for t in kb], np.int32)
+    red_start = np.zeros(rows + 1, np.int32)
+    red_start[1:] = np.cumsum([len(x) for x in red])
+    red_list = np.array([x for lst in red for x in lst], np.int32)
+    arrays = {"ids": p_ids, "pos": p_pos, "key_mask": p_km, "score_src": score_src, "targets": targets,
+              "answer_mask": answer_mask, "sc_start": sc_start, "sc_list": sc_list, "qblocks": qblocks.reshape(-1),
+              "kblocks": kblocks.reshape(-1), "red_start": red_start, "red_list": red_list}
+    return PackedHost(rows=rows, B=B, P=P, T=T, n_groups=G, part_rows=part_rows, arrays=arrays, seq_group=seq_group)
+
+
+class PackedDevice:
+    """Device-resident packed micro-batch: one int32 blob + the C descriptor struct pointing into it."""
+
+    def __init__(self, host: PackedHost, device, pinned=True):
+        blob, offs = host.blob()
+        t = torch.from_numpy(blob)
+        if pinned:
+            t = t.pin_memory()
+        self.blob = t.to(device, non_blocking=True)
+        self.host = host
+        self.h2d_bytes = blob.nbytes
+        base = self.blob.data_ptr()
+
+        def p(name):
+            return base + 4 * offs[name][0]
+
+        self.answer_mask = self.blob[offs["answer_mask"][0]:offs["answer_mask"][0] + offs["answer_mask"][1]].view(host.B, host.T)
+        self.c = PackedBatchC(host.rows, host.B, host.T, host.P + host.T, offs["qblocks"][1] // QB_FIELDS,
+                              offs["kblocks"][1] // KB_FIELDS, host.part_rows, p("ids"), p("pos"), p("key_mask"),
+                              p("score_src"), p("targets"), p("answer_mask"), p("sc_start"), p("sc_list"),
+                              p("qblocks"), p("kblocks"), p("red_start"), p("red_list"))

@@ -233,6 +233,14 @@ class Policy:
                                                1 if backward else 0, 1 if lora_off else 0, ptr(ref_lp),
                                                float(kl_beta), stream()), "model_microbatch")
 
+    def microbatch_packed(self, packed, adv, nb, grpo, backward, lp_out=None, lora_off=False, ref_lp=None,
+                          kl_beta=0.0):
+        """Same as microbatch() on the packed shared-prompt layout (`packed`: packing.PackedDevice)."""
+        check(lib().b200rl_model_microbatch_packed(self.handle, C.byref(packed.c), ptr(adv), ptr(lp_out),
+                                                   ptr(self.loss_accum), nb, 1 if grpo else 0, 1 if backward else 0,
+                                                   1 if lora_off else 0, ptr(ref_lp), float(kl_beta), stream()),
+              "model_microbatch_packed")
+
     def debug_tensor(self, name, layer, shape, dtype=torch.bfloat16):
         p = lib().b200rl_model_debug_ptr(self.handle, name.encode(), layer)
         if not p:

@@ -57,6 +57,11 @@ int b200rl_swiglu_bwd(const void* gu, const void* dact, void* dgu, int M, int I,
 /* logits[:, P-1:L-1] row selection of distributed_actor.py:245-249 applied BEFORE lm_head */
 int b200rl_gather_rows(const void* x, void* out, int B, int L, int T, int start, int H, void* stream);
 int b200rl_scatter_rows(const void* d, void* dx, int B, int L, int T, int start, int H, void* stream);
+/* packed layout variants: explicit RoPE positions, indexed gather, CSR scatter-add (fixed order) */
+int b200rl_rope_pos(void* qkv, const float* cs, const int* pos, int M, long long row_stride, int n_rot_heads,
+                    int head_dim, int backward, void* stream);
+int b200rl_gather_rows_idx(const void* x, const int* src, void* out, int R, int H, void* stream);
+int b200rl_scatter_add_rows(const void* d, const int* start, const int* list, void* dx, int M, int H, void* stream);
 
 /* ---- G4: causal GQA attention with key-padding mask (reference: attention inside policy(...)
  *      with attention_mask = cat(prompt_mask, answer_mask), distributed_actor.py:236-243) -------- */
@@ -67,6 +72,32 @@ int b200rl_attn_set_tc(int enable);
 int b200rl_attn_bwd(const void* qkv, const int* key_mask, const void* out, const void* dout,
                     const float* lse, float* delta, void* dqkv, int B, int L, int n_q_heads,
                     int n_kv_heads, int head_dim, float scale, void* stream);
+
+/* ---- G4, packed "shared-prompt" layout (head_dim 128): every distinct prompt of a micro-batch is stored once;
+ *      completion segments see their prompt segment as a fully visible prefix.  Block descriptors are built on the
+ *      host (distrl_llm_b200/packing.py) and passed as device arrays.  lse / delta are [n_q_heads][rows]. */
+typedef struct b200rl_attn_qblock {  /* one <=128-query block of a segment (forward and dQ kernels) */
+  int q_row0, q_rows;     /* first query row, number of valid query rows */
+  int q_local0;           /* index of the first query inside its segment */
+  int own_row0, own_len;  /* the segment itself: keys with local index <= query index are visible */
+  int pre_row0, pre_len;  /* fully visible prefix (shared prompt), pre_len = 0 for prompt segments */
+  int stat0;              /* lse/delta index of (head 0, first query): idx = stat0 + head*rows + r */
+} b200rl_attn_qblock;
+typedef struct b200rl_attn_kblock {  /* one <=128-key block and ONE query segment that sees it (dK/dV kernel) */
+  int k_row0, k_rows, k_local0;
+  int q_row0, q_len;      /* the query segment */
+  int causal;             /* 1: queries and keys belong to the same segment */
+  int stat0;              /* lse/delta index of (head 0, query 0 of the segment) */
+  int out_row0;           /* first row of this block's fp32 partial slab */
+} b200rl_attn_kblock;
+int b200rl_attn_seg_fwd(const void* qkv, const int* key_mask, void* out, float* lse, long long rows,
+                        int n_q_heads, int n_kv_heads, float scale, const b200rl_attn_qblock* qblocks_dev,
+                        int n_qblocks, void* stream);
+int b200rl_attn_seg_bwd(const void* qkv, const int* key_mask, const void* out, const void* dout, const float* lse,
+                        float* delta, void* dqkv, float* kv_part, long long rows, int n_q_heads, int n_kv_heads,
+                        float scale, const b200rl_attn_qblock* qblocks_dev, int n_qblocks,
+                        const b200rl_attn_kblock* kblocks_dev, int n_kblocks, const int* red_start_dev,
+                        const int* red_list_dev, void* stream);
 
 /* ---- G7: fused log-softmax + target gather + loss-gradient scale
  *      (distributed_actor.py:252-260 scoring; :375 PG / :467-470 GRPO loss; :382/:479 scaling) --- */
@@ -168,6 +199,31 @@ int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const int* attn_
                                const int* answer_mask, const double* adv, float* lp_out,
                                double* loss_accum, int B, int P, int T, int nb, int grpo, int backward,
                                int lora_off, const float* ref_lp, double kl_beta, void* stream);
+
+/* packed ("shared-prompt") micro-batch: all arrays are device int32 built by distrl_llm_b200/packing.py */
+typedef struct b200rl_packed_batch {
+  int rows;        /* G*P + B*T packed token rows */
+  int B, T;        /* sequences, scored positions per sequence */
+  int max_pos;     /* P + T (RoPE table length) */
+  int n_qblocks, n_kblocks;
+  int part_rows;   /* rows of the fp32 dK/dV partial buffer */
+  const int* ids;          /* [rows] */
+  const int* pos;          /* [rows] position of the token in its original sequence */
+  const int* key_mask;     /* [rows] 1 = real token */
+  const int* score_src;    /* [B*T] packed row whose hidden state predicts completion token (i, t) */
+  const int* targets;      /* [B*T] completion token ids */
+  const int* answer_mask;  /* [B*T] */
+  const int* sc_start;     /* [rows+1] CSR: scored rows fed by each packed row */
+  const int* sc_list;
+  const b200rl_attn_qblock* qblocks;
+  const b200rl_attn_kblock* kblocks;
+  const int* red_start;    /* [rows+1] CSR: dK/dV partial rows of each packed row */
+  const int* red_list;
+} b200rl_packed_batch;
+/* same contract as b200rl_model_microbatch_ex on the packed layout (head_dim 128 only) */
+int b200rl_model_microbatch_packed(b200rl_model* m, const b200rl_packed_batch* pb, const double* adv, float* lp_out,
+                                   double* loss_accum, int nb, int grpo, int backward, int lora_off,
+                                   const float* ref_lp, double kl_beta, void* stream);
 
 /* per-op CUDA-event profiling of the driver (categories: 0 gemm, 1 skinny LoRA gemm, 2 dW gemm, 3 nf4
  * dequant, 4 attn fwd, 5 attn bwd, 6 row kernels, 7 logprob, 8 misc); read() returns sums since the last

@@ -379,3 +379,80 @@ def test_attention(cuda, attn_mode, B, L, nq, nkv, hd):
     for name, sl in (("dq", slice(0, nqh)), ("dk", slice(nqh, nqh + nkv * hd)), ("dv", slice(nqh + nkv * hd, None))):
         err = _rel_err(dqkv[:, sl], g[:, sl])
         assert err < 2e-2, f"{name} rel err {err}"
+
+
+# ------------------------------------------------------------------------------------------------
+# packed "shared-prompt" attention (tcgen05, head_dim 128): each distinct prompt stored once
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("groups,per_group,P,T", [(2, 3, 70, 130), (1, 8, 350, 512), (3, 1, 40, 64)])
+def test_attention_packed_shared_prompt(cuda, groups, per_group, P, T):
+    import ctypes as C
+    from distrl_llm_b200 import _capi, packing
+    nq, nkv, hd = 4, 2, 128
+    B = groups * per_group
+    rng = np.random.default_rng(P + T)
+    ids = np.zeros((B, P + T), np.int32)
+    am = np.zeros_like(ids)
+    for g in range(groups):
+        plen = int(rng.integers(P // 2, P + 1))
+        pr = rng.integers(1, 1000, size=plen)
+        for j in range(per_group):
+            i = g * per_group + j
+            ids[i, P - plen:P] = pr
+            am[i, P - plen:P] = 1
+            n = int(rng.integers(T // 4, T + 1))
+            ids[i, P:P + n] = rng.integers(1, 1000, size=n)
+            am[i, P:P + n] = 1
+    host = packing.pack_microbatch(ids, am, P, T)
+    assert host.n_groups == groups and host.rows == groups * P + B * T
+    pk = packing.PackedDevice(host, cuda)
+    rows, cols = host.rows, (nq + 2 * nkv) * hd
+    qkv = _rand((rows, cols), cuda, seed=1)
+    dout = _rand((rows, nq * hd), cuda, seed=2)
+    out = torch.empty(rows, nq * hd, device=cuda, dtype=torch.bfloat16)
+    lse = torch.empty(nq, rows, device=cuda, dtype=torch.float32)
+    delta = torch.empty_like(lse)
+    dqkv = torch.zeros_like(qkv)
+    kvpart = torch.empty(host.part_rows, 2 * nkv * hd, device=cuda, dtype=torch.float32)
+    scale = hd ** -0.5
+    lib = _capi.lib()
+    c = pk.c
+    _capi.check(lib.b200rl_attn_seg_fwd(qkv.data_ptr(), c.key_mask, out.data_ptr(), lse.data_ptr(), rows, nq, nkv, scale,
+                                        c.qblocks, c.n_qblocks, _capi.stream()), "attn_seg_fwd")
+    _capi.check(lib.b200rl_attn_seg_bwd(qkv.data_ptr(), c.key_mask, out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                        delta.data_ptr(), dqkv.data_ptr(), kvpart.data_ptr(), rows, nq, nkv, scale,
+                                        c.qblocks, c.n_qblocks, c.kblocks, c.n_kblocks, c.red_start, c.red_list,
+                                        _capi.stream()), "attn_seg_bwd")
+    torch.cuda.synchronize()
+    # reference: expand the packed rows to the per-sequence [B, L] layout (gather), plain fp32 attention with autograd
+    comp0 = groups * P
+    idx = np.zeros((B, P + T), np.int64)
+    for i in range(B):
+        idx[i, :P] = host.seq_group[i] * P + np.arange(P)
+        idx[i, P:] = comp0 + i * T + np.arange(T)
+    idx_t = torch.from_numpy(idx).to(cuda)
+    leaf = qkv.float().requires_grad_(True)
+    full = leaf[idx_t.view(-1)]                                     # [B*L, cols]
+    key_mask = torch.from_numpy(am).to(cuda)
+    ref_full = _attn_ref(full, key_mask, B, P + T, nq, nkv, hd)     # [B*L, nq*hd]
+    # packed outputs: prompt rows from the first sequence of the group, completion rows from their own sequence
+    valid = torch.from_numpy(host.arrays["key_mask"]).to(cuda).bool()
+    got_full = out.float()[idx_t.view(-1)]
+    vq = key_mask.view(-1).bool()
+    assert torch.isfinite(out.float()).all()
+    assert _rel_err(got_full[vq], ref_full[vq]) < 8e-3
+    # backward: dout per packed row; expand the same way but count each shared prompt row ONCE (first sequence of group)
+    w = torch.zeros(B, P + T, device=cuda)
+    first = [int(np.argmax(host.seq_group == g)) for g in range(groups)]
+    for i in range(B):
+        w[i, P:] = 1.0
+        if i in first:
+            w[i, :P] = 1.0
+    dfull = dout.float()[idx_t.view(-1)] * w.view(-1, 1)
+    (ref_full * dfull).sum().backward()
+    g_ref = leaf.grad                                               # already summed over the group through the gather
+    nqh = nq * hd
+    vrow = valid
+    for name, sl in (("dq", slice(0, nqh)), ("dk", slice(nqh, nqh + nkv * hd)), ("dv", slice(nqh + nkv * hd, None))):
+        err = _rel_err(dqkv[:, sl][vrow], g_ref[:, sl][vrow])
+        assert err < 2e-2, f"{name} rel err {err}"

@@ -204,3 +204,38 @@ def test_kl_term_vs_oracle(cuda):
     ln.kl_beta = 0.0
     _, loss_b0 = ln._compute_gradients(prompts, answers, list(rewards))
     assert abs(loss_b0 - loss0) < 1e-9
+
+
+@pytest.mark.parametrize("kind,beta", [("grpo", 0.0), ("pg", 0.0), ("grpo", 0.2)])
+def test_shared_prompt_packing_vs_oracle(cuda, kind, beta):
+    """Packed shared-prompt layout (packing.py): 3 problems x 4 completions with identical prompts inside a group,
+    micro-batches of 6 (so one group straddles two micro-batches);
+    the oracle computes every (prompt, completion) pair separately like the reference."""
+    ocfg = lo.OracleConfig(vocab=4096, hidden=512, inter=1024, n_layers=3, n_q_heads=4, n_kv_heads=2, head_dim=128,
+                           lora_r=16, lora_alpha=16)
+    params, nf4 = lo.make_params(ocfg, seed=31, lora_b_std=0.05 if beta else 0.01)
+    P, T, B, G, n = 40, 72, 6, 3, 4
+    rng = np.random.default_rng(17)
+    prompts, answers = [], []
+    for g in range(G):
+        pr = rng.integers(1, ocfg.vocab, size=int(rng.integers(P // 2, P + 1))).tolist()
+        for _ in range(n):
+            prompts.append(pr)
+            answers.append(rng.integers(1, ocfg.vocab, size=int(rng.integers(T // 4, T + 1))).tolist())
+    _, _, rewards = lo.make_batch(ocfg, G * n, P, T, seed=5, group_size=n, learner=kind)
+    dparams = {k: (v.detach().to(cuda).requires_grad_(v.requires_grad)) for k, v in params.items()}
+    ids, am, ansm = lo.pad_batch(prompts, answers, P, T)
+    kw = {"kl_beta": beta} if beta else {}
+    ref_grads, ref_loss = lo.compute_gradients(dparams, ocfg, ids.to(cuda), am.to(cuda), ansm.to(cuda), rewards, P, B, kind, **kw)
+    ln = _mk_learner(kind, ocfg, params, nf4, P, T, B, cuda)
+    ln.kl_beta = beta
+    assert ln.share_prompts
+    grads, loss = ln._compute_gradients(prompts, answers, list(rewards))
+    loss_tol = 4e-2 * sum(np.abs(rewards[i:i + B]).mean() for i in range(0, len(rewards), B)) + 2e-3
+    assert abs(loss - ref_loss) <= loss_tol, (loss, ref_loss)
+    _compare_grads(grads, ref_grads, ocfg, ln.policy)
+    # and the unshared (classic) layout of the same learner gives the same gradients up to bf16 reassociation
+    ln.share_prompts = False
+    grads2, loss2 = ln._compute_gradients(prompts, answers, list(rewards))
+    _compare_grads(grads, {f"l{i}.{m}.{ab}": grads2[ln.policy.peft_name(i, m, ab)] for i in range(ocfg.n_layers)
+                           for m in lo.LORA_MODULES for ab in ("A", "B")}, ocfg, ln.policy, cos_min=0.9995, rel_max=3e-2)
