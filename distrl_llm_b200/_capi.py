@@ -86,6 +86,8 @@ SIGNATURES = {
     "b200rl_model_create": (c_int, [C.POINTER(ModelConfig), C.POINTER(LayerWeights), c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_ll, C.POINTER(c_void_p)]),
     "b200rl_model_destroy": (c_int, [c_void_p]),
+    "b200rl_model_weight_cache_bytes": (c_ll, [C.POINTER(ModelConfig)]),
+    "b200rl_model_set_weight_cache": (c_int, [c_void_p, c_void_p, c_ll]),
     "b200rl_model_sync_lora": (c_int, [c_void_p, c_void_p]),
     "b200rl_model_debug_ptr": (c_void_p, [c_void_p, C.c_char_p, c_int]),
     "b200rl_model_microbatch_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -179,6 +179,11 @@ struct b200rl_model {
   int *targets, *lens;
   long long slab_elems;
   int rope_L;
+  // optional resident bf16 copy of the dequantised base weights (b200rl_model_set_weight_cache): 15 GB for a 7B
+  // model, 8 % of a B200's HBM, and it removes 2 x n_layers x 4 dequant passes per micro-batch
+  bf16* wcache = nullptr;
+  long long wcache_per_layer = 0;
+  std::vector<uint8_t> wcache_valid;  // [n_layers*4]
   // optional per-op CUDA-event profiling (bench.py roofline / DESIGN.md breakdown)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -626,6 +631,30 @@ struct Layout {
 };
 }  // namespace
 
+// Dequantised base weight of projection `which` (0 qkv, 1 o, 2 gate|up, 3 down) of layer l: from the resident cache
+// when one is attached (filled on first use), else NF4 -> bf16 into the shared scratch right before the GEMM.
+static int base_weight(b200rl_model* m, cudaStream_t st, int l, int which, const bf16** out) {
+  const b200rl_model_config& c = m->cfg;
+  const b200rl_layer_weights& w = m->layers[l];
+  const int H = c.hidden, I = c.inter, QKV = m->QKV, QD = m->QD;
+  const void* packed[4] = {w.qkv_packed, w.o_packed, w.gu_packed, w.down_packed};
+  const float* absmax[4] = {(const float*)w.qkv_absmax, (const float*)w.o_absmax, (const float*)w.gu_absmax, (const float*)w.down_absmax};
+  const int rows[4] = {QKV, H, 2 * I, H}, cols[4] = {H, QD, H, I};
+  bf16* dst = m->wbuf;
+  if (m->wcache) {
+    long long off = 0;
+    for (int i = 0; i < which; ++i) off += (long long)rows[i] * cols[i];
+    dst = m->wcache + m->wcache_per_layer * l + off;
+    *out = dst;
+    if (m->wcache_valid[l * 4 + which]) return 0;
+    m->wcache_valid[l * 4 + which] = 1;
+  }
+  *out = dst;
+  PM(CAT_DEQUANT, 2.5625 * rows[which] * (double)cols[which]);
+  RC(b200rl_nf4_dequant(packed[which], absmax[which], dst, rows[which], cols[which], 0, (void*)st));
+  return 0;
+}
+
 static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv, float* lp_out, double* loss_accum,
                           int nb, int grpo, int backward, int lora_off, const float* ref_lp, double kl_beta,
                           void* stream) {
@@ -650,6 +679,7 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     m->rope_L = L;
   }
   // ---------------- forward ----------------
+  const bf16* Wd = nullptr;
   const bool lora = !lora_off;  // adapter-disabled pass = reference policy pi_ref (KL term)
   PM(CAT_ROW, 2.0 * M * H * 2);
   RC(b200rl_embed(ids, m->embed, m->X, M, H, V, stream));
@@ -666,9 +696,8 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(x, w.ln1_w, a.h1, a.rstd1, M, H, c.rms_eps, stream));
     if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
-    PM(CAT_DEQUANT, 2.5625 * (QKV) * (H));
-    RC(b200rl_nf4_dequant(w.qkv_packed, w.qkv_absmax, m->wbuf, QKV, H, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 0, st, a.h1, H, m->wbuf, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, lora ? gq.K2 : 0, a.qkv, QKV,
+    RC(base_weight(m, st, l, 0, &Wd));
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.h1, H, Wd, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, lora ? gq.K2 : 0, a.qkv, QKV,
                (const bf16*)w.qkv_bias, nullptr, 0, 1.f, M, QKV));
     PM(CAT_ROW, 2.0 * M * (c.n_q_heads + c.n_kv_heads) * c.head_dim * 2);
     if (pb) RC(b200rl_rope_pos(a.qkv, m->rope_cs, pb->pos, M, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 0, stream));
@@ -677,23 +706,20 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     if (pb) RC(b200rl_attn_seg_fwd(a.qkv, attn_mask, a.attn_o, a.lse, M, c.n_q_heads, c.n_kv_heads, attn_scale, pb->qblocks, pb->n_qblocks, stream));
     else RC(b200rl_attn_fwd(a.qkv, attn_mask, a.attn_o, a.lse, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
     if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
-    PM(CAT_DEQUANT, 2.5625 * (H) * (QD));
-    RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 0, st, a.attn_o, QD, m->wbuf, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, lora ? go.K2 : 0, a.x_mid, H,
+    RC(base_weight(m, st, l, 1, &Wd));
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.attn_o, QD, Wd, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, lora ? go.K2 : 0, a.x_mid, H,
                nullptr, x, H, 1.f, M, H));
     PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(a.x_mid, w.ln2_w, a.h2, a.rstd2, M, H, c.rms_eps, stream));
     if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
-    PM(CAT_DEQUANT, 2.5625 * (2 * I) * (H));
-    RC(b200rl_nf4_dequant(w.gu_packed, w.gu_absmax, m->wbuf, 2 * I, H, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, m->wbuf, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, lora ? gg.K2 : 0, a.gu, 2 * I,
+    RC(base_weight(m, st, l, 2, &Wd));
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, Wd, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, lora ? gg.K2 : 0, a.gu, 2 * I,
                nullptr, nullptr, 0, 1.f, M, 2 * I));
     PM(CAT_ROW, 3.0 * M * I * 2);
     RC(b200rl_swiglu_fwd(a.gu, a.act, M, I, stream));
     if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
-    PM(CAT_DEQUANT, 2.5625 * (H) * (I));
-    RC(b200rl_nf4_dequant(w.down_packed, w.down_absmax, m->wbuf, H, I, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 0, st, a.act, I, m->wbuf, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, lora ? gd.K2 : 0, xn, H, nullptr,
+    RC(base_weight(m, st, l, 3, &Wd));
+    RC(gemm_l(m, CAT_GEMM, 0, st, a.act, I, Wd, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, lora ? gd.K2 : 0, xn, H, nullptr,
                a.x_mid, H, 1.f, M, H));
   }
   // head: only the T scored positions (rows P-1 .. L-2) go through the final norm and lm_head
@@ -744,25 +770,22 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     // ---- down projection:  X[l+1] = x_mid + act.Wd^T + u_d.Bd^T
     RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + gd.bcat, gd.K2, H, nullptr, 0, nullptr, 0, 0, m->du, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
     RC(lora_dw(m, st, gd, m->dx, H, a.u_d, a.act, I, m->du, M));
-    PM(CAT_DEQUANT, 2.5625 * (H) * (I));
-    RC(b200rl_nf4_dequant(w.down_packed, w.down_absmax, m->wbuf, H, I, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, m->wbuf, I, H, m->du, gd.K2, ar + gd.acat, I, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
+    RC(base_weight(m, st, l, 3, &Wd));
+    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, m->du, gd.K2, ar + gd.acat, I, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
     PM(CAT_ROW, 5.0 * M * I * 2);
     RC(b200rl_swiglu_bwd(a.gu, m->dact, m->dgu, M, I, stream));
     // ---- gate|up:  gu = h2.Wgu^T + u_gu.Bgu^T
     RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dgu, 2 * I, ar + gg.bcat, gg.K2, 2 * I, nullptr, 0, nullptr, 0, 0, m->du, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
     RC(lora_dw(m, st, gg, m->dgu, 2 * I, a.u_gu, a.h2, H, m->du, M));
-    PM(CAT_DEQUANT, 2.5625 * (2 * I) * (H));
-    RC(b200rl_nf4_dequant(w.gu_packed, w.gu_absmax, m->wbuf, 2 * I, H, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 2, st, m->dgu, 2 * I, m->wbuf, H, 2 * I, m->du, gg.K2, ar + gg.acat, H, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+    RC(base_weight(m, st, l, 2, &Wd));
+    RC(gemm_l(m, CAT_GEMM, 2, st, m->dgu, 2 * I, Wd, H, 2 * I, m->du, gg.K2, ar + gg.acat, H, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
     PM(CAT_ROW, 4.0 * M * H * 2);
     RC(b200rl_rmsnorm_bwd(m->dh, a.x_mid, w.ln2_w, a.rstd2, m->dx, m->dx, M, H, stream));
     // ---- o projection:  x_mid = x + attn_o.Wo^T + u_o.Bo^T
     RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + go.bcat, go.K2, H, nullptr, 0, nullptr, 0, 0, m->du, go.K2, nullptr, nullptr, 0, s, M, go.K2));
     RC(lora_dw(m, st, go, m->dx, H, a.u_o, a.attn_o, QD, m->du, M));
-    PM(CAT_DEQUANT, 2.5625 * (H) * (QD));
-    RC(b200rl_nf4_dequant(w.o_packed, w.o_absmax, m->wbuf, H, QD, 0, stream));
-    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, m->wbuf, QD, H, m->du, go.K2, ar + go.acat, QD, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
+    RC(base_weight(m, st, l, 1, &Wd));
+    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, QD, H, m->du, go.K2, ar + go.acat, QD, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
     // ---- attention + rope
     PM(CAT_ATTN_BWD, 4.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
     if (pb) RC(b200rl_attn_seg_bwd(a.qkv, attn_mask, a.attn_o, m->dattn, a.lse, m->delta, m->dqkv, m->kvpart, M, c.n_q_heads, c.n_kv_heads, attn_scale,
@@ -775,14 +798,32 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dqkv, QKV, ar + gq.bcat, gq.K2, QKV, nullptr, 0, nullptr, 0, 0, m->du, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
     RC(lora_dw(m, st, gq, m->dqkv, QKV, a.u_qkv, a.h1, H, m->du, M));
     if (l > 0) {  // embeddings are frozen: layer 0 needs no input gradient
-      PM(CAT_DEQUANT, 2.5625 * (QKV) * (H));
-      RC(b200rl_nf4_dequant(w.qkv_packed, w.qkv_absmax, m->wbuf, QKV, H, 0, stream));
-      RC(gemm_l(m, CAT_GEMM, 2, st, m->dqkv, QKV, m->wbuf, H, QKV, m->du, gq.K2, ar + gq.acat, H, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+      RC(base_weight(m, st, l, 0, &Wd));
+      RC(gemm_l(m, CAT_GEMM, 2, st, m->dqkv, QKV, Wd, H, QKV, m->du, gq.K2, ar + gq.acat, H, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
       PM(CAT_ROW, 4.0 * M * H * 2);
       RC(b200rl_rmsnorm_bwd(m->dh, x, w.ln1_w, a.rstd1, m->dx, m->dx, M, H, stream));
     }
   }
   PM(CAT_END, 0);
+  return 0;
+}
+
+// ---- resident dequantised-weight cache ---------------------------------------------------------------
+extern "C" long long b200rl_model_weight_cache_bytes(const b200rl_model_config* c) {
+  if (!c) return -1;
+  const long long QKV = (long long)(c->n_q_heads + 2 * c->n_kv_heads) * c->head_dim, QD = (long long)c->n_q_heads * c->head_dim;
+  const long long per = QKV * c->hidden + c->hidden * QD + 2LL * c->inter * c->hidden + (long long)c->hidden * c->inter;
+  return per * 2 * c->n_layers;
+}
+extern "C" int b200rl_model_set_weight_cache(b200rl_model* m, void* buf, long long bytes) {
+  B200RL_REQUIRE(m != nullptr, "model_set_weight_cache: null model");
+  if (!buf) { m->wcache = nullptr; return 0; }
+  const long long need = b200rl_model_weight_cache_bytes(&m->cfg);
+  B200RL_REQUIRE(bytes >= need, "model_set_weight_cache: buffer too small");
+  B200RL_REQUIRE((reinterpret_cast<uintptr_t>(buf) & 1023) == 0, "model_set_weight_cache: buffer must be 1024-byte aligned");
+  m->wcache = (bf16*)buf;
+  m->wcache_per_layer = need / 2 / m->cfg.n_layers;
+  m->wcache_valid.assign((size_t)m->cfg.n_layers * 4, 0);
   return 0;
 }
 

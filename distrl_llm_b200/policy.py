@@ -73,7 +73,7 @@ class Policy:
     for layer in layers: for mod in (q,k,v,o,gate,up,down): A [r, in] then B [out, r]."""
 
     def __init__(self, cfg: LMConfig, device, max_batch, max_prompt_tokens, max_new_tokens,
-                 lora_flat=None, lora_grad=None):
+                 lora_flat=None, lora_grad=None, cache_weights="auto"):
         _capi.load_library()
         check(lib().b200rl_check_device(), "check_device")
         self.cfg = cfg
@@ -97,6 +97,8 @@ class Policy:
         self.embed = self.final_norm = self.lm_head = None
         self.handle = None
         self.workspace = None
+        self.cache_weights = cache_weights   # True / False / "auto": resident bf16 copy of the dequantised base
+        self.weight_cache = None
         self.loss_accum = torch.zeros(1, device=self.device, dtype=torch.float64)
         # offsets of every LoRA tensor in the flat buffer
         self.offsets = {}
@@ -128,7 +130,22 @@ class Policy:
                                         ptr(self.lm_head), ptr(self.lora_flat),
                                         ptr(self.lora_grad), aligned, int(nbytes), C.byref(h)), "model_create")
         self.handle = h
+        self._attach_weight_cache()
         self.sync_lora()
+
+    def _attach_weight_cache(self):
+        """Keep the dequantised base resident in HBM when it fits comfortably ("auto": cache <= 1/3 of the free
+        memory).  The NF4 tensors stay the source of truth; the cache only removes the per-micro-batch dequant passes."""
+        want = self.cache_weights
+        need = int(lib().b200rl_model_weight_cache_bytes(C.byref(self.ccfg)))
+        if want == "auto":
+            free, _ = torch.cuda.mem_get_info(self.device)
+            want = need * 3 <= free
+        if not want:
+            return
+        self.weight_cache = torch.empty(need + 1024, device=self.device, dtype=torch.uint8)
+        base = self.weight_cache.data_ptr()
+        check(lib().b200rl_model_set_weight_cache(self.handle, (base + 1023) // 1024 * 1024, need), "model_set_weight_cache")
 
     def __del__(self):
         try:

@@ -180,6 +180,11 @@ int b200rl_model_create(const b200rl_model_config* cfg, const b200rl_layer_weigh
                         float* lora_flat, float* lora_grad_flat,
                         void* workspace, long long workspace_bytes, b200rl_model** out);
 int b200rl_model_destroy(b200rl_model* m);
+/* Optional resident bf16 copy of the dequantised NF4 base weights (filled lazily, never invalidated: the base is frozen,
+ * bitsandbytes Linear4bit in the reference, distributed_actor.py:125-139). buf = NULL detaches. Results are bit-identical
+ * with and without the cache (same dequant kernel, same GEMM operands). */
+long long b200rl_model_weight_cache_bytes(const b200rl_model_config* cfg);
+int b200rl_model_set_weight_cache(b200rl_model* m, void* buf, long long bytes);
 /* refresh the bf16 operand copies of the LoRA tensors after an optimizer step */
 int b200rl_model_sync_lora(b200rl_model* m, void* stream);
 /* one micro-batch: scores B sequences of length L = P+T, accumulates LoRA grads.

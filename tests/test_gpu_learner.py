@@ -239,3 +239,24 @@ def test_shared_prompt_packing_vs_oracle(cuda, kind, beta):
     grads2, loss2 = ln._compute_gradients(prompts, answers, list(rewards))
     _compare_grads(grads, {f"l{i}.{m}.{ab}": grads2[ln.policy.peft_name(i, m, ab)] for i in range(ocfg.n_layers)
                            for m in lo.LORA_MODULES for ab in ("A", "B")}, ocfg, ln.policy, cos_min=0.9995, rel_max=3e-2)
+
+
+def test_weight_cache_is_bit_identical(cuda):
+    """Resident bf16 copy of the dequantised base (b200rl_model_set_weight_cache) vs per-layer dequant scratch:
+    same dequant kernel, same GEMM operands -> identical gradients and log-probs, bit for bit."""
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer
+    from distrl_llm_b200.policy import Policy
+    ocfg = lo.OracleConfig(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=64,
+                           lora_r=16, lora_alpha=16)
+    params, nf4 = lo.make_params(ocfg, seed=2)
+    P, T, B = 12, 36, 4
+    prompts, answers, rewards = lo.make_batch(ocfg, 8, P, T, seed=4, ragged=True, group_size=4, learner="grpo")
+    out = []
+    for cache in (False, True):
+        pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, cuda, max_batch=B, P=P, T=T, cache_weights=cache)
+        assert (pol.weight_cache is not None) == cache
+        ln = GRPOLearner(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5})
+        for _ in range(2):   # second pass reads the already-filled cache
+            ln._compute_gradients(prompts, answers, list(rewards), export=False)
+        out.append((pol.lora_grad.clone(), float(pol.loss_accum.item())))
+    assert torch.equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
