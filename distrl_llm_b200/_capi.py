@@ -45,6 +45,9 @@ SIGNATURES = {
                             c_void_p, c_ll, c_int, c_void_p, c_void_p, c_ll, c_float, c_int, c_int,
                             c_int, c_int, c_ll, c_int, c_int, c_void_p]),
     "b200rl_gemm_set_cta_pair": (c_int, [c_int]),
+    "b200rl_gemm_set_tail_split": (c_int, [c_int]),
+    "b200rl_gemm_swiglu": (c_int, [c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int,
+                                   c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "b200rl_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200rl_rmsnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "b200rl_rmsnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -88,6 +91,7 @@ SIGNATURES = {
     "b200rl_model_destroy": (c_int, [c_void_p]),
     "b200rl_model_weight_cache_bytes": (c_ll, [C.POINTER(ModelConfig)]),
     "b200rl_model_set_weight_cache": (c_int, [c_void_p, c_void_p, c_ll]),
+    "b200rl_model_set_fusion": (c_int, [c_void_p, c_int]),
     "b200rl_model_sync_lora": (c_int, [c_void_p, c_void_p]),
     "b200rl_model_debug_ptr": (c_void_p, [c_void_p, C.c_char_p, c_int]),
     "b200rl_model_microbatch_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -231,4 +231,25 @@ __device__ __forceinline__ void tmem_ld_wait() {
 
 #endif  // __CUDACC__
 
+// ---- SwiGLU element math, shared by the row kernels (elementwise.cu) and the fused GEMM epilogues (gemm2_tcgen05.cu)
+// so that both paths are bit-identical.  a = gate, b = up (already bf16-rounded values), HF Qwen2MLP:
+// act_fn(gate) is rounded to bf16 before the product.
+__device__ __forceinline__ void swiglu_fwd8(const float* a, const float* b, float* o) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float s = a[j] / (1.f + __expf(-a[j]));
+    o[j] = __bfloat162float(__float2bfloat16_rn(s)) * b[j];
+  }
+}
+// og = dact * up * silu'(gate), ou = dact * silu(gate)
+__device__ __forceinline__ void swiglu_bwd8(const float* a, const float* b, const float* c, float* og, float* ou) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float sg = 1.f / (1.f + __expf(-a[j]));
+    const float silu = a[j] * sg;
+    og[j] = c[j] * b[j] * sg * (1.f + a[j] * (1.f - sg));
+    ou[j] = c[j] * silu;
+  }
+}
+
 }  // namespace b200rl

@@ -169,12 +169,7 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
   float a[8], b[8], o[8];
   unpack8(g[i], a);
   unpack8(u[i], b);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float s = a[j] / (1.f + __expf(-a[j]));
-    // HF: act_fn(gate) is rounded to bf16 before the product
-    o[j] = __bfloat162float(__float2bfloat16_rn(s)) * b[j];
-  }
+  swiglu_fwd8(a, b, o);
   reinterpret_cast<bf16x8*>(act + row * I)[i] = pack8(o);
 }
 
@@ -191,13 +186,7 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __res
   unpack8(g[i], a);
   unpack8(u[i], b);
   unpack8(d[i], c);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float sg = 1.f / (1.f + __expf(-a[j]));
-    const float silu = a[j] * sg;
-    og[j] = c[j] * b[j] * sg * (1.f + a[j] * (1.f - sg));
-    ou[j] = c[j] * silu;
-  }
+  swiglu_bwd8(a, b, c, og, ou);
   reinterpret_cast<bf16x8*>(dgu + row * 2 * I)[i] = pack8(og);
   reinterpret_cast<bf16x8*>(dgu + row * 2 * I + I)[i] = pack8(ou);
 }

@@ -12,9 +12,15 @@
 //   empty[s]  (each CTA, count 1)    : tcgen05.commit.cta_group::2 ... multicast to both CTAs
 //   tmem_full[a]  (each CTA, count 1): multicast commit after the last k-block of a tile
 //   tmem_empty[a] (leader, count 8)  : one arrive per epilogue warp of both CTAs (peer arrives remotely)
+//
+// Tail split: with T tiles on P CTA pairs the last wave holds r = T mod P tiles (Qwen2.5-7B, M = 4446: the N = 3584
+// GEMMs have 252 tiles on 74 pairs -> 3.4 waves, the 4th wave is 40 % full).  When 0 < r <= P/2 the last r tiles are
+// each cut into S = min(4, P / r) K-ranges, so the last wave costs 1/S of a tile time (3.5 instead of 4 waves).
 #include "gemm_common.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
 
 namespace b200rl {
 
@@ -79,10 +85,35 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
-template <int BN>
+// work unit -> (tile, k-block range, part).  part < 0: whole tile.
+__device__ __forceinline__ void unit_decode(const GemmParams& p, int unit, int kb_total, int& tile, int& kb0,
+                                            int& kb1, int& part, int& sidx) {
+  if (unit < p.tail_first) {
+    tile = unit; kb0 = 0; kb1 = kb_total; part = -1; sidx = 0;
+    return;
+  }
+  const int idx = unit - p.tail_first;
+  sidx = idx / p.tail_split;
+  part = idx - sidx * p.tail_split;
+  tile = p.tail_first + sidx;
+  const int per = (kb_total + p.tail_split - 1) / p.tail_split;
+  kb0 = part * per;
+  kb1 = min(kb_total, kb0 + per);
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int BN, bool B_MN>
 struct PairCfg {
   static constexpr int BH = BN / 2;                      // B columns staged per CTA
-  static constexpr int B_TILE_BYTES = BH * BK * 2;
+  static constexpr int B_SLABS = (BH + 63) / 64;         // MN-major: 64-column swizzle slabs (the last may be partly used)
+  static constexpr int B_TILE_BYTES = B_MN ? B_SLABS * 8192 : BH * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;  // per CTA
   static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
@@ -91,12 +122,14 @@ struct PairCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 };
 
-template <int BN, bool B_MN>
-__global__ void __launch_bounds__(256, 1)
+// EW = epilogue warps per CTA (4 or 8): the fused SwiGLU epilogues use 8, two per TMEM lane quadrant, each pair
+// splitting the accumulator columns.
+template <int BN, bool B_MN, int FUSE, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const GemmParams p) {
-  using C = PairCfg<BN>;
+  using C = PairCfg<BN, B_MN>;
   constexpr int STAGES = C::STAGES;
   constexpr int BM2 = 2 * BM;  // rows per pair tile
   extern __shared__ uint8_t smem_raw[];
@@ -117,7 +150,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 8);
+      mbar_init(&tmem_empty_bar[a], 2 * EW);
     }
     fence_barrier_init();
   }
@@ -138,17 +171,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int num_clusters = gridDim.x >> 1;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;  // num_m_blocks counts 256-row pair tiles
   const int kb_total = p.kb1 + p.kb2;
+  const int num_units = num_tiles <= p.tail_first ? num_tiles : p.tail_first + (num_tiles - p.tail_first) * p.tail_split;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      int m_blk, n_blk;
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      int tile, kb_begin, kb_end, part, sidx, m_blk, n_blk;
+      unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
       tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
       const int row0 = m_blk * BM2 + (int)rank * BM;
-      const int col0 = n_blk * BN + (int)rank * C::BH;
-      for (int kb = 0; kb < kb_total; ++kb) {
+      // FUSE 1: CTA 0 stages 128 gate rows of the weight, CTA 1 the 128 up rows with the same index
+      const int col0 = FUSE == 1 ? n_blk * C::BH + (int)rank * p.fuse_I : n_blk * BN + (int)rank * C::BH;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = smem_gen + stage * C::STAGE_BYTES;
         uint8_t* sb = sa + A_TILE_BYTES;
@@ -162,7 +198,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           tma_load_2d_pair(sb, tb, &full_bar[stage], k0, col0);
         } else {
 #pragma unroll
-          for (int h = 0; h < C::BH / 64; ++h)
+          for (int h = 0; h < C::B_SLABS; ++h)
             tma_load_2d_pair(sb + h * 8192, tb, &full_bar[stage], col0 + h * 64, k0);
         }
         if (!leader) mbar_arrive_remote(&full_bar[stage], 0);
@@ -180,13 +216,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++local) {
+      int tile, kb_begin, kb_end, part, sidx;
+      unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
-      for (int kb = 0; kb < kb_total; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -196,7 +234,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
           const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
                                    : make_smem_desc(sb + k * 32, 16, 1024);
-          umma_bf16_pair(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_bf16_pair(tmem_d, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
         }
         umma_commit_pair(&empty_bar[stage]);
         if (++stage == STAGES) {
@@ -209,9 +247,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;  // 0, or 1 for the second warp of a quadrant (EW == 8)
+    constexpr int NH = EW / 4;          // column shares
     int local = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
-      int m_blk, n_blk;
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++local) {
+      int tile, kb_begin, kb_end, part, sidx, m_blk, n_blk;
+      unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
       tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -220,12 +261,129 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       const int row = m_blk * BM2 + (int)rank * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr0 = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+      if constexpr (FUSE == 1) {
+        // accumulator columns [0,128) = gate(j0..), [128,256) = up(j0..) with j0 = n_blk * 128
+        bf16* gu_row = reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc;
+        bf16* act_row = p.aux_out + (long long)row * p.ld_aux;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr0 + c * 32, r);
-        tmem_ld_wait();
-        if (row_ok) epilogue_store32(p, r, row, n_blk * BN + c * 32, 0);
+        for (int c = half * (4 / NH); c < (half + 1) * (4 / NH); ++c) {
+          uint32_t rg[32], ru[32];
+          tmem_ld_32x32(taddr0 + c * 32, rg);
+          tmem_ld_32x32(taddr0 + 128 + c * 32, ru);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = n_blk * 128 + c * 32 + g * 8;
+              float a[8], b[8], o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                a[i] = __uint_as_float(rg[g * 8 + i]) * p.alpha;
+                b[i] = __uint_as_float(ru[g * 8 + i]) * p.alpha;
+              }
+              const bf16x8 ga = pack8(a), ub = pack8(b);
+              *reinterpret_cast<bf16x8*>(gu_row + col) = ga;
+              *reinterpret_cast<bf16x8*>(gu_row + p.fuse_I + col) = ub;
+              unpack8(ga, a);  // the activation is computed from the bf16-rounded gate / up, like the row kernel
+              unpack8(ub, b);
+              swiglu_fwd8(a, b, o);
+              *reinterpret_cast<bf16x8*>(act_row + col) = pack8(o);
+            }
+          }
+        }
+      } else if constexpr (FUSE == 2) {
+        const bf16* gu_row = p.aux_in + (long long)row * p.ld_aux;
+        bf16* dgu_row = reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc;
+#pragma unroll 1
+        for (int c = half * (BN / 32 / NH); c < (half + 1) * (BN / 32 / NH); ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr0 + c * 32, r);
+          const int colc = n_blk * BN + c * 32;
+          bf16x8 gq[4], uq[4];
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (colc + g * 8 < p.N) {
+                gq[g] = *reinterpret_cast<const bf16x8*>(gu_row + colc + g * 8);
+                uq[g] = *reinterpret_cast<const bf16x8*>(gu_row + p.fuse_I + colc + g * 8);
+              }
+          }
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = colc + g * 8;
+              if (col < p.N) {
+                float a[8], b[8], d[8], og[8], ou[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(r[g * 8 + i]) * p.alpha;
+                unpack8(pack8(d), d);  // dact is a bf16 tensor in the unfused path
+                unpack8(gq[g], a);
+                unpack8(uq[g], b);
+                swiglu_bwd8(a, b, d, og, ou);
+                *reinterpret_cast<bf16x8*>(dgu_row + col) = pack8(og);
+                *reinterpret_cast<bf16x8*>(dgu_row + p.fuse_I + col) = pack8(ou);
+              }
+            }
+          }
+        }
+      } else
+      if (part > 0) {
+        // K-range 1..S-1 of a tail tile: raw fp32 accumulators -> workspace, then raise this warp's flag
+        float* ws = p.tail_ws + ((long long)(sidx * (p.tail_split - 1) + (part - 1)) * 2 + rank) * (BM * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr0 + c * 32, r);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(ws + ((c * 4 + quad) * 32 + lane) * 32);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            dst[g] = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                                 __uint_as_float(r[4 * g + 3]));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(p.tail_flags + (sidx * p.tail_split + part) * 8 + rank * 4 + quad, p.tail_epoch);
+      } else {
+        if (part == 0) {
+          // wait for the same warp (rank, quad) of every other K-range of this tile
+          if (lane == 0) {
+            for (int s = 1; s < p.tail_split; ++s) {
+              const int* f = p.tail_flags + (sidx * p.tail_split + s) * 8 + rank * 4 + quad;
+              long long t0 = clock64();
+              while (ld_acquire_gpu(f) != p.tail_epoch) {
+                if (clock64() - t0 > 40000000000LL) {
+                  printf("b200rl: gemm tail-split flag wait timed out (block %d)\n", blockIdx.x);
+                  __trap();
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr0 + c * 32, r);
+          tmem_ld_wait();
+          if (part == 0) {
+            for (int s = 1; s < p.tail_split; ++s) {
+              const float4* src = reinterpret_cast<const float4*>(
+                  p.tail_ws + ((long long)(sidx * (p.tail_split - 1) + (s - 1)) * 2 + rank) * (BM * BN) +
+                  ((c * 4 + quad) * 32 + lane) * 32);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 v = __ldcg(src + g);
+                r[4 * g] = __float_as_uint(__uint_as_float(r[4 * g]) + v.x);
+                r[4 * g + 1] = __float_as_uint(__uint_as_float(r[4 * g + 1]) + v.y);
+                r[4 * g + 2] = __float_as_uint(__uint_as_float(r[4 * g + 2]) + v.z);
+                r[4 * g + 3] = __float_as_uint(__uint_as_float(r[4 * g + 3]) + v.w);
+              }
+            }
+          }
+          if (row_ok) epilogue_store32(p, r, row, n_blk * BN + c * 32, 0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -254,16 +412,50 @@ bool gemm_pair_enabled() {
   return g_pair_enabled != 0;
 }
 
-template <int BN, bool B_MN>
+// ---- tail-split workspace: one per (device, stream), grown lazily; flags compare against a per-workspace epoch ----
+struct TailWs {
+  float* ws = nullptr;
+  int* flags = nullptr;
+  size_t ws_bytes = 0;
+  int epoch = 0;
+};
+static std::mutex g_tail_mu;
+static std::map<std::pair<int, cudaStream_t>, TailWs> g_tail_ws;
+static int g_tail_enabled = -1;
+static constexpr int TAIL_MAX_FLAGS = 128 * 4 * 8;  // <= 128 tail tiles x 4 parts x 8 warps
+
+void gemm_pair_set_tail_split(int enable) { g_tail_enabled = enable ? 1 : 0; }
+
+static int tail_workspace(cudaStream_t stream, size_t bytes, TailWs** out) {
+  int dev = 0;
+  B200RL_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_tail_mu);
+  TailWs& w = g_tail_ws[std::make_pair(dev, stream)];
+  if (w.ws_bytes < bytes) {
+    if (w.ws) B200RL_CUDA_OK(cudaFree(w.ws));  // synchronises: no kernel still uses the old buffer
+    w.ws = nullptr;
+    w.ws_bytes = 0;
+    B200RL_CUDA_OK(cudaMalloc(&w.ws, bytes));
+    w.ws_bytes = bytes;
+  }
+  if (!w.flags) {
+    B200RL_CUDA_OK(cudaMalloc(&w.flags, TAIL_MAX_FLAGS * sizeof(int)));
+    B200RL_CUDA_OK(cudaMemset(w.flags, 0, TAIL_MAX_FLAGS * sizeof(int)));
+  }
+  *out = &w;
+  return 0;
+}
+
+template <int BN, bool B_MN, int FUSE = 0, int EW = 4>
 static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
-  using C = PairCfg<BN>;
+  using C = PairCfg<BN, B_MN>;
   GemmParams p;
   p.M = a.M;
   p.N = a.N;
   p.kb1 = (a.K1 + BK - 1) / BK;
   p.kb2 = (a.K2 + BK - 1) / BK;
   p.num_m_blocks = (a.M + 2 * BM - 1) / (2 * BM);
-  p.num_n_blocks = (a.N + BN - 1) / BN;
+  p.num_n_blocks = FUSE == 1 ? a.N / BN : (a.N + BN - 1) / BN;
   p.splits = 1;
   p.kb_per_split = p.kb1 + p.kb2;
   p.C = a.C;
@@ -274,6 +466,12 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   p.residual = reinterpret_cast<const bf16*>(a.residual);
   p.ldr = a.ldr;
   p.alpha = a.alpha;
+  if (FUSE) {
+    p.fuse_I = FUSE == 1 ? a.N / 2 : a.N;
+    p.aux_in = reinterpret_cast<const bf16*>(a.aux);
+    p.aux_out = reinterpret_cast<bf16*>(a.aux);
+    p.ld_aux = a.ld_aux;
+  }
   CUtensorMap tA1, tB1, tA2, tB2;
   int rc;
   if ((rc = make_map(&tA1, a.A1, a.K1, a.M, a.lda1, BK, BM))) return rc;
@@ -285,7 +483,7 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
     tA2 = tA1;
     tB2 = tB1;
   }
-  auto kern = gemm_pair_kernel<BN, B_MN>;
+  auto kern = gemm_pair_kernel<BN, B_MN, FUSE, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -295,10 +493,27 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   int clusters = num_sms() / 2;
   if (a.max_ctas > 0 && a.max_ctas / 2 < clusters) clusters = a.max_ctas / 2 > 0 ? a.max_ctas / 2 : 1;
   if (tiles < clusters) clusters = tiles;
+  if (g_tail_enabled < 0) {
+    const char* e = getenv("B200RL_GEMM_TAIL_SPLIT");
+    g_tail_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int kb_total = p.kb1 + p.kb2;
+  const int S = (g_tail_enabled && FUSE == 0) ? pair_tail_split(tiles, clusters, kb_total) : 1;
+  if (S > 1) {
+    const int rem = tiles % clusters;
+    TailWs* w = nullptr;
+    int rc2 = tail_workspace(stream, (size_t)rem * (S - 1) * 2 * BM * BN * sizeof(float), &w);
+    if (rc2) return rc2;
+    p.tail_first = tiles - rem;
+    p.tail_split = S;
+    p.tail_ws = w->ws;
+    p.tail_flags = w->flags;
+    p.tail_epoch = ++w->epoch;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(128 + 32 * EW);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -313,10 +528,33 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   return 0;
 }
 
-// Called by gemm_dispatch for A K-major layouts (TN / dX) without split-K; bn in {128, 256}.
+// Called by gemm_dispatch for A K-major layouts (TN / dX) without split-K; bn in {128, 192, 224, 256}.
+static int fuse_epilogue_warps() {
+  static int ew = 0;
+  if (!ew) {
+    const char* e = getenv("B200RL_GEMM_FUSE_EW");
+    ew = (e && e[0] == '4') ? 4 : 8;
+  }
+  return ew;
+}
+
+bool gemm_fuse_supported(int M, int I) { return gemm_pair_enabled() && M > BM && I % 128 == 0; }
+
 int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream) {
   const bool b_mn = (a.mn_major & 2) != 0;
+  if (a.fuse == 1) {
+    B200RL_REQUIRE(!b_mn && !a.c_fp32 && !a.bias && !a.residual && a.aux && a.N % 256 == 0 && a.ld_aux % 8 == 0,
+                   "gemm(fused swiglu fwd): needs TN layout, bf16 C, N = 2I with I %% 128 == 0, no bias/residual");
+    return fuse_epilogue_warps() == 8 ? launch_pair<256, false, 1, 8>(a, stream) : launch_pair<256, false, 1, 4>(a, stream);
+  }
+  if (a.fuse == 2) {
+    B200RL_REQUIRE(b_mn && !a.c_fp32 && !a.bias && !a.residual && a.aux && a.N % 8 == 0 && a.ld_aux % 8 == 0,
+                   "gemm(fused swiglu bwd): needs dX layout, bf16 C, no bias/residual");
+    return fuse_epilogue_warps() == 8 ? launch_pair<256, true, 2, 8>(a, stream) : launch_pair<256, true, 2, 4>(a, stream);
+  }
   if (bn == 256) return b_mn ? launch_pair<256, true>(a, stream) : launch_pair<256, false>(a, stream);
+  if (bn == 224) return b_mn ? launch_pair<224, true>(a, stream) : launch_pair<224, false>(a, stream);
+  if (bn == 192) return b_mn ? launch_pair<192, true>(a, stream) : launch_pair<192, false>(a, stream);
   if (bn == 128) return b_mn ? launch_pair<128, true>(a, stream) : launch_pair<128, false>(a, stream);
   return set_error(B200RL_ERR_UNSUPPORTED, "gemm(pair): BN=%d not instantiated", bn);
 }
@@ -326,5 +564,10 @@ int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream) {
 // test / bisection switch: 1 = use CTA-pair kernels where applicable (default), 0 = single-CTA only
 extern "C" int b200rl_gemm_set_cta_pair(int enable) {
   b200rl::g_pair_enabled = enable ? 1 : 0;
+  return 0;
+}
+// test / bisection switch for the K-split of the last partial wave (default on; env B200RL_GEMM_TAIL_SPLIT=0 disables)
+extern "C" int b200rl_gemm_set_tail_split(int enable) {
+  b200rl::gemm_pair_set_tail_split(enable);
   return 0;
 }

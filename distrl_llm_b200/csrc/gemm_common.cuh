@@ -22,6 +22,19 @@ struct GemmParams {
   const bf16* residual;
   long long ldr;
   float alpha;
+  // CTA-pair kernel only: split-K of the LAST (partial) wave.  Work units 0..tail_first-1 are whole tiles; every
+  // later tile is cut into tail_split K-ranges that run concurrently on different CTA pairs.  Parts 1.. spill their
+  // fp32 accumulators to tail_ws and raise tail_flags (value = tail_epoch); part 0 adds them and runs the epilogue.
+  int tail_first = 0x7fffffff;
+  int tail_split = 1;
+  float* tail_ws = nullptr;
+  int* tail_flags = nullptr;
+  int tail_epoch = 0;
+  // CTA-pair kernel only: fused SwiGLU epilogues (GemmArgs::fuse)
+  const bf16* aux_in = nullptr;
+  bf16* aux_out = nullptr;
+  long long ld_aux = 0;
+  int fuse_I = 0;
 };
 
 // ---- descriptors ---------------------------------------------------------------------------
@@ -155,10 +168,33 @@ struct GemmArgs {
   long long c_split_stride;
   int force_bn;   // 0 = heuristic
   int max_ctas;   // 0 = all SMs
+  // Fused SwiGLU epilogues (CTA-pair kernel, 256-wide tiles; the caller checks gemm_fuse_supported()):
+  //  1: gate|up projection, N = 2I.  Each 256-column tile holds gate columns j0..j0+127 (B rows j0.., staged by
+  //     CTA 0) and up columns j0..j0+127 (B rows I+j0.., staged by CTA 1); the epilogue writes gate|up to C [M,2I]
+  //     AND silu(gate)*up to aux [M, I] (ld_aux).
+  //  2: down-projection input gradient, N = I (dX form).  The epilogue turns the accumulator dact into
+  //     dgate|dup using gate|up read from aux [M,2I] (ld_aux) and writes them to C [M,2I].
+  int fuse = 0;
+  void* aux = nullptr;
+  long long ld_aux = 0;
 };
+bool gemm_fuse_supported(int M, int I);
 
+
+// K-split factor of the last partial wave of the CTA-pair kernel (1 = none): only when that wave is at most half full
+// and every K-range keeps >= 64 k-blocks -- measured on B200 (profiles/r1_run19*): with K = 3584 the spill / flag /
+// reload chain (~15 us) costs more than the quarter wave it saves, with K >= 18944 it saves 7-13 % of the GEMM.
+inline int pair_tail_split(long long tiles, int clusters, int kb_total) {
+  const long long rem = tiles % clusters;
+  if (tiles <= clusters || rem == 0 || rem * 2 > clusters || rem > 128) return 1;
+  int S = (int)(clusters / rem);
+  if (S > 4) S = 4;
+  while (S > 1 && kb_total < 64 * S) --S;
+  return S;
+}
 
 int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream);  // gemm2_tcgen05.cu
+void gemm_pair_set_tail_split(int enable);
 bool gemm_pair_enabled();
 
 }  // namespace b200rl

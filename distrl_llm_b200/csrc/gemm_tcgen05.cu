@@ -250,6 +250,9 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+// relative per-flop cost of the narrower pair tiles (measured on B200, scripts/bench_gemm.py)
+static double g_pair_cost224 = 1.12, g_pair_cost192 = 1.35;
+
 int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
   B200RL_REQUIRE(a.M > 0 && a.N > 0 && a.K1 > 0 && a.K2 >= 0, "gemm: bad shape M=%d N=%d K1=%d K2=%d",
                  a.M, a.N, a.K1, a.K2);
@@ -274,11 +277,36 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
     if (bn == 128) return launch<128, true, true>(a, stream);
     return set_error(B200RL_ERR_UNSUPPORTED, "gemm(dW form): BN=%d not instantiated", bn);
   }
+  if (a.fuse) {
+    B200RL_REQUIRE(!a_mn && a.splits <= 1 && gemm_fuse_supported(a.M, a.fuse == 1 ? a.N / 2 : a.N),
+                   "gemm: fused SwiGLU epilogue needs the CTA-pair kernel (M > 128, I %% 128 == 0)");
+    return gemm_pair_dispatch(a, 256, stream);
+  }
   // CTA-pair kernel (cta_group::2, 256-row tiles) for the large activation x weight GEMMs
   if (gemm_pair_enabled() && a.splits <= 1 && a.M > BM && a.N >= 256 &&
-      (a.force_bn == 0 || a.force_bn == 128 || a.force_bn == 256)) {
-    // pair tiles are 256 x 256: the 128-wide pair tile is smem-bound again (measured 630-750 TFLOP/s)
-    const int pbn = a.force_bn ? a.force_bn : 256;
+      (a.force_bn == 0 || a.force_bn == 128 || a.force_bn == 192 || a.force_bn == 224 || a.force_bn == 256)) {
+    // Pair tiles are 256 x BN.  256 x 256 is the most efficient per flop (the 128-wide pair tile is smem-bound
+    // again, measured 630-750 TFLOP/s), but N = 3584 (14 tiles of 256) leaves the last of 3.4 waves 40 % full on
+    // 74 CTA pairs: pick the width in {256, 224, 192} with the lowest waves x per-tile cost.
+    int pbn = a.force_bn;
+    if (pbn == 0) {
+      const int clusters = num_sms() / 2;
+      const long long mb = (a.M + 2 * BM - 1) / (2 * BM);
+      double best = 1e30;
+      const int cands[3] = {256, 224, 192};
+      const double cost[3] = {256.0, 224.0 * g_pair_cost224, 192.0 * g_pair_cost192};
+      for (int i = 0; i < 3; ++i) {
+        const long long tiles = mb * ((a.N + cands[i] - 1) / cands[i]);
+        // waves, counting the K-split of a last wave that is at most half full (gemm2_tcgen05.cu)
+        double waves = (double)(tiles / clusters);
+        if (tiles % clusters) waves += 1.0 / pair_tail_split(tiles, clusters, (a.K1 + BK - 1) / BK + (a.K2 + BK - 1) / BK);
+        const double t = waves * cost[i];
+        if (t < best - 1e-9) {
+          best = t;
+          pbn = cands[i];
+        }
+      }
+    }
     return gemm_pair_dispatch(a, pbn, stream);
   }
   if (bn == 0) {
@@ -342,5 +370,25 @@ extern "C" int b200rl_gemm(const void* A1, long long lda1, const void* B1, long 
   a.alpha = alpha; a.M = M; a.N = N;
   a.mn_major = mn_major; a.splits = splits; a.c_split_stride = c_split_stride;
   a.force_bn = force_bn; a.max_ctas = max_ctas;
+  return gemm_dispatch(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Fused SwiGLU GEMMs (CTA-pair kernel).  mode 1: gu[M,2I] = A1.B1^T + A2.B2^T and act[M,I] = silu(gate)*up;
+// mode 2: dgu[M,2I] = swiglu_bwd(gu, dact = A1.B1 + A2.B2) with B stored [K, I].  Bit-identical to b200rl_gemm
+// followed by b200rl_swiglu_fwd / b200rl_swiglu_bwd.
+extern "C" int b200rl_gemm_swiglu(int mode, const void* A1, long long lda1, const void* B1, long long ldb1, int K1,
+                                  const void* A2, long long lda2, const void* B2, long long ldb2, int K2,
+                                  void* C, long long ldc, void* aux, long long ld_aux, int M, int I, void* stream) {
+  B200RL_REQUIRE(mode == 1 || mode == 2, "gemm_swiglu: mode must be 1 (forward) or 2 (backward)");
+  GemmArgs a;
+  a.A1 = A1; a.B1 = B1; a.A2 = A2; a.B2 = B2;
+  a.lda1 = lda1; a.ldb1 = ldb1; a.lda2 = lda2; a.ldb2 = ldb2;
+  a.K1 = K1; a.K2 = K2;
+  a.C = C; a.ldc = ldc; a.c_fp32 = 0;
+  a.bias = nullptr; a.residual = nullptr; a.ldr = 0;
+  a.alpha = 1.f; a.M = M; a.N = mode == 1 ? 2 * I : I;
+  a.mn_major = mode == 1 ? 0 : 2; a.splits = 1; a.c_split_stride = 0;
+  a.force_bn = 0; a.max_ctas = 0;
+  a.fuse = mode; a.aux = aux; a.ld_aux = ld_aux;
   return gemm_dispatch(a, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -43,8 +43,12 @@ struct GemmArgs {
   long long c_split_stride;
   int force_bn;
   int max_ctas;
+  int fuse = 0;          // keep in sync with gemm_common.cuh
+  void* aux = nullptr;
+  long long ld_aux = 0;
 };
 int gemm_dispatch(const GemmArgs& a, cudaStream_t stream);
+bool gemm_fuse_supported(int M, int I);
 
 }  // namespace b200rl
 
@@ -181,6 +185,7 @@ struct b200rl_model {
   int rope_L;
   // optional resident bf16 copy of the dequantised base weights (b200rl_model_set_weight_cache): 15 GB for a 7B
   // model, 8 % of a B200's HBM, and it removes 2 x n_layers x 4 dequant passes per micro-batch
+  bool fuse_swiglu = true;  // b200rl_model_set_fusion
   bf16* wcache = nullptr;
   long long wcache_per_layer = 0;
   std::vector<uint8_t> wcache_valid;  // [n_layers*4]
@@ -527,7 +532,7 @@ namespace {
 int gemm_l(b200rl_model* m, int cat, int layout, cudaStream_t st, const bf16* A1, long long lda1, const bf16* B1, long long ldb1, int K1,
             const bf16* A2, long long lda2, const bf16* B2, long long ldb2, int K2, bf16* C,
             long long ldc, const bf16* bias, const bf16* residual, long long ldr, float alpha, int M,
-            int N) {
+            int N, int fuse = 0, void* aux = nullptr, long long ld_aux = 0) {
   GemmArgs a;
   a.A1 = A1; a.B1 = B1; a.A2 = A2; a.B2 = B2;
   a.lda1 = lda1; a.ldb1 = ldb1; a.lda2 = lda2; a.ldb2 = ldb2;
@@ -535,6 +540,7 @@ int gemm_l(b200rl_model* m, int cat, int layout, cudaStream_t st, const bf16* A1
   a.bias = bias; a.residual = residual; a.ldr = ldr; a.alpha = alpha;
   a.M = M; a.N = N; a.mn_major = layout; a.splits = 1; a.c_split_stride = 0;
   a.force_bn = 0; a.max_ctas = 0;
+  a.fuse = fuse; a.aux = aux; a.ld_aux = ld_aux;
   PM(cat, 2.0 * M * N * K1 + (K2 ? 2.0 * M * N * m->cfg.lora_r : 0.0));
   if (cat == CAT_GEMM_SKINNY) {
     // rank-r LoRA intermediates (N = K2 <= 192): only ceil(M/128) output tiles, so split K across CTAs
@@ -680,6 +686,7 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
   }
   // ---------------- forward ----------------
   const bf16* Wd = nullptr;
+  const bool fuse_swiglu = m->fuse_swiglu && gemm_fuse_supported(M, I);
   const bool lora = !lora_off;  // adapter-disabled pass = reference policy pi_ref (KL term)
   PM(CAT_ROW, 2.0 * M * H * 2);
   RC(b200rl_embed(ids, m->embed, m->X, M, H, V, stream));
@@ -713,10 +720,15 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     RC(b200rl_rmsnorm_fwd(a.x_mid, w.ln2_w, a.h2, a.rstd2, M, H, c.rms_eps, stream));
     if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
     RC(base_weight(m, st, l, 2, &Wd));
-    RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, Wd, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, lora ? gg.K2 : 0, a.gu, 2 * I,
-               nullptr, nullptr, 0, 1.f, M, 2 * I));
-    PM(CAT_ROW, 3.0 * M * I * 2);
-    RC(b200rl_swiglu_fwd(a.gu, a.act, M, I, stream));
+    if (fuse_swiglu) {  // gate|up GEMM whose epilogue also writes act = silu(gate)*up
+      RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, Wd, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, lora ? gg.K2 : 0, a.gu, 2 * I,
+                 nullptr, nullptr, 0, 1.f, M, 2 * I, 1, a.act, I));
+    } else {
+      RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, Wd, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, lora ? gg.K2 : 0, a.gu, 2 * I,
+                 nullptr, nullptr, 0, 1.f, M, 2 * I));
+      PM(CAT_ROW, 3.0 * M * I * 2);
+      RC(b200rl_swiglu_fwd(a.gu, a.act, M, I, stream));
+    }
     if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
     RC(base_weight(m, st, l, 3, &Wd));
     RC(gemm_l(m, CAT_GEMM, 0, st, a.act, I, Wd, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, lora ? gd.K2 : 0, xn, H, nullptr,
@@ -771,9 +783,14 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + gd.bcat, gd.K2, H, nullptr, 0, nullptr, 0, 0, m->du, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
     RC(lora_dw(m, st, gd, m->dx, H, a.u_d, a.act, I, m->du, M));
     RC(base_weight(m, st, l, 3, &Wd));
-    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, m->du, gd.K2, ar + gd.acat, I, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
-    PM(CAT_ROW, 5.0 * M * I * 2);
-    RC(b200rl_swiglu_bwd(a.gu, m->dact, m->dgu, M, I, stream));
+    if (fuse_swiglu) {  // dact never reaches HBM: the epilogue turns it into dgate|dup
+      RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, m->du, gd.K2, ar + gd.acat, I, gd.K2, m->dgu, 2 * I, nullptr, nullptr, 0, 1.f, M, I,
+                 2, a.gu, 2 * I));
+    } else {
+      RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, m->du, gd.K2, ar + gd.acat, I, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
+      PM(CAT_ROW, 5.0 * M * I * 2);
+      RC(b200rl_swiglu_bwd(a.gu, m->dact, m->dgu, M, I, stream));
+    }
     // ---- gate|up:  gu = h2.Wgu^T + u_gu.Bgu^T
     RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dgu, 2 * I, ar + gg.bcat, gg.K2, 2 * I, nullptr, 0, nullptr, 0, 0, m->du, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
     RC(lora_dw(m, st, gg, m->dgu, 2 * I, a.u_gu, a.h2, H, m->du, M));
@@ -824,6 +841,13 @@ extern "C" int b200rl_model_set_weight_cache(b200rl_model* m, void* buf, long lo
   m->wcache = (bf16*)buf;
   m->wcache_per_layer = need / 2 / m->cfg.n_layers;
   m->wcache_valid.assign((size_t)m->cfg.n_layers * 4, 0);
+  return 0;
+}
+
+// bit 0: SwiGLU fused into the gate|up / down-dX GEMM epilogues (default on; results are bit-identical either way)
+extern "C" int b200rl_model_set_fusion(b200rl_model* m, int flags) {
+  B200RL_REQUIRE(m != nullptr, "model_set_fusion: null model");
+  m->fuse_swiglu = (flags & 1) != 0;
   return 0;
 }
 

@@ -42,6 +42,16 @@ int b200rl_gemm(const void* A1, long long lda1, const void* B1, long long ldb1, 
                 int force_bn, int max_ctas, void* stream);
 /* bisection switch: 1 (default) = CTA-pair (cta_group::2) kernels where applicable, 0 = single-CTA kernels only */
 int b200rl_gemm_set_cta_pair(int enable);
+/* 1 (default) = the CTA-pair GEMM splits the tiles of its last, partially filled wave along K (gemm2_tcgen05.cu) */
+int b200rl_gemm_set_tail_split(int enable);
+/* G1 + G5 fused (CTA-pair kernel; needs M > 128 and I % 128 == 0, else B200RL_ERR_*):
+ * mode 1: gu[M,2I] = A1.B1^T + A2.B2^T (gate rows then up rows of the weight, Qwen2MLP gate_proj|up_proj) and
+ *         aux = act[M,I] = silu(gate)*up written by the same epilogue;
+ * mode 2: C = dgu[M,2I] from dact = A1.B1 + A2.B2 (B stored [K, I]) and aux = gu[M,2I].
+ * Bit-identical to b200rl_gemm followed by b200rl_swiglu_fwd / b200rl_swiglu_bwd. */
+int b200rl_gemm_swiglu(int mode, const void* A1, long long lda1, const void* B1, long long ldb1, int K1,
+                       const void* A2, long long lda2, const void* B2, long long ldb2, int K2,
+                       void* C, long long ldc, void* aux, long long ld_aux, int M, int I, void* stream);
 
 /* ---- G2/G3/G5 row kernels (reference: Unsloth RMSNorm / RoPE / SwiGLU inside policy(...)) ---- */
 int b200rl_embed(const int* ids, const void* table, void* out, int M, int H, int vocab, void* stream);
@@ -185,6 +195,8 @@ int b200rl_model_destroy(b200rl_model* m);
  * with and without the cache (same dequant kernel, same GEMM operands). */
 long long b200rl_model_weight_cache_bytes(const b200rl_model_config* cfg);
 int b200rl_model_set_weight_cache(b200rl_model* m, void* buf, long long bytes);
+/* bit 0: fuse SwiGLU into the gate|up and down-dX GEMM epilogues (default 1; bit-identical results) */
+int b200rl_model_set_fusion(b200rl_model* m, int flags);
 /* refresh the bf16 operand copies of the LoRA tensors after an optimizer step */
 int b200rl_model_sync_lora(b200rl_model* m, void* stream);
 /* one micro-batch: scores B sequences of length L = P+T, accumulates LoRA grads.

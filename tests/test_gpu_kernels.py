@@ -36,6 +36,9 @@ GEMM_SHAPES = [
     (640, 4608, 3584, 64, 256),   # QKV-shaped
     (4096, 1024, 2048, 0, 256),   # many tiles per CTA (pipeline wrap-around)
     (4100, 3584, 1024, 64, 0),
+    (600, 3584, 512, 64, 224),    # 224-wide pair tile (N = 16 x 224)
+    (900, 1000, 320, 64, 224),    # ragged N with the 224 tile
+    (4446, 3584, 1024, 64, 192),
 ]
 
 
@@ -50,6 +53,8 @@ def gemm_mode(request, cuda):
 
 @pytest.mark.parametrize("M,N,K1,K2,bn", GEMM_SHAPES)
 def test_gemm_tn(cuda, gemm_mode, M, N, K1, K2, bn):
+    if bn == 224 and not gemm_mode:
+        pytest.skip("224-wide tiles exist only in the CTA-pair kernel")
     from distrl_llm_b200 import ops
     a1 = _rand((M, K1), cuda, seed=1)
     b1 = _rand((N, K1), cuda, seed=2)
@@ -64,6 +69,72 @@ def test_gemm_tn(cuda, gemm_mode, M, N, K1, K2, bn):
     err = _rel_err(out, ref)
     assert err < 4e-3, f"rel err {err}"
     assert torch.isfinite(out.float()).all()
+
+
+@pytest.mark.parametrize("M,N,K1,b_mn", [(4446, 3584, 8192, False), (4446, 3584, 8192, True),    # rem 30 of 74 -> 2 K-ranges
+                                        (1536, 3584, 16384, False), (1536, 3584, 16384, True),  # rem 10 -> 4 K-ranges
+                                        (2100, 4608, 12288, False)])
+def test_gemm_tail_split(cuda, M, N, K1, b_mn):
+    """CTA-pair GEMM with the last partial wave split along K (gemm2_tcgen05.cu): same result as with the split
+    disabled, up to the fp32 summation order of the K-ranges; fp32 output compared tightly against torch."""
+    from distrl_llm_b200 import _capi, ops
+    K2 = 64
+    a1 = _rand((M, K1), cuda, seed=1)
+    b1 = _rand((K1, N) if b_mn else (N, K1), cuda, seed=2)
+    a2 = _rand((M, K2), cuda, seed=3)
+    b2 = _rand((K2, N) if b_mn else (N, K2), cuda, seed=4)
+    bias = _rand((N,), cuda, seed=5)
+    res = _rand((M, N), cuda, seed=6)
+    ref = a1.float() @ (b1.float() if b_mn else b1.float().T) + a2.float() @ (b2.float() if b_mn else b2.float().T)
+    ref = 0.25 * ref + bias.float()[None] + res.float()
+    outs = []
+    try:
+        for en in (1, 0):
+            _capi.lib().b200rl_gemm_set_tail_split(en)
+            for _ in range(3):   # repeated launches reuse the workspace with a new epoch
+                o32 = ops.gemm(a1, b1, a2, b2, bias=bias, residual=res, alpha=0.25, out_fp32=True, force_bn=256, b_mn=b_mn)
+            o16 = ops.gemm(a1, b1, a2, b2, bias=bias, residual=res, alpha=0.25, force_bn=256, b_mn=b_mn)
+            torch.cuda.synchronize()
+            assert _rel_err(o32, ref) < 2e-5 and _rel_err(o16, ref) < 4e-3
+            outs.append((o32, o16))
+    finally:
+        _capi.lib().b200rl_gemm_set_tail_split(1)
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,I,H", [(300, 256, 192), (4446, 1024, 512), (700, 18944, 256)])
+def test_gemm_swiglu_fused_is_bit_identical(cuda, M, I, H):
+    """G1+G5 fusion (gemm2_tcgen05.cu FUSE 1/2): the fused epilogues give exactly the bits of GEMM + row kernel."""
+    from distrl_llm_b200 import _capi, ops
+    lib = _capi.lib()
+    K2 = 64
+    st = _capi.stream()
+    try:
+        lib.b200rl_gemm_set_tail_split(0)      # same K summation order in both paths
+        # forward: gu = h.Wgu^T + u.Bgu^T ; act = silu(gate)*up
+        h, u = _rand((M, H), cuda, seed=1), _rand((M, K2), cuda, seed=2)
+        Wgu, Bgu = _rand((2 * I, H), cuda, seed=3, scale=0.2), _rand((2 * I, K2), cuda, seed=4, scale=0.2)
+        gu_ref = ops.gemm(h, Wgu, u, Bgu, force_bn=256)
+        act_ref = ops.swiglu_fwd(gu_ref)
+        gu = torch.empty_like(gu_ref)
+        act = torch.empty_like(act_ref)
+        _capi.check(lib.b200rl_gemm_swiglu(1, h.data_ptr(), H, Wgu.data_ptr(), H, H, u.data_ptr(), K2, Bgu.data_ptr(), K2, K2,
+                                           gu.data_ptr(), 2 * I, act.data_ptr(), I, M, I, st), "gemm_swiglu fwd")
+        torch.cuda.synchronize()
+        assert torch.equal(gu.view(torch.int16), gu_ref.view(torch.int16))
+        assert torch.equal(act.view(torch.int16), act_ref.view(torch.int16))
+        # backward: dact = dx.Wd + du.Acat (Wd stored [H, I]) ; dgu = swiglu_bwd(gu, dact)
+        dx, du = _rand((M, H), cuda, seed=5), _rand((M, K2), cuda, seed=6)
+        Wd, Ad = _rand((H, I), cuda, seed=7, scale=0.2), _rand((K2, I), cuda, seed=8, scale=0.2)
+        dact_ref = ops.gemm(dx, Wd, du, Ad, force_bn=256, b_mn=True)
+        dgu_ref = ops.swiglu_bwd(gu_ref, dact_ref)
+        dgu = torch.empty_like(dgu_ref)
+        _capi.check(lib.b200rl_gemm_swiglu(2, dx.data_ptr(), H, Wd.data_ptr(), I, H, du.data_ptr(), K2, Ad.data_ptr(), I, K2,
+                                           dgu.data_ptr(), 2 * I, gu_ref.data_ptr(), 2 * I, M, I, st), "gemm_swiglu bwd")
+        torch.cuda.synchronize()
+        assert torch.equal(dgu.view(torch.int16), dgu_ref.view(torch.int16))
+    finally:
+        lib.b200rl_gemm_set_tail_split(1)
 
 
 def test_gemm_epilogues(cuda, gemm_mode):
@@ -87,8 +158,12 @@ def test_gemm_epilogues(cuda, gemm_mode):
 
 @pytest.mark.parametrize("M,N,K1,K2,bn", [(128, 64, 64, 0, 0), (300, 200, 192, 0, 0), (1000, 512, 1024, 64, 0),
                                            (640, 3584, 4608, 64, 256), (4100, 1024, 2048, 64, 192),
-                                           (512, 384, 256, 128, 128), (6896, 3584, 1024, 64, 0)])
+                                           (512, 384, 256, 128, 128), (6896, 3584, 1024, 64, 0),
+                                           (600, 3584, 512, 64, 224), (900, 1000, 320, 64, 224),
+                                           (700, 1000, 320, 64, 192)])
 def test_gemm_dx_form(cuda, gemm_mode, M, N, K1, K2, bn):
+    if bn == 224 and not gemm_mode:
+        pytest.skip("224-wide tiles exist only in the CTA-pair kernel")
     """dX form: C = A1 @ B1 + A2 @ B2 with the B operands stored [K, N] (weights as stored [out, in])."""
     from distrl_llm_b200 import ops
     a1 = _rand((M, K1), cuda, seed=1)

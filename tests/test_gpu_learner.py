@@ -260,3 +260,24 @@ def test_weight_cache_is_bit_identical(cuda):
             ln._compute_gradients(prompts, answers, list(rewards), export=False)
         out.append((pol.lora_grad.clone(), float(pol.loss_accum.item())))
     assert torch.equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+
+
+def test_swiglu_fusion_is_bit_identical(cuda):
+    """b200rl_model_set_fusion: SwiGLU inside the GEMM epilogues vs separate row kernels -> identical gradients."""
+    from distrl_llm_b200 import _capi
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer
+    from distrl_llm_b200.policy import Policy
+    ocfg = lo.OracleConfig(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=64,
+                           lora_r=16, lora_alpha=16)
+    params, nf4 = lo.make_params(ocfg, seed=2)
+    P, T, B = 12, 36, 4          # 192 rows per micro-batch > 128: the CTA-pair kernels are used
+    prompts, answers, rewards = lo.make_batch(ocfg, 8, P, T, seed=4, ragged=True, group_size=4, learner="grpo")
+    out = []
+    for fuse in (1, 0):
+        pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, cuda, max_batch=B, P=P, T=T)
+        _capi.check(_capi.lib().b200rl_model_set_fusion(pol.handle, fuse), "set_fusion")
+        ln = GRPOLearner(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5})
+        ln._compute_gradients(prompts, answers, list(rewards), export=False)
+        out.append((pol.lora_grad.clone(), float(pol.loss_accum.item())))
+    assert out[0][0].abs().max() > 0
+    assert torch.equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
