@@ -104,6 +104,7 @@ SIGNATURES = {
     "b200rl_model_profile": (c_int, [c_void_p, c_int]),
     "b200rl_model_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200rl_launch_count": (c_ll, []),
+    "b200rl_set_pdl": (c_int, [c_int]),
     "b200rl_model_microbatch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }

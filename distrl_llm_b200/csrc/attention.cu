@@ -274,6 +274,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ key_mask,
 // ------------------------------------------------------------------------------------------
 __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout,
                                   float* __restrict__ delta, int L, int nq, int hd, long long rows) {
+  pdl_enter();
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (row, head)
   if (w >= rows * nq) return;
   const long long row = w / nq;
@@ -609,8 +610,8 @@ static int attn_bwd_launch(const void* qkv, const int* key_mask, const void* out
   const long long rows = (long long)B * L;
   {
     const long long warps = rows * nq;
-    attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>((const bf16*)out, (const bf16*)dout,
-                                                                        delta, L, nq, HD, rows);
+    B200RL_CUDA_OK(launch_pdl(attn_delta_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, (const bf16*)out, (const bf16*)dout,
+                                                                        delta, L, nq, HD, rows));
     B200RL_LAUNCH_OK();
   }
   {
@@ -643,8 +644,8 @@ static int attn_bwd_tc(const void* qkv, const int* key_mask, const void* out, co
                        float* delta, void* dqkv, int B, int L, int nq, int nkv, float scale, cudaStream_t stream) {
   const long long rows = (long long)B * L;
   const long long warps = rows * nq;
-  attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, L, nq,
-                                                                      128, rows);
+  B200RL_CUDA_OK(launch_pdl(attn_delta_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, (const bf16*)out, (const bf16*)dout, delta, L, nq,
+                                                                      128, rows));
   B200RL_LAUNCH_OK();
   return attn_bwd_tc_launch(qkv, key_mask, dout, lse, delta, dqkv, B, L, nq, nkv, scale, stream);
 }
@@ -727,8 +728,8 @@ extern "C" int b200rl_attn_seg_bwd(const void* qkv, const int* key_mask, const v
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // delta[h][row]: the classic kernel with B = 1, L = rows uses exactly that index
   const long long warps = rows * n_q_heads;
-  attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, (int)rows,
-                                                                  n_q_heads, 128, rows);
+  B200RL_CUDA_OK(launch_pdl(attn_delta_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, st, (const bf16*)out, (const bf16*)dout, delta, (int)rows,
+                                                                  n_q_heads, 128, rows));
   B200RL_LAUNCH_OK();
   return attn_bwd_seg_launch(qkv, key_mask, dout, lse, delta, dqkv, kv_part, rows, n_q_heads, n_kv_heads, scale,
                              qblocks_dev, n_qblocks, kblocks_dev, n_kblocks, red_start_dev, red_list_dev, st);

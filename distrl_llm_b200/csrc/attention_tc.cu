@@ -171,6 +171,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_enter();
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer: Q, then the K ring (a K slot is free as soon as QK_j retired) ====
@@ -438,6 +439,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_enter();
   // TMEM columns: S0 [0,64) S1 [64,128) dP0 [128,192) dP1 [192,256) dQ [256,384)
 
   if (warp == 0 && lane == 0) {
@@ -653,6 +655,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_enter();
   // TMEM columns: S^T0 [0,64) S^T1 [64,128) dP^T0 [128,192) dP^T1 [192,256) dK [256,384) dV [384,512)
 
   if (warp == 0 && lane == 0) {
@@ -823,6 +826,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
 // packed layout: dK/dV of key row m = sum (fixed order) of its fp32 partial rows -> bf16 into dqkv
 __global__ void kv_reduce_kernel(const float* __restrict__ part, const int* __restrict__ row_start,
                                  const int* __restrict__ row_list, bf16* __restrict__ dqkv, int nq, int nkv) {
+  pdl_enter();
   const int m = blockIdx.x;
   const int s0 = row_start[m], s1 = row_start[m + 1];
   const int width = 2 * nkv * HD;
@@ -924,7 +928,7 @@ int attn_fwd_tc_launch(const void* qkv, const int* key_mask, void* out, float* l
   p.L = L;
   p.stat_h = L;
   dim3 grid((L + BQ - 1) / BQ, nq, B);
-  attn_fwd_tc_kernel<<<grid, 384, SMEM_FWD, stream>>>(tm, p);
+  B200RL_CUDA_OK(launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(384), SMEM_FWD, stream, tm, p));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -942,12 +946,12 @@ int attn_bwd_tc_launch(const void* qkv, const int* key_mask, const void* dout, c
   p.stat_h = L;
   {
     dim3 grid((L + BQ - 1) / BQ, nq, B);
-    attn_bwd_dq_tc_kernel<<<grid, 384, SMEM_DQ, stream>>>(m.q128, m.d128, m.q64, p);
+    B200RL_CUDA_OK(launch_pdl(attn_bwd_dq_tc_kernel, dim3(grid), dim3(384), SMEM_DQ, stream, m.q128, m.d128, m.q64, p));
     B200RL_LAUNCH_OK();
   }
   {
     dim3 grid((L + BQ - 1) / BQ, nkv, B);
-    attn_bwd_dkv_tc_kernel<<<grid, 384, SMEM_DKV, stream>>>(m.q128, m.q64, m.d64, p);
+    B200RL_CUDA_OK(launch_pdl(attn_bwd_dkv_tc_kernel, dim3(grid), dim3(384), SMEM_DKV, stream, m.q128, m.q64, m.d64, p));
     B200RL_LAUNCH_OK();
   }
   return 0;
@@ -966,7 +970,7 @@ int attn_fwd_seg_launch(const void* qkv, const int* key_mask, void* out, float* 
   p.qblocks = qblocks_dev;
   p.stat_h = (int)rows;
   dim3 grid(n_qblocks, nq, 1);
-  attn_fwd_tc_kernel<<<grid, 384, SMEM_FWD, stream>>>(tm, p);
+  B200RL_CUDA_OK(launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(384), SMEM_FWD, stream, tm, p));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -988,15 +992,15 @@ int attn_bwd_seg_launch(const void* qkv, const int* key_mask, const void* dout, 
   p.stat_h = (int)rows;
   {
     dim3 grid(n_qblocks, nq, 1);
-    attn_bwd_dq_tc_kernel<<<grid, 384, SMEM_DQ, stream>>>(m.q128, m.d128, m.q64, p);
+    B200RL_CUDA_OK(launch_pdl(attn_bwd_dq_tc_kernel, dim3(grid), dim3(384), SMEM_DQ, stream, m.q128, m.d128, m.q64, p));
     B200RL_LAUNCH_OK();
   }
   {
     dim3 grid(n_kblocks, nkv, 1);
-    attn_bwd_dkv_tc_kernel<<<grid, 384, SMEM_DKV, stream>>>(m.q128, m.q64, m.d64, p);
+    B200RL_CUDA_OK(launch_pdl(attn_bwd_dkv_tc_kernel, dim3(grid), dim3(384), SMEM_DKV, stream, m.q128, m.q64, m.d64, p));
     B200RL_LAUNCH_OK();
   }
-  kv_reduce_kernel<<<(unsigned)rows, 128, 0, stream>>>(kv_part, red_start_dev, red_list_dev, (bf16*)dqkv, nq, nkv);
+  B200RL_CUDA_OK(launch_pdl(kv_reduce_kernel, dim3((unsigned)rows), dim3(128), 0, stream, kv_part, red_start_dev, red_list_dev, (bf16*)dqkv, nq, nkv));
   B200RL_LAUNCH_OK();
   return 0;
 }

@@ -4,6 +4,8 @@
 // Error convention (SURVEY.md §8b "C-ABI the replacement must export"): every entry point
 // returns 0 on success or a negative code; b200rl_last_error() returns a thread-local message.
 #pragma once
+#include <utility>
+#include <string.h>
 #include <cuda.h>          // CUtensorMap types only; the driver symbol is resolved at run time
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -46,6 +48,7 @@ int set_error(int code, const char* fmt, ...);
 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 extern long long g_launch_count;  // kernels launched by this library (bench.py's gpu_launches)
+extern int g_pdl_enabled;         // programmatic dependent launch on the hot-path kernels (b200rl_set_pdl / B200RL_PDL)
 
 typedef __nv_bfloat16 bf16;
 
@@ -250,6 +253,33 @@ __device__ __forceinline__ void swiglu_bwd8(const float* a, const float* b, cons
     og[j] = c[j] * b[j] * sg * (1.f + a[j] * (1.f - sg));
     ou[j] = c[j] * silu;
   }
+}
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// The learner step is ~12k dependent launches on one stream.  Kernels launched through launch_pdl() may start while
+// the previous kernel drains: they run their prologue (barrier init, TMEM allocation, tensor-map prefetch) and then
+// block in pdl_enter() until the previous grid has completed and its writes are visible.  Rules for a kernel:
+// nothing before pdl_enter() may touch global memory that an earlier kernel of the stream writes or reads.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the NEXT kernel may start its prologue
+  asm volatile("griddepcontrol.wait;" ::: "memory");               // the PREVIOUS kernel is complete and flushed
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 }  // namespace b200rl

@@ -12,6 +12,7 @@ namespace b200rl {
 // ------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const int* __restrict__ ids, const bf16* __restrict__ table,
                              bf16* __restrict__ out, int H, int vocab) {
+  pdl_enter();
   const int m = blockIdx.x;
   int id = ids[m];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
@@ -43,6 +44,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __global__ void rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                    bf16* __restrict__ y, float* __restrict__ rstd, int H,
                                    float eps) {
+  pdl_enter();
   __shared__ float red[32];
   const size_t row = blockIdx.x;
   const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + row * H);
@@ -73,6 +75,7 @@ __global__ void rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __res
 __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                    const bf16* __restrict__ w, const float* __restrict__ rstd,
                                    const bf16* __restrict__ dres, bf16* __restrict__ dx, int H) {
+  pdl_enter();
   __shared__ float red[32];
   const size_t row = blockIdx.x;
   const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + row * H);
@@ -131,6 +134,7 @@ __global__ void rope_table_kernel(float* __restrict__ cs, int L, int half, float
 __global__ void rope_kernel(bf16* __restrict__ qkv, const float* __restrict__ cs, int L,
                             long long row_stride, int n_rot_heads, int D, float sign,
                             const int* __restrict__ pos_idx) {
+  pdl_enter();
   const size_t m = blockIdx.x;
   const int pos = pos_idx ? pos_idx[m] : (int)(m % L);  // packed layout carries explicit positions
   const int half = D / 2;
@@ -161,6 +165,7 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, const float* __restrict__ cs
 // SwiGLU on a fused [M, 2I] gate|up buffer
 // ------------------------------------------------------------------------------------------
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int I) {
+  pdl_enter();
   const size_t row = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= I / 8) return;
@@ -176,6 +181,7 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
 // dgu[:, :I] = dact * up * silu'(gate) ; dgu[:, I:] = dact * silu(gate)
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dact,
                                   bf16* __restrict__ dgu, int I) {
+  pdl_enter();
   const size_t row = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= I / 8) return;
@@ -194,6 +200,7 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __res
 // select rows: out[b*T + t, :] = x[b*L + start + t, :]   (completion positions P-1 .. L-2)
 __global__ void gather_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int L,
                                    int T, int start) {
+  pdl_enter();
   const int r = blockIdx.x;
   const int b = r / T, t = r % T;
   const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)b * L + start + t) * H);
@@ -203,6 +210,7 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ x, bf16* __restrict_
 // packed layout: out[r, :] = x[src[r], :]
 __global__ void gather_rows_idx_kernel(const bf16* __restrict__ x, const int* __restrict__ src,
                                        bf16* __restrict__ out, int H) {
+  pdl_enter();
   const int r = blockIdx.x;
   const uint4* s4 = reinterpret_cast<const uint4*>(x + (size_t)src[r] * H);
   uint4* d4 = reinterpret_cast<uint4*>(out + (size_t)r * H);
@@ -212,6 +220,7 @@ __global__ void gather_rows_idx_kernel(const bf16* __restrict__ x, const int* __
 // rows without a scored position get zeros.  The shared last prompt row collects one term per completion.
 __global__ void scatter_add_rows_kernel(const bf16* __restrict__ d, const int* __restrict__ start,
                                         const int* __restrict__ list, bf16* __restrict__ dx, int H) {
+  pdl_enter();
   const int m = blockIdx.x;
   const int s0 = start[m], s1 = start[m + 1];
   bf16x8* dst = reinterpret_cast<bf16x8*>(dx + (size_t)m * H);
@@ -229,6 +238,7 @@ __global__ void scatter_add_rows_kernel(const bf16* __restrict__ d, const int* _
 // scatter back (zero elsewhere): dx[b*L + start + t, :] = d[b*T + t, :], other rows 0
 __global__ void scatter_rows_kernel(const bf16* __restrict__ d, bf16* __restrict__ dx, int H, int L,
                                     int T, int start) {
+  pdl_enter();
   const int m = blockIdx.x;
   const int b = m / L, pos = m % L;
   uint4* dst = reinterpret_cast<uint4*>(dx + (size_t)m * H);
@@ -249,7 +259,7 @@ using namespace b200rl;
 extern "C" int b200rl_embed(const int* ids, const void* table, void* out, int M, int H, int vocab,
                             void* stream) {
   B200RL_REQUIRE(ids && table && out && M > 0 && H % 8 == 0, "embed: bad args (M=%d H=%d)", M, H);
-  embed_kernel<<<M, 128, 0, STREAM>>>(ids, (const bf16*)table, (bf16*)out, H, vocab);
+  B200RL_CUDA_OK(launch_pdl(embed_kernel, dim3(M), dim3(128), 0, STREAM, ids, (const bf16*)table, (bf16*)out, H, vocab));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -257,7 +267,7 @@ extern "C" int b200rl_embed(const int* ids, const void* table, void* out, int M,
 extern "C" int b200rl_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int H,
                                   float eps, void* stream) {
   B200RL_REQUIRE(x && w && y && M > 0 && H % 8 == 0, "rmsnorm_fwd: bad args (M=%d H=%d)", M, H);
-  rmsnorm_fwd_kernel<<<M, 256, 0, STREAM>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, H, eps);
+  B200RL_CUDA_OK(launch_pdl(rmsnorm_fwd_kernel, dim3(M), dim3(256), 0, STREAM, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, H, eps));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -266,8 +276,8 @@ extern "C" int b200rl_rmsnorm_bwd(const void* dy, const void* x, const void* w, 
                                   const void* dres, void* dx, int M, int H, void* stream) {
   B200RL_REQUIRE(dy && x && w && rstd && dx && M > 0 && H % 8 == 0,
                  "rmsnorm_bwd: bad args (M=%d H=%d)", M, H);
-  rmsnorm_bwd_kernel<<<M, 256, 0, STREAM>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
-                                            (const bf16*)dres, (bf16*)dx, H);
+  B200RL_CUDA_OK(launch_pdl(rmsnorm_bwd_kernel, dim3(M), dim3(256), 0, STREAM, (const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
+                                            (const bf16*)dres, (bf16*)dx, H));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -284,8 +294,8 @@ extern "C" int b200rl_rope(void* qkv, const float* cs, int M, int L, long long r
                            int n_rot_heads, int head_dim, int backward, void* stream) {
   B200RL_REQUIRE(qkv && cs && M > 0 && L > 0 && head_dim % 16 == 0 && row_stride % 8 == 0,
                  "rope: bad args");
-  rope_kernel<<<M, 128, 0, STREAM>>>((bf16*)qkv, cs, L, row_stride, n_rot_heads, head_dim,
-                                     backward ? -1.f : 1.f, nullptr);
+  B200RL_CUDA_OK(launch_pdl(rope_kernel, dim3(M), dim3(128), 0, STREAM, (bf16*)qkv, cs, L, row_stride, n_rot_heads, head_dim,
+                                     backward ? -1.f : 1.f, nullptr));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -293,14 +303,14 @@ extern "C" int b200rl_rope(void* qkv, const float* cs, int M, int L, long long r
 extern "C" int b200rl_rope_pos(void* qkv, const float* cs, const int* pos, int M, long long row_stride,
                                int n_rot_heads, int head_dim, int backward, void* stream) {
   B200RL_REQUIRE(qkv && cs && pos && M > 0 && head_dim % 16 == 0 && row_stride % 8 == 0, "rope_pos: bad args");
-  rope_kernel<<<M, 128, 0, STREAM>>>((bf16*)qkv, cs, 1, row_stride, n_rot_heads, head_dim, backward ? -1.f : 1.f, pos);
+  B200RL_CUDA_OK(launch_pdl(rope_kernel, dim3(M), dim3(128), 0, STREAM, (bf16*)qkv, cs, 1, row_stride, n_rot_heads, head_dim, backward ? -1.f : 1.f, pos));
   B200RL_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int b200rl_gather_rows_idx(const void* x, const int* src, void* out, int R, int H, void* stream) {
   B200RL_REQUIRE(x && src && out && R > 0 && H % 8 == 0, "gather_rows_idx: bad args");
-  gather_rows_idx_kernel<<<R, 128, 0, STREAM>>>((const bf16*)x, src, (bf16*)out, H);
+  B200RL_CUDA_OK(launch_pdl(gather_rows_idx_kernel, dim3(R), dim3(128), 0, STREAM, (const bf16*)x, src, (bf16*)out, H));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -308,7 +318,7 @@ extern "C" int b200rl_gather_rows_idx(const void* x, const int* src, void* out, 
 extern "C" int b200rl_scatter_add_rows(const void* d, const int* start, const int* list, void* dx, int M, int H,
                                        void* stream) {
   B200RL_REQUIRE(d && start && list && dx && M > 0 && H % 8 == 0, "scatter_add_rows: bad args");
-  scatter_add_rows_kernel<<<M, 128, 0, STREAM>>>((const bf16*)d, start, list, (bf16*)dx, H);
+  B200RL_CUDA_OK(launch_pdl(scatter_add_rows_kernel, dim3(M), dim3(128), 0, STREAM, (const bf16*)d, start, list, (bf16*)dx, H));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -316,7 +326,7 @@ extern "C" int b200rl_scatter_add_rows(const void* d, const int* start, const in
 extern "C" int b200rl_swiglu_fwd(const void* gu, void* act, int M, int I, void* stream) {
   B200RL_REQUIRE(gu && act && M > 0 && I % 8 == 0, "swiglu_fwd: bad args");
   dim3 grid((I / 8 + 255) / 256, M);
-  swiglu_fwd_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)gu, (bf16*)act, I);
+  B200RL_CUDA_OK(launch_pdl(swiglu_fwd_kernel, dim3(grid), dim3(256), 0, STREAM, (const bf16*)gu, (bf16*)act, I));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -325,7 +335,7 @@ extern "C" int b200rl_swiglu_bwd(const void* gu, const void* dact, void* dgu, in
                                  void* stream) {
   B200RL_REQUIRE(gu && dact && dgu && M > 0 && I % 8 == 0, "swiglu_bwd: bad args");
   dim3 grid((I / 8 + 255) / 256, M);
-  swiglu_bwd_kernel<<<grid, 256, 0, STREAM>>>((const bf16*)gu, (const bf16*)dact, (bf16*)dgu, I);
+  B200RL_CUDA_OK(launch_pdl(swiglu_bwd_kernel, dim3(grid), dim3(256), 0, STREAM, (const bf16*)gu, (const bf16*)dact, (bf16*)dgu, I));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -334,7 +344,7 @@ extern "C" int b200rl_gather_rows(const void* x, void* out, int B, int L, int T,
                                   void* stream) {
   B200RL_REQUIRE(x && out && B > 0 && T > 0 && start >= 0 && start + T <= L && H % 8 == 0,
                  "gather_rows: bad args");
-  gather_rows_kernel<<<B * T, 128, 0, STREAM>>>((const bf16*)x, (bf16*)out, H, L, T, start);
+  B200RL_CUDA_OK(launch_pdl(gather_rows_kernel, dim3(B * T), dim3(128), 0, STREAM, (const bf16*)x, (bf16*)out, H, L, T, start));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -343,7 +353,7 @@ extern "C" int b200rl_scatter_rows(const void* d, void* dx, int B, int L, int T,
                                    void* stream) {
   B200RL_REQUIRE(d && dx && B > 0 && T > 0 && start >= 0 && start + T <= L && H % 8 == 0,
                  "scatter_rows: bad args");
-  scatter_rows_kernel<<<B * L, 128, 0, STREAM>>>((const bf16*)d, (bf16*)dx, H, L, T, start);
+  B200RL_CUDA_OK(launch_pdl(scatter_rows_kernel, dim3(B * L), dim3(128), 0, STREAM, (const bf16*)d, (bf16*)dx, H, L, T, start));
   B200RL_LAUNCH_OK();
   return 0;
 }

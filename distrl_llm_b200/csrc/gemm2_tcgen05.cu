@@ -166,6 +166,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_enter();  // prologue done: let the next kernel start its own, then wait for the previous kernel's data
 
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
@@ -516,13 +517,15 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   cfg.blockDim = dim3(128 + 32 * EW);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl_enabled ? 2 : 1;
   B200RL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tA1, tB1, tA2, tB2, p));
   B200RL_LAUNCH_OK();
   return 0;

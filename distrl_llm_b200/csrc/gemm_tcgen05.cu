@@ -76,6 +76,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_enter();
 
   const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
   const int kb_total = p.kb1 + p.kb2;
@@ -245,7 +246,7 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
   int ctas = num_sms();
   if (a.max_ctas > 0 && a.max_ctas < ctas) ctas = a.max_ctas;
   if (tiles < ctas) ctas = tiles;
-  kern<<<ctas, 256, C::SMEM_BYTES, stream>>>(tA1, tB1, tA2, tB2, p);
+  B200RL_CUDA_OK(launch_pdl(kern, dim3(ctas), dim3(256), C::SMEM_BYTES, stream, tA1, tB1, tA2, tB2, p));
   B200RL_LAUNCH_OK();
   return 0;
 }

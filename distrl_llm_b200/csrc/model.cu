@@ -17,6 +17,7 @@
 //   Acat [K2, Kin] (A_j stacked, zero padded to K2 = roundup(nproj*r, 64)),  Bcat [Nout, K2]
 //   (block diagonal).  Backward GEMMs read W / Acat / Bcat as stored through MN-major UMMA descriptors
 //   (no transposed copies, no transposed dequant).
+#include <stdlib.h>
 #include "common.cuh"
 #include "b200rl.h"
 #include <vector>
@@ -105,6 +106,7 @@ struct AccumArgs {
 };
 
 __global__ void grad_accum_kernel(float* __restrict__ flat, const AccumArgs a) {
+  pdl_enter();
   const AccumBlock d = a.blk[blockIdx.y];
   const long long n = (long long)d.rows * d.cols;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
@@ -121,6 +123,7 @@ __global__ void grad_accum_kernel(float* __restrict__ flat, const AccumArgs a) {
 // out[i] = bf16(sum_s slabs[s][i])  (fixed order; alpha was applied per slab by the GEMM epilogue)
 __global__ void reduce_slabs_bf16_kernel(const float* __restrict__ slabs, long long slab_stride, int splits,
                                          bf16* __restrict__ out, long long n8) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -135,6 +138,7 @@ __global__ void reduce_slabs_bf16_kernel(const float* __restrict__ slabs, long l
 
 __global__ void targets_kernel(const int* __restrict__ ids, int* __restrict__ targets, int L, int P,
                                int T, int n) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int b = i / T, t = i % T;
@@ -185,7 +189,7 @@ struct b200rl_model {
   int rope_L;
   // optional resident bf16 copy of the dequantised base weights (b200rl_model_set_weight_cache): 15 GB for a 7B
   // model, 8 % of a B200's HBM, and it removes 2 x n_layers x 4 dequant passes per micro-batch
-  bool fuse_swiglu = true;  // b200rl_model_set_fusion
+  bool fuse_swiglu = !(getenv("B200RL_FUSE_SWIGLU") && getenv("B200RL_FUSE_SWIGLU")[0] == '0');  // b200rl_model_set_fusion
   bf16* wcache = nullptr;
   long long wcache_per_layer = 0;
   std::vector<uint8_t> wcache_valid;  // [n_layers*4]
@@ -565,7 +569,7 @@ int gemm_l(b200rl_model* m, int cat, int layout, cudaStream_t st, const bf16* A1
       int rc = gemm_dispatch(a, st);
       if (rc) return rc;
       const long long n8 = stride / 8;
-      reduce_slabs_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(m->slabs, stride, splits, C, n8);
+      B200RL_CUDA_OK(launch_pdl(reduce_slabs_bf16_kernel, dim3((unsigned)((n8 + 255) / 256)), dim3(256), 0, st, m->slabs, stride, splits, C, n8));
       B200RL_LAUNCH_OK();
       return 0;
     }
@@ -618,7 +622,7 @@ int lora_dw(b200rl_model* m, cudaStream_t st, const Group& g, const bf16* dY, lo
     int bx = (max_elems + 255) / 256;
     if (bx > 128) bx = 128;
     dim3 grid(bx, g.nproj);
-    grad_accum_kernel<<<grid, 256, 0, st>>>(m->lora_grad, acc);
+    B200RL_CUDA_OK(launch_pdl(grad_accum_kernel, dim3(grid), dim3(256), 0, st, m->lora_grad, acc));
     B200RL_LAUNCH_OK();
   }
   return 0;
@@ -745,7 +749,7 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
   PM(CAT_MISC, 0);
   const int* targets = pb ? pb->targets : m->targets;
   if (!pb) {
-    targets_kernel<<<(R + 255) / 256, 256, 0, st>>>(ids, m->targets, L, P, T, R);
+    B200RL_CUDA_OK(launch_pdl(targets_kernel, dim3((R + 255) / 256), dim3(256), 0, st, ids, m->targets, L, P, T, R));
     B200RL_LAUNCH_OK();
   }
   PM(CAT_MISC, 0);

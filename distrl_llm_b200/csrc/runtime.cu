@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // Library runtime: thread-local error string, device attribute cache, version.
 #include "common.cuh"
 #include <stdarg.h>
@@ -7,6 +8,11 @@ namespace b200rl {
 
 static thread_local char g_last_error[1024] = "";
 long long g_launch_count = 0;
+static int pdl_default() {
+  const char* e = getenv("B200RL_PDL");
+  return (e && e[0] == '0') ? 0 : 1;
+}
+int g_pdl_enabled = pdl_default();
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -47,5 +53,11 @@ extern "C" int b200rl_check_device(void) {
     return b200rl::set_error(b200rl::B200RL_ERR_UNSUPPORTED,
                              "libb200rl is built for sm_100a only; device %d is sm_%d%d", dev, major,
                              minor);
+  return 0;
+}
+
+// 1 (default; env B200RL_PDL=0 disables): hot-path kernels use programmatic dependent launch (common.cuh)
+extern "C" int b200rl_set_pdl(int enable) {
+  b200rl::g_pdl_enabled = enable ? 1 : 0;
   return 0;
 }

@@ -248,6 +248,9 @@ int b200rl_model_microbatch_packed(b200rl_model* m, const b200rl_packed_batch* p
 int b200rl_model_profile(b200rl_model* m, int enable);
 int b200rl_model_profile_read(b200rl_model* m, double* ms, double* work, long long* count);
 long long b200rl_launch_count(void); /* kernels launched by the library so far */
+/* 1 (default; env B200RL_PDL=0): hot-path kernels are launched with programmatic dependent launch, so that each
+ * kernel's prologue overlaps the previous kernel's tail (csrc/common.cuh). Results are unaffected. */
+int b200rl_set_pdl(int enable);
 
 #ifdef __cplusplus
 }
