@@ -50,6 +50,10 @@ struct GemmArgs {
 };
 int gemm_dispatch(const GemmArgs& a, cudaStream_t stream);
 bool gemm_fuse_supported(int M, int I);
+int dw_grouped_splits(int total_m_blocks, int kb_total);
+int dw_grouped_dispatch(int nprob, const void* const* Y, const long long* ldy, const int* rows, const void* const* U,
+                        const long long* ldu, float* const* C, const long long* split_stride, int tokens, int splits,
+                        cudaStream_t stream);
 
 }  // namespace b200rl
 
@@ -104,6 +108,18 @@ struct AccumArgs {
   int splits;
   int ld;
 };
+// grouped variant: every block names its own slab set (one launch for all dA / dB blocks of a layer)
+struct AccumBlockG {
+  AccumBlock b;
+  const float* slabs;
+  long long slab_stride;
+};
+struct AccumArgsG {
+  AccumBlockG blk[16];
+  int nblk;
+  int splits;
+  int ld;
+};
 
 __global__ void grad_accum_kernel(float* __restrict__ flat, const AccumArgs a) {
   pdl_enter();
@@ -116,6 +132,23 @@ __global__ void grad_accum_kernel(float* __restrict__ flat, const AccumArgs a) {
                                     : (long long)(d.row_off + i) * a.ld + d.col_off + j;
     float acc = 0.f;
     for (int s = 0; s < a.splits; ++s) acc += a.slabs[(long long)s * a.slab_stride + o];  // fixed order
+    flat[d.dst_off + idx] += acc;
+  }
+}
+
+__global__ void grad_accum_grouped_kernel(float* __restrict__ flat, const AccumArgsG a) {
+  pdl_enter();
+  const AccumBlock d = a.blk[blockIdx.y].b;
+  const float* __restrict__ slabs = a.blk[blockIdx.y].slabs;
+  const long long stride = a.blk[blockIdx.y].slab_stride;
+  const long long n = (long long)d.rows * d.cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / d.cols), j = (int)(idx % d.cols);
+    const long long o = d.transpose ? (long long)(d.row_off + j) * a.ld + d.col_off + i
+                                    : (long long)(d.row_off + i) * a.ld + d.col_off + j;
+    float acc = 0.f;
+    for (int s = 0; s < a.splits; ++s) acc += slabs[(long long)s * stride + o];  // fixed order
     flat[d.dst_off + idx] += acc;
   }
 }
@@ -181,7 +214,10 @@ struct b200rl_model {
     float *rstd1, *rstd2, *lse;
   };
   std::vector<LayerAct> act;
-  bf16 *wbuf, *xsel, *hsel, *logits, *dhsel, *dx, *dh, *dact, *dgu, *dattn, *dqkv, *du;
+  bf16 *wbuf, *xsel, *hsel, *logits, *dhsel, *dx, *dx2, *dh, *dact, *dgu, *dattn, *dqkv, *du;  // du: 4 x [Mt][K2max]
+  float* gslabs;            // grouped dW slabs
+  long long gslab_elems;
+  bool grouped_dw = !(getenv("B200RL_GROUPED_DW") && getenv("B200RL_GROUPED_DW")[0] == '0');
   float *rstd_f, *lp, *coef, *klw, *delta, *slabs, *rope_cs, *kvpart;
   long long kvpart_rows;
   int *targets, *lens;
@@ -277,10 +313,10 @@ static int dw_splits(int tokens, int Ny, int bn_cols) {
 struct WsPlan {
   long long total;
   long long off_arena, off_pack, off_X, off_wbuf, off_xsel, off_hsel, off_logits, off_dhsel, off_dx,
-      off_dh, off_dact, off_dgu, off_dattn, off_dqkv, off_du, off_rstd_f, off_lp, off_coef, off_klw, off_delta, off_kvpart,
+      off_dh, off_dx2, off_gslabs, off_dact, off_dgu, off_dattn, off_dqkv, off_du, off_rstd_f, off_lp, off_coef, off_klw, off_delta, off_kvpart,
       off_slabs, off_rope, off_targets, off_lens, off_layers;
   long long per_layer;
-  long long slab_elems;
+  long long slab_elems, gslab_elems;
 };
 
 static WsPlan plan_ws(const b200rl_model* m) {
@@ -306,11 +342,15 @@ static WsPlan plan_ws(const b200rl_model* m) {
   p.off_dhsel = take(R * H * 2);
   p.off_dx = take(Mt * H * 2);
   p.off_dh = take(Mt * H * 2);
+  p.off_dx2 = take(Mt * H * 2);
+  // grouped dW: <= 4 K-ranges of [rows, 64] fp32 for the 8 problems of a layer (dB rows = out dims, dA rows = in dims)
+  p.gslab_elems = 4 * (QKV + H + 2 * I + H + H + QD + H + I) * 64;
+  p.off_gslabs = take(p.gslab_elems * 4);
   p.off_dact = take(Mt * I * 2);
   p.off_dgu = take(Mt * 2 * I * 2);
   p.off_dattn = take(Mt * QD * 2);
   p.off_dqkv = take(Mt * QKV * 2);
-  p.off_du = take(Mt * m->K2max * 2);
+  p.off_du = take(4 * Mt * m->K2max * 2);
   p.off_rstd_f = take(R * 4);
   p.off_lp = take(R * 4);
   p.off_coef = take(R * 4);
@@ -410,6 +450,9 @@ extern "C" int b200rl_model_create(const b200rl_model_config* cfg, const b200rl_
   m->pack_descs = w + p.off_pack;
   m->X = (bf16*)(w + p.off_X);
   m->wbuf = (bf16*)(w + p.off_wbuf);
+  m->dx2 = (bf16*)(w + p.off_dx2);
+  m->gslabs = (float*)(w + p.off_gslabs);
+  m->gslab_elems = p.gslab_elems;
   m->xsel = (bf16*)(w + p.off_xsel);
   m->hsel = (bf16*)(w + p.off_hsel);
   m->logits = (bf16*)(w + p.off_logits);
@@ -628,6 +671,67 @@ int lora_dw(b200rl_model* m, cudaStream_t st, const Group& g, const bf16* dY, lo
   return 0;
 }
 
+// Grouped form of lora_dw for one layer (all K2 == 64): problems 2g = dBcat_g = dY_g^T . u_g, 2g+1 = dAcat_g^T = x_g^T . du_g.
+int lora_dw_grouped(b200rl_model* m, cudaStream_t st, const Group* const* gs, const bf16* const* dYs, const long long* ldYs,
+                    const bf16* const* us, const bf16* const* xs, const long long* ldXs, const bf16* const* dus, int M) {
+  const void* Y[8];
+  const void* U[8];
+  long long ldy[8], ldu[8], stride[8];
+  int rows[8];
+  float* C[8];
+  int total_blocks = 0;
+  double flops = 0;
+  for (int g = 0; g < 4; ++g) {
+    Y[2 * g] = dYs[g]; ldy[2 * g] = ldYs[g]; rows[2 * g] = gs[g]->Nout; U[2 * g] = us[g]; ldu[2 * g] = 64;
+    Y[2 * g + 1] = xs[g]; ldy[2 * g + 1] = ldXs[g]; rows[2 * g + 1] = gs[g]->Kin; U[2 * g + 1] = dus[g]; ldu[2 * g + 1] = 64;
+    total_blocks += (gs[g]->Nout + 127) / 128 + (gs[g]->Kin + 127) / 128;
+    flops += 2.0 * M * (gs[g]->Nout + gs[g]->Kin) * m->cfg.lora_r * gs[g]->nproj;
+  }
+  const int splits = dw_grouped_splits(total_blocks, (M + 63) / 64);
+  long long off = 0;
+  for (int i = 0; i < 8; ++i) {
+    stride[i] = (long long)rows[i] * 64;
+    C[i] = m->gslabs + off;
+    off += stride[i] * splits;
+  }
+  if (off > m->gslab_elems) return set_error(B200RL_ERR_STATE, "lora_dw_grouped: slab scratch too small (%lld > %lld)", off, m->gslab_elems);
+  PM(CAT_GEMM_DW, flops);
+  const int used = dw_grouped_dispatch(8, Y, ldy, rows, U, ldu, C, stride, M, splits, st);
+  if (used <= 0) return used < 0 ? used : set_error(B200RL_ERR_STATE, "lora_dw_grouped: dispatch returned 0");
+  PM(CAT_MISC, 0);
+  AccumArgsG acc;
+  memset(&acc, 0, sizeof(acc));
+  acc.splits = used;
+  acc.ld = 64;
+  const int r = m->cfg.lora_r;
+  int nb = 0, max_elems = 0;
+  for (int g = 0; g < 4; ++g) {
+    const Group& G = *gs[g];
+    int row_off = 0;
+    for (int j = 0; j < G.nproj; ++j) {
+      AccumBlockG& b = acc.blk[nb++];   // dB_j [out_j, r] = slab[row_off + i][j*r + jj]
+      b.slabs = C[2 * g]; b.slab_stride = stride[2 * g];
+      b.b.dst_off = G.b_off[j]; b.b.rows = G.out_dims[j]; b.b.cols = r;
+      b.b.row_off = row_off; b.b.col_off = j * r; b.b.transpose = 0;
+      max_elems = std::max(max_elems, b.b.rows * b.b.cols);
+      row_off += G.out_dims[j];
+    }
+    for (int j = 0; j < G.nproj; ++j) {
+      AccumBlockG& b = acc.blk[nb++];   // dA_j [r, Kin]: dA_j[i][k] = slab[k][j*r + i]
+      b.slabs = C[2 * g + 1]; b.slab_stride = stride[2 * g + 1];
+      b.b.dst_off = G.a_off[j]; b.b.rows = r; b.b.cols = G.Kin;
+      b.b.row_off = 0; b.b.col_off = j * r; b.b.transpose = 1;
+      max_elems = std::max(max_elems, b.b.rows * b.b.cols);
+    }
+  }
+  acc.nblk = nb;
+  int bx = (max_elems + 255) / 256;
+  if (bx > 64) bx = 64;
+  B200RL_CUDA_OK(launch_pdl(grad_accum_grouped_kernel, dim3(bx, nb), dim3(256), 0, st, m->lora_grad, acc));
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace
 
 namespace {
@@ -783,30 +887,37 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     const Group& gd = m->groups[l * 4 + 3];
     bf16* x = m->X + (long long)l * Mt * H;
     // Backward GEMMs read W (and the LoRA operands) exactly as stored: B operand MN-major (layout 2).
+    // Every group keeps its own du; dx / dx2 alternate as the residual-stream gradient so that all (dY, u, x, du) of
+    // the layer are still alive when the grouped dW launch runs (before the layer's last rmsnorm_bwd overwrites dx).
+    const bool grouped = m->grouped_dw && gq.K2 == 64 && go.K2 == 64 && gg.K2 == 64 && gd.K2 == 64;
+    bf16* du_d = m->du;
+    bf16* du_g = m->du + 1 * Mt * m->K2max;
+    bf16* du_o = m->du + 2 * Mt * m->K2max;
+    bf16* du_q = m->du + 3 * Mt * m->K2max;
     // ---- down projection:  X[l+1] = x_mid + act.Wd^T + u_d.Bd^T
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + gd.bcat, gd.K2, H, nullptr, 0, nullptr, 0, 0, m->du, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
-    RC(lora_dw(m, st, gd, m->dx, H, a.u_d, a.act, I, m->du, M));
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + gd.bcat, gd.K2, H, nullptr, 0, nullptr, 0, 0, du_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    if (!grouped) RC(lora_dw(m, st, gd, m->dx, H, a.u_d, a.act, I, du_d, M));
     RC(base_weight(m, st, l, 3, &Wd));
     if (fuse_swiglu) {  // dact never reaches HBM: the epilogue turns it into dgate|dup
-      RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, m->du, gd.K2, ar + gd.acat, I, gd.K2, m->dgu, 2 * I, nullptr, nullptr, 0, 1.f, M, I,
+      RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, du_d, gd.K2, ar + gd.acat, I, gd.K2, m->dgu, 2 * I, nullptr, nullptr, 0, 1.f, M, I,
                  2, a.gu, 2 * I));
     } else {
-      RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, m->du, gd.K2, ar + gd.acat, I, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
+      RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, du_d, gd.K2, ar + gd.acat, I, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
       PM(CAT_ROW, 5.0 * M * I * 2);
       RC(b200rl_swiglu_bwd(a.gu, m->dact, m->dgu, M, I, stream));
     }
     // ---- gate|up:  gu = h2.Wgu^T + u_gu.Bgu^T
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dgu, 2 * I, ar + gg.bcat, gg.K2, 2 * I, nullptr, 0, nullptr, 0, 0, m->du, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
-    RC(lora_dw(m, st, gg, m->dgu, 2 * I, a.u_gu, a.h2, H, m->du, M));
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dgu, 2 * I, ar + gg.bcat, gg.K2, 2 * I, nullptr, 0, nullptr, 0, 0, du_g, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    if (!grouped) RC(lora_dw(m, st, gg, m->dgu, 2 * I, a.u_gu, a.h2, H, du_g, M));
     RC(base_weight(m, st, l, 2, &Wd));
-    RC(gemm_l(m, CAT_GEMM, 2, st, m->dgu, 2 * I, Wd, H, 2 * I, m->du, gg.K2, ar + gg.acat, H, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+    RC(gemm_l(m, CAT_GEMM, 2, st, m->dgu, 2 * I, Wd, H, 2 * I, du_g, gg.K2, ar + gg.acat, H, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
     PM(CAT_ROW, 4.0 * M * H * 2);
-    RC(b200rl_rmsnorm_bwd(m->dh, a.x_mid, w.ln2_w, a.rstd2, m->dx, m->dx, M, H, stream));
+    RC(b200rl_rmsnorm_bwd(m->dh, a.x_mid, w.ln2_w, a.rstd2, m->dx, m->dx2, M, H, stream));
     // ---- o projection:  x_mid = x + attn_o.Wo^T + u_o.Bo^T
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + go.bcat, go.K2, H, nullptr, 0, nullptr, 0, 0, m->du, go.K2, nullptr, nullptr, 0, s, M, go.K2));
-    RC(lora_dw(m, st, go, m->dx, H, a.u_o, a.attn_o, QD, m->du, M));
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx2, H, ar + go.bcat, go.K2, H, nullptr, 0, nullptr, 0, 0, du_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    if (!grouped) RC(lora_dw(m, st, go, m->dx2, H, a.u_o, a.attn_o, QD, du_o, M));
     RC(base_weight(m, st, l, 1, &Wd));
-    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, QD, H, m->du, go.K2, ar + go.acat, QD, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
+    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx2, H, Wd, QD, H, du_o, go.K2, ar + go.acat, QD, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
     // ---- attention + rope
     PM(CAT_ATTN_BWD, 4.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
     if (pb) RC(b200rl_attn_seg_bwd(a.qkv, attn_mask, a.attn_o, m->dattn, a.lse, m->delta, m->dqkv, m->kvpart, M, c.n_q_heads, c.n_kv_heads, attn_scale,
@@ -816,13 +927,24 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     if (pb) RC(b200rl_rope_pos(m->dqkv, m->rope_cs, pb->pos, M, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 1, stream));
     else RC(b200rl_rope(m->dqkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 1, stream));
     // ---- qkv projection:  qkv = h1.Wqkv^T + u_qkv.Bqkv^T + bias
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dqkv, QKV, ar + gq.bcat, gq.K2, QKV, nullptr, 0, nullptr, 0, 0, m->du, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
-    RC(lora_dw(m, st, gq, m->dqkv, QKV, a.u_qkv, a.h1, H, m->du, M));
+    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dqkv, QKV, ar + gq.bcat, gq.K2, QKV, nullptr, 0, nullptr, 0, 0, du_q, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    if (!grouped) RC(lora_dw(m, st, gq, m->dqkv, QKV, a.u_qkv, a.h1, H, du_q, M));
+    if (grouped) {
+      // all eight dB / dA GEMMs of the layer in one launch, all their blocks accumulated by one more
+      const Group* gs[4] = {&gd, &gg, &go, &gq};
+      const bf16* dYs[4] = {m->dx, m->dgu, m->dx2, m->dqkv};
+      const long long ldYs[4] = {H, 2 * I, H, QKV};
+      const bf16* us[4] = {a.u_d, a.u_gu, a.u_o, a.u_qkv};
+      const bf16* xs[4] = {a.act, a.h2, a.attn_o, a.h1};
+      const long long ldXs[4] = {I, H, QD, H};
+      const bf16* dus[4] = {du_d, du_g, du_o, du_q};
+      RC(lora_dw_grouped(m, st, gs, dYs, ldYs, us, xs, ldXs, dus, M));
+    }
     if (l > 0) {  // embeddings are frozen: layer 0 needs no input gradient
       RC(base_weight(m, st, l, 0, &Wd));
-      RC(gemm_l(m, CAT_GEMM, 2, st, m->dqkv, QKV, Wd, H, QKV, m->du, gq.K2, ar + gq.acat, H, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+      RC(gemm_l(m, CAT_GEMM, 2, st, m->dqkv, QKV, Wd, H, QKV, du_q, gq.K2, ar + gq.acat, H, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
       PM(CAT_ROW, 4.0 * M * H * 2);
-      RC(b200rl_rmsnorm_bwd(m->dh, x, w.ln1_w, a.rstd1, m->dx, m->dx, M, H, stream));
+      RC(b200rl_rmsnorm_bwd(m->dh, x, w.ln1_w, a.rstd1, m->dx2, m->dx, M, H, stream));
     }
   }
   PM(CAT_END, 0);

@@ -52,6 +52,13 @@ int b200rl_gemm_set_tail_split(int enable);
 int b200rl_gemm_swiglu(int mode, const void* A1, long long lda1, const void* B1, long long ldb1, int K1,
                        const void* A2, long long lda2, const void* B2, long long ldb2, int K2,
                        void* C, long long ldc, void* aux, long long ld_aux, int M, int I, void* stream);
+/* G1 grouped dW form (csrc/gemm_dw_grouped.cu): nprob <= 8 independent products C_i = Y_i^T . U_i with the reduction
+ * over `tokens` rows, Y_i [tokens, rows_i] (ld ldy_i, rows_i % 8 == 0), U_i [tokens, 64] (ld ldu_i), all bf16 as stored;
+ * C_i fp32 [splits][rows_i][64] K-range slabs, split_stride_i elements apart (sum them in order).  One persistent
+ * launch.  Returns the number of K-ranges actually written (>= 1), or a negative error code. */
+int b200rl_gemm_dw_grouped(int nprob, const void* const* Y, const long long* ldy, const int* rows,
+                           const void* const* U, const long long* ldu, float* const* C,
+                           const long long* split_stride, int tokens, int splits, void* stream);
 
 /* ---- G2/G3/G5 row kernels (reference: Unsloth RMSNorm / RoPE / SwiGLU inside policy(...)) ---- */
 int b200rl_embed(const int* ids, const void* table, void* out, int M, int H, int vocab, void* stream);

@@ -137,6 +137,31 @@ def test_gemm_swiglu_fused_is_bit_identical(cuda, M, I, H):
         lib.b200rl_gemm_set_tail_split(1)
 
 
+@pytest.mark.parametrize("tokens,splits", [(4446, 2), (700, 1), (1000, 4)])
+def test_gemm_dw_grouped(cuda, tokens, splits):
+    """All dB / dA products of a layer in one persistent launch (gemm_dw_grouped.cu) vs torch fp32."""
+    import ctypes as C
+    from distrl_llm_b200 import _capi
+    rows = [3584, 18944, 1024, 256, 4608, 512, 72, 136]
+    Y = [_rand((tokens, r), cuda, seed=10 + i) for i, r in enumerate(rows)]
+    U = [_rand((tokens, 64), cuda, seed=30 + i) for i in range(len(rows))]
+    out = [torch.full((splits, r, 64), float("nan"), device=cuda, dtype=torch.float32) for r in rows]
+    n = len(rows)
+    arr_p = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    arr_ll = lambda xs: (C.c_longlong * n)(*xs)
+    yp, up, cp = arr_p(Y), arr_p(U), arr_p(out)
+    ldy, ldu, strides = arr_ll(rows), arr_ll([64] * n), arr_ll([r * 64 for r in rows])
+    rws = (C.c_int * n)(*rows)
+    used = _capi.lib().b200rl_gemm_dw_grouped(n, yp, ldy, rws, up, ldu, cp, strides, tokens, splits, _capi.stream())
+    assert used >= 1, _capi.lib().b200rl_last_error()
+    torch.cuda.synchronize()
+    for y, u, o in zip(Y, U, out):
+        ref = y.float().T @ u.float()
+        got = o[:used].sum(0)
+        assert torch.isfinite(got).all()
+        assert _rel_err(got, ref) < 2e-5
+
+
 def test_gemm_epilogues(cuda, gemm_mode):
     from distrl_llm_b200 import ops
     M, N, K = 384, 320, 256

@@ -281,3 +281,25 @@ def test_swiglu_fusion_is_bit_identical(cuda):
         out.append((pol.lora_grad.clone(), float(pol.loss_accum.item())))
     assert out[0][0].abs().max() > 0
     assert torch.equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+
+
+def test_grouped_dw_matches_per_group_path(cuda, monkeypatch):
+    """One grouped dW launch per layer (default) vs eight separate dW GEMMs: same K-ranges are NOT guaranteed, so the
+    comparison is numerical (fp32 slabs summed in a different split): rel-L2 < 1e-5 on the flat gradient."""
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer
+    from distrl_llm_b200.policy import Policy
+    ocfg = lo.OracleConfig(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=64,
+                           lora_r=16, lora_alpha=16)
+    params, nf4 = lo.make_params(ocfg, seed=2)
+    P, T, B = 12, 36, 4
+    prompts, answers, rewards = lo.make_batch(ocfg, 8, P, T, seed=4, ragged=True, group_size=4, learner="grpo")
+    out = []
+    for env in ("1", "0"):
+        monkeypatch.setenv("B200RL_GROUPED_DW", env)   # read at model creation
+        pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, cuda, max_batch=B, P=P, T=T)
+        ln = GRPOLearner(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5})
+        ln._compute_gradients(prompts, answers, list(rewards), export=False)
+        out.append(pol.lora_grad.clone())
+    assert out[1].abs().max() > 0
+    rel = ((out[0] - out[1]).norm() / out[1].norm()).item()
+    assert rel < 1e-5, rel
