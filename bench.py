@@ -209,6 +209,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in this image) goes away
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     w = workload(args)
     cfg = LMConfig.qwen25_7b(lora_r=args.lora_rank)
@@ -332,10 +335,15 @@ def main():
     gemm = prof["gemm"]
     ach_tf = gemm["work"] / (gemm["ms"] / 1e3) / 1e12 if gemm["ms"] > 0 else 0.0
     step_flops = flops_per_sequence(P, T, args.lora_rank) * N * (args.layers / 28.0 if args.layers != 28 else 1.0)
-    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,TN> (tcgen05, base+LoRA mainloop)",
+    traffic = None
+    try:  # dram__bytes_read + dram__bytes_write per GEMM launch from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")))["per_launch_traffic_bytes"]
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "gemm_pair_kernel<256> (tcgen05 cta_group::2, base+LoRA mainloop)",
                 "achieved": round(ach_tf, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach_tf / peak_tf, 4),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
-                "traffic": None,
+                "traffic": traffic, "traffic_unit": "bytes per GEMM launch (ncu dram read+write, profiles/r1_gemm_dram_traffic.json)",
                 "gemm_share_of_step": round(gemm["ms"] / max(sum(p["ms"] for p in prof.values()), 1e-9), 4),
                 "avg_launch_ms": round(gemm["ms"] / max(gemm["launches"], 1), 4),
                 "flops_per_launch": gemm["work"] / max(gemm["launches"], 1),

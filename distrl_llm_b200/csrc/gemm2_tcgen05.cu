@@ -181,7 +181,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
       int tile, kb_begin, kb_end, part, sidx, m_blk, n_blk;
       unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
-      tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+      tile_coords(tile, p.num_m_blocks, p.num_n_blocks, p.gm, m_blk, n_blk);
       const int row0 = m_blk * BM2 + (int)rank * BM;
       // FUSE 1: CTA 0 stages 128 gate rows of the weight, CTA 1 the 128 up rows with the same index
       const int col0 = FUSE == 1 ? n_blk * C::BH + (int)rank * p.fuse_I : n_blk * BN + (int)rank * C::BH;
@@ -254,7 +254,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++local) {
       int tile, kb_begin, kb_end, part, sidx, m_blk, n_blk;
       unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
-      tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+      tile_coords(tile, p.num_m_blocks, p.num_n_blocks, p.gm, m_blk, n_blk);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -467,6 +467,7 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   p.residual = reinterpret_cast<const bf16*>(a.residual);
   p.ldr = a.ldr;
   p.alpha = a.alpha;
+  p.gm = raster_group((long long)a.M * (a.K1 + a.K2) * 2, p.num_m_blocks);
   if (FUSE) {
     p.fuse_I = FUSE == 1 ? a.N / 2 : a.N;
     p.aux_in = reinterpret_cast<const bf16*>(a.aux);

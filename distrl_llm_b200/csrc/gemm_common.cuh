@@ -2,6 +2,7 @@
 // kernel parameters, UMMA descriptors, tensor-map construction, host argument block.
 #pragma once
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b200rl {
 
@@ -30,6 +31,7 @@ struct GemmParams {
   float* tail_ws = nullptr;
   int* tail_flags = nullptr;
   int tail_epoch = 0;
+  int gm = 8;  // m-blocks per rasterisation group (tile_coords); host: raster_group()
   // CTA-pair kernel only: fused SwiGLU epilogues (GemmArgs::fuse)
   const bf16* aux_in = nullptr;
   bf16* aux_out = nullptr;
@@ -63,8 +65,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 // Tile rasterisation: groups of GM m-blocks sweep all n-blocks before the next group, so the ~74-148 tiles in
 // flight form a compact (GM x ~9..18) patch of C and share both A and B tiles through L2 (ncu on the m-fastest
 // order: 3.2-4.4x DRAM read amplification on the MLP GEMMs, A = 261 MB does not fit the 126 MB L2).
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
-  constexpr int GM = 8;
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int GM, int& m_blk, int& n_blk) {
   const int per_group = GM * num_n;
   const int group = tile / per_group;
   const int first_m = group * GM;
@@ -184,6 +185,20 @@ bool gemm_fuse_supported(int M, int I);
 // K-split factor of the last partial wave of the CTA-pair kernel (1 = none): only when that wave is at most half full
 // and every K-range keeps >= 64 k-blocks -- measured on B200 (profiles/r1_run19*): with K = 3584 the spill / flag /
 // reload chain (~15 us) costs more than the quarter wave it saves, with K >= 18944 it saves 7-13 % of the GEMM.
+// Rasterisation group height.  The tiles in flight sweep n inside a group of gm m-blocks: B panels are shared by gm
+// tiles through L2, A panels are re-read once per n step.  If the whole A operand fits in L2 next to the streams
+// (ncu, packed config 2: the gate|up GEMM read B 3x from DRAM with gm = 8 because 18 m-blocks = 3 groups), one group
+// over all m-blocks streams B exactly once.  Otherwise a square-ish 8 x ~9 patch minimises (gm + gn) panels per wave.
+inline int raster_group(long long a_bytes, int num_m_blocks) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("B200RL_GEMM_GM");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0) return forced;
+  return a_bytes <= (48ll << 20) ? (num_m_blocks > 0 ? num_m_blocks : 1) : 8;
+}
+
 inline int pair_tail_split(long long tiles, int clusters, int kb_total) {
   const long long rem = tiles % clusters;
   if (tiles <= clusters || rem == 0 || rem * 2 > clusters || rem > 128) return 1;

@@ -89,7 +89,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       const int mn = p.num_m_blocks * p.num_n_blocks;
       const int split = tile / mn;
       int m_blk, n_blk;
-      tile_coords(tile - split * mn, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+      tile_coords(tile - split * mn, p.num_m_blocks, p.num_n_blocks, p.gm, m_blk, n_blk);
       const int kb_begin = split * p.kb_per_split;
       const int kb_end = min(kb_begin + p.kb_per_split, kb_total);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -170,7 +170,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       const int mn = p.num_m_blocks * p.num_n_blocks;
       const int split = tile / mn;
       int m_blk, n_blk;
-      tile_coords(tile - split * mn, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+      tile_coords(tile - split * mn, p.num_m_blocks, p.num_n_blocks, p.gm, m_blk, n_blk);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -222,6 +222,7 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
   p.residual = reinterpret_cast<const bf16*>(a.residual);
   p.ldr = a.ldr;
   p.alpha = a.alpha;
+  p.gm = raster_group((long long)a.M * (a.K1 + a.K2) * 2, p.num_m_blocks);
 
   CUtensorMap tA1, tB1, tA2, tB2;
   int rc;
