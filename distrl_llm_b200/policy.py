@@ -51,6 +51,22 @@ class LMConfig:
                 "gate": (H, I), "up": (H, I), "down": (I, H)}
 
     @staticmethod
+    def from_hf_config(hf, lora_r=16, lora_alpha=16.0):
+        """From a transformers Qwen2Config-like object or dict (config.json of the checkpoint the reference loads,
+        distributed_actor.py:58-66)."""
+        g = (lambda k, d=None: hf.get(k, d)) if isinstance(hf, dict) else (lambda k, d=None: getattr(hf, k, d))
+        nq = g("num_attention_heads")
+        hd = g("head_dim") or g("hidden_size") // nq
+        theta = g("rope_theta")
+        if theta is None and g("rope_parameters"):
+            rp = g("rope_parameters")
+            theta = rp.get("rope_theta") if isinstance(rp, dict) else getattr(rp, "rope_theta", None)
+        return LMConfig(vocab=g("vocab_size"), hidden=g("hidden_size"), inter=g("intermediate_size"),
+                        n_layers=g("num_hidden_layers"), n_q_heads=nq, n_kv_heads=g("num_key_value_heads") or nq,
+                        head_dim=hd, lora_r=lora_r, lora_alpha=lora_alpha, rms_eps=g("rms_norm_eps", 1e-6),
+                        rope_theta=float(theta or 1e6))
+
+    @staticmethod
     def qwen25_7b(lora_r=16, lora_alpha=16.0):
         return LMConfig(vocab=152064, hidden=3584, inter=18944, n_layers=28, n_q_heads=28, n_kv_heads=4,
                         head_dim=128, lora_r=lora_r, lora_alpha=lora_alpha)
@@ -234,6 +250,79 @@ class Policy:
             self.lora_flat[off:off + t.numel()] = t.to(dev)
         self._finish()
         return self
+
+    @classmethod
+    def from_hf_state_dict(cls, cfg: LMConfig, sd: dict, device, max_batch, P, T, lora_seed=0, lora_state=None, **kw):
+        """Build from a Hugging Face Qwen2-family state dict (`model.layers.{i}.self_attn.q_proj.weight`, ...), dense
+        bf16/fp16/fp32 tensors.  The seven linear weights of every layer are NF4-quantised ON THE GPU at load time
+        (blocksize 64, fp32 absmax) -- what `load_in_4bit=True` does in the reference (distributed_actor.py:58-66) -- and
+        fused row-wise into qkv / gate|up.  LoRA: PEFT's default init (A kaiming-uniform(a=sqrt 5) = U(+-1/sqrt(in)),
+        B = 0) from `lora_seed`, or `lora_state` = {PEFT name: tensor} (see peft_name) to resume an adapter."""
+        self = cls(cfg, device, max_batch, P, T, **kw)
+        dev = self.device
+
+        def get(name):
+            if name not in sd:
+                raise KeyError(f"state dict has no '{name}'")
+            return sd[name]
+
+        def bf(t):
+            return t.detach().to(dev, torch.bfloat16).contiguous()
+
+        def quant(names):
+            w = torch.cat([bf(get(n)) for n in names], dim=0).contiguous()
+            if w.shape[1] % 64:
+                raise ValueError(f"{names[0]}: in_features {w.shape[1]} is not a multiple of the NF4 block (64)")
+            return ops.nf4_quantize(w)
+
+        self.embed = bf(get("model.embed_tokens.weight"))
+        self.lm_head = bf(sd["lm_head.weight"]) if "lm_head.weight" in sd else self.embed   # tied embeddings
+        self.final_norm = bf(get("model.norm.weight"))
+        if tuple(self.embed.shape) != (cfg.vocab, cfg.hidden):
+            raise ValueError(f"embed_tokens is {tuple(self.embed.shape)}, config says {(cfg.vocab, cfg.hidden)}")
+        for i in range(cfg.n_layers):
+            a, m = f"model.layers.{i}.self_attn.", f"model.layers.{i}.mlp."
+            L = {}
+            L["qkv_p"], L["qkv_a"] = quant([a + "q_proj.weight", a + "k_proj.weight", a + "v_proj.weight"])
+            L["o_p"], L["o_a"] = quant([a + "o_proj.weight"])
+            L["gu_p"], L["gu_a"] = quant([m + "gate_proj.weight", m + "up_proj.weight"])
+            L["down_p"], L["down_a"] = quant([m + "down_proj.weight"])
+            if a + "q_proj.bias" in sd:
+                L["qkv_bias"] = torch.cat([bf(get(a + x + "_proj.bias")) for x in "qkv"]).contiguous()
+            else:   # Llama-style: no qkv bias
+                L["qkv_bias"] = torch.zeros(cfg.qd + 2 * cfg.kd, device=dev, dtype=torch.bfloat16)
+            L["ln1"] = bf(get(f"model.layers.{i}.input_layernorm.weight"))
+            L["ln2"] = bf(get(f"model.layers.{i}.post_attention_layernorm.weight"))
+            self.layers.append(L)
+        g = torch.Generator(device=dev).manual_seed(lora_seed)
+        shapes = cfg.module_shapes()
+        for (i, mod, ab), (off, shp) in self.offsets.items():
+            n = shp[0] * shp[1]
+            if lora_state is not None:
+                t = lora_state[self.peft_name(i, mod, ab)].detach().float().reshape(-1)
+                assert t.numel() == n, (self.peft_name(i, mod, ab), tuple(t.shape), shp)
+                self.lora_flat[off:off + n] = t.to(dev)
+            elif ab == "A":
+                bound = shapes[mod][0] ** -0.5
+                self.lora_flat[off:off + n] = (torch.rand(n, generator=g, device=dev) * 2 - 1) * bound
+        self._finish()
+        return self
+
+    @classmethod
+    def from_pretrained(cls, path, device, max_batch, P, T, lora_r=16, lora_alpha=16.0, **kw):
+        """Local checkpoint directory with config.json + *.safetensors (dense weights).  Returns (policy, cfg)."""
+        import glob
+        import json
+        import os
+        from safetensors.torch import load_file
+        cfg = LMConfig.from_hf_config(json.load(open(os.path.join(path, "config.json"))), lora_r, lora_alpha)
+        sd = {}
+        files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+        if not files:
+            raise FileNotFoundError(f"no *.safetensors under {path}")
+        for f in files:
+            sd.update(load_file(f))
+        return cls.from_hf_state_dict(cfg, sd, device, max_batch, P, T, **kw), cfg
 
     # ---- hot path ------------------------------------------------------------------------------
     def sync_lora(self):

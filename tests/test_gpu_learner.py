@@ -303,3 +303,54 @@ def test_grouped_dw_matches_per_group_path(cuda, monkeypatch):
     assert out[1].abs().max() > 0
     rel = ((out[0] - out[1]).norm() / out[1].norm()).item()
     assert rel < 1e-5, rel
+
+
+def test_hf_state_dict_loader_vs_transformers(cuda):
+    """Policy.from_hf_state_dict (HF Qwen2 names, NF4 quantisation at load like load_in_4bit) against
+    transformers' own Qwen2ForCausalLM run on the NF4-dequantised weights: per-token log-probs of the scoring API
+    (reference distributed_actor.py:241-260) agree within bf16 error.  LoRA B = 0 (PEFT init) => adapter is a no-op."""
+    transformers = pytest.importorskip("transformers")
+    from distrl_llm_b200 import ops
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer
+    from distrl_llm_b200.policy import LMConfig, Policy
+    hfc = transformers.Qwen2Config(vocab_size=1024, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                                   num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=256,
+                                   tie_word_embeddings=False, attn_implementation="eager")
+    torch.manual_seed(0)
+    hf = transformers.Qwen2ForCausalLM(hfc).to(cuda).float().eval()
+    with torch.no_grad():   # make the biases / norms non-trivial
+        for n, p in hf.named_parameters():
+            if n.endswith("bias"):
+                p.normal_(0, 0.02)
+            if "layernorm" in n or n == "model.norm.weight":
+                p.uniform_(0.8, 1.2)
+    cfg = LMConfig.from_hf_config(hfc, lora_r=16, lora_alpha=16)
+    assert (cfg.head_dim, cfg.n_kv_heads, cfg.inter) == (64, 2, 512) and cfg.rope_theta == 10000.0
+    P, T, B = 10, 30, 4
+    pol = Policy.from_hf_state_dict(cfg, hf.state_dict(), cuda, max_batch=B, P=P, T=T)
+    # give HF exactly the weights the learner holds: NF4 round trip of every linear, bf16 round trip of the rest
+    with torch.no_grad():
+        for i, L in enumerate(pol.layers):
+            lay = hf.model.layers[i]
+            qkv = ops.nf4_dequant(L["qkv_p"], L["qkv_a"], cfg.qd + 2 * cfg.kd, cfg.hidden).float()
+            lay.self_attn.q_proj.weight.copy_(qkv[:cfg.qd]); lay.self_attn.k_proj.weight.copy_(qkv[cfg.qd:cfg.qd + cfg.kd])
+            lay.self_attn.v_proj.weight.copy_(qkv[cfg.qd + cfg.kd:])
+            lay.self_attn.o_proj.weight.copy_(ops.nf4_dequant(L["o_p"], L["o_a"], cfg.hidden, cfg.qd).float())
+            gu = ops.nf4_dequant(L["gu_p"], L["gu_a"], 2 * cfg.inter, cfg.hidden).float()
+            lay.mlp.gate_proj.weight.copy_(gu[:cfg.inter]); lay.mlp.up_proj.weight.copy_(gu[cfg.inter:])
+            lay.mlp.down_proj.weight.copy_(ops.nf4_dequant(L["down_p"], L["down_a"], cfg.hidden, cfg.inter).float())
+        for p in hf.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+    ln = GRPOLearner(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5})
+    rng = np.random.default_rng(0)
+    prompts = [rng.integers(1, 1024, size=int(rng.integers(4, P + 1))).tolist() for _ in range(B)]
+    answers = [rng.integers(1, 1024, size=int(rng.integers(8, T + 1))).tolist() for _ in range(B)]
+    lp, mask = ln.compute_current_policy_probs(pol, prompts, answers)
+    ids, am, _ = lo.pad_batch(prompts, answers, P, T)
+    ids, am = ids.to(cuda), am.to(cuda)
+    with torch.no_grad():   # reference :241-260 verbatim in spirit: logits -> shift -> log_softmax -> gather
+        logits = hf(input_ids=ids, attention_mask=am).logits[:, P - 1:-1, :]
+        ref = torch.log_softmax(logits.float(), -1).gather(-1, ids[:, P:].unsqueeze(-1)).squeeze(-1)
+    m = mask.bool()
+    assert (lp[m] - ref[m]).abs().max().item() < 4e-2
+    assert (lp[m] - ref[m]).abs().mean().item() < 6e-3
