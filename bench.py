@@ -166,6 +166,7 @@ def config_dict(args):
                         f"(P={args.prompt_len}, micro-batch {args.micro_batch})",
             "global_batch": args.seqs * args.gpus, "seq_len": args.prompt_len + args.new_tokens,
             "parallelism": f"dp{args.gpus}" if args.gpus > 1 else "single learner",
+            "passes": f"{getattr(args, 'fuse_microbatches', 1)} reference micro-batches of 8 per model pass (gradient accumulation is linear: identical result)",
             "layout": "classic [B, P+T] rows" if getattr(args, "no_share_prompts", False) else
                       "packed shared-prompt rows (each group's prompt processed once; identical gradients)",
             "l2": "per-step activations and weights (>30 GB) far exceed the 126 MB L2; no flush needed"}
@@ -187,6 +188,7 @@ def main():
     ap.add_argument("--layers", type=int, default=28, help="debug only: anything but 28 is not the benchmark")
     ap.add_argument("--cpu_rows", type=int, default=2, help="sequences in the CPU sample micro-batch")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--fuse_microbatches", type=int, default=2, help="reference micro-batches per model pass (identical gradients; 1 = one pass per micro-batch like the reference)")
     ap.add_argument("--no_share_prompts", action="store_true", help="classic [B, P+T] layout (every prompt recomputed per completion)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -219,9 +221,10 @@ def main():
     P, T, B, N = w["P"], w["T"], w["B"], w["n_seq"]
     group = None
     kw = {}
+    FK = max(1, args.fuse_microbatches)
     if world > 1:
-        group, kw = P2PGroup.from_torch_distributed(cfg, B, P, T, dev)
-    pol = Policy.random_init(cfg, dev, B, P, T, seed=1234, **kw)   # same base + LoRA on every learner
+        group, kw = P2PGroup.from_torch_distributed(cfg, FK * B, P, T, dev)
+    pol = Policy.random_init(cfg, dev, FK * B, P, T, seed=1234, **kw)   # same base + LoRA on every learner
     if group is not None:
         group.attach(pol)
     config = {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 2e-5}
@@ -242,23 +245,36 @@ def main():
 
     share = learner.share_prompts and not args.no_share_prompts
     learner.share_prompts = share
+    assert learner.fuse_microbatches == FK
+    # passes of FK reference micro-batches each (learner.compute_loss does the same planning on the e2e path)
+    bounds = [(i * B, min((i + 1) * B, N)) for i in range(nb)]
+    passes, cur = [], []
+    for (s_, e_) in bounds:
+        if e_ - s_ == B and FK > 1:
+            cur.append((s_, e_))
+            if len(cur) == FK:
+                passes.append(cur); cur = []
+        else:
+            passes.append([(s_, e_)])
+    if cur:
+        passes.append(cur)
+    pass_rng = [(g[0][0], g[-1][1], len(g)) for g in passes]      # contiguous because only full micro-batches fuse
+    d_adv_k = [d_adv[s_:e_] * float(k) for (s_, e_, k) in pass_rng]
     packed = []
     if share:  # packed shared-prompt layout, device-resident for the `value` measurement
         from distrl_llm_b200 import packing
-        for i in range(nb):
-            s_, e_ = i * B, min((i + 1) * B, N)
+        for (s_, e_, k) in pass_rng:
             packed.append(packing.PackedDevice(packing.pack_microbatch(ids_h[s_:e_].numpy(), am_h[s_:e_].numpy(), P, T), dev))
         torch.cuda.synchronize()
 
     def device_step():
         pol.zero_grad()
         pol.loss_accum.zero_()
-        for i in range(nb):
-            s, e = i * B, min((i + 1) * B, N)
+        for i, (s, e, k) in enumerate(pass_rng):
             if share:
-                pol.microbatch_packed(packed[i], d_adv[s:e], nb, True, backward=True)
+                pol.microbatch_packed(packed[i], d_adv_k[i], nb, True, backward=True)
             else:
-                pol.microbatch(d_ids[s:e], d_am[s:e], d_ansm[s:e], d_adv[s:e], P, T, nb, True, backward=True)
+                pol.microbatch(d_ids[s:e], d_am[s:e], d_ansm[s:e], d_adv_k[i], P, T, nb, True, backward=True)
         if group is not None:
             group.reduce_adam_step(pol, learner.lr, 0.0)
         else:

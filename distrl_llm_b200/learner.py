@@ -75,6 +75,15 @@ class BaseLearner:
         # packed shared-prompt layout (packing.py): identical results, each distinct prompt of a micro-batch is
         # processed once; needs the tcgen05 attention kernels (head_dim 128)
         self.share_prompts = bool(config.get("share_prompts", policy.cfg.head_dim == 128))
+        # Pass fusion: the reference accumulates gradients over micro-batches of train_batch_size sequences
+        # (:354-389) because a pass has to fit a 24-80 GB GPU.  The accumulated gradient is linear in the per-sequence
+        # coefficients, so k full micro-batches can go through the model as ONE pass with every advantage (and the KL
+        # weight) scaled by k -- coef = -(k A)/(len * kB * nb) = -A/(len * B * nb) -- with identical results: weights are
+        # streamed once per k micro-batches and the GEMM M dimension fills its last tile.  k is bounded by the capacity
+        # the policy was built with (max_batch // train_batch_size) and by config["fuse_microbatches"] (0 = auto).
+        cap = max(1, policy.max_batch // max(1, self.update_batch_size))
+        want = int(config.get("fuse_microbatches", 0))
+        self.fuse_microbatches = cap if want <= 0 else max(1, min(want, cap))
         self.lora_save_path = config.get("lora_save_path", "lora_request_math")
         self.reference_quirks = reference_quirks
         self.generator = generator
@@ -124,31 +133,48 @@ class BaseLearner:
         pol.zero_grad()                                                       # :358 / :450
         pol.loss_accum.zero_()
         grpo = self.learner_type == "grpo"
+        B = self.update_batch_size
+        # plan the passes: runs of up to `fuse_microbatches` FULL micro-batches that survive the skip predicate
+        passes, cur = [], []
         for i in range(nb):
-            s, e = i * self.update_batch_size, min((i + 1) * self.update_batch_size, n)
-            r = rewards[s:e]
+            s, e = i * B, min((i + 1) * B, n)
             # :367 / :459  `if batch_rewards.all() == 0: continue` — true when ANY reward is exactly 0 (quirk Q1)
-            if self.reference_quirks and not bool(np.all(r != 0)):
+            if self.reference_quirks and not bool(np.all(rewards[s:e] != 0)):
                 continue
-            ids, am, ansm = self._encode(messages[s:e], answers[s:e])
+            if e - s == B and self.fuse_microbatches > 1:
+                cur.append((s, e))
+                if len(cur) == self.fuse_microbatches:
+                    passes.append(cur)
+                    cur = []
+            else:
+                passes.append([(s, e)])
+        if cur:
+            passes.append(cur)
+        for group in passes:
+            k = len(group)
+            idx = [j for (s, e) in group for j in range(s, e)]
+            msgs, answ = [messages[j] for j in idx], [answers[j] for j in idx]
+            r = rewards[idx] * float(k)          # see __init__: k fused micro-batches
+            beta = self.kl_beta * k
+            ids, am, ansm = self._encode(msgs, answ)
             if self.share_prompts:
                 pk = self._pack(ids, am)
                 ref_lp = None
                 if self.kl_beta != 0.0:
-                    ref_lp = torch.empty(e - s, self.max_new_tokens, device=pol.device, dtype=torch.float32)
+                    ref_lp = torch.empty(len(idx), self.max_new_tokens, device=pol.device, dtype=torch.float32)
                     pol.microbatch_packed(pk, None, 1, False, backward=False, lp_out=ref_lp, lora_off=True)
                 pol.microbatch_packed(pk, self._h2d(torch.from_numpy(r)), nb, grpo, backward=True, ref_lp=ref_lp,
-                                      kl_beta=self.kl_beta)
+                                      kl_beta=beta)
                 continue
             d_ids, d_am, d_ansm = self._h2d(ids), self._h2d(am), self._h2d(ansm)
             ref_lp = None
             if self.kl_beta != 0.0:
                 # reference policy = the frozen base with the adapter disabled (one extra forward, no backward)
-                ref_lp = torch.empty(e - s, self.max_new_tokens, device=pol.device, dtype=torch.float32)
+                ref_lp = torch.empty(len(idx), self.max_new_tokens, device=pol.device, dtype=torch.float32)
                 pol.microbatch(d_ids, d_am, d_ansm, None, self.max_prompt_tokens, self.max_new_tokens, 1, False,
                                backward=False, lp_out=ref_lp, lora_off=True)
             pol.microbatch(d_ids, d_am, d_ansm, self._h2d(torch.from_numpy(r)), self.max_prompt_tokens,
-                           self.max_new_tokens, nb, grpo, backward=True, ref_lp=ref_lp, kl_beta=self.kl_beta)
+                           self.max_new_tokens, nb, grpo, backward=True, ref_lp=ref_lp, kl_beta=beta)
         return float(pol.loss_accum.item())   # sum of per-micro-batch losses (quirk Q2), one sync
 
     # ---- gradient export / merge (:283-333) --------------------------------------------------------

@@ -354,3 +354,44 @@ def test_hf_state_dict_loader_vs_transformers(cuda):
     m = mask.bool()
     assert (lp[m] - ref[m]).abs().max().item() < 4e-2
     assert (lp[m] - ref[m]).abs().mean().item() < 6e-3
+
+
+@pytest.mark.parametrize("kind,beta,hd", [("grpo", 0.0, 64), ("pg", 0.0, 128), ("grpo", 0.3, 128)])
+def test_fused_passes_match_per_microbatch_oracle(cuda, kind, beta, hd):
+    """Pass fusion (learner.fuse_microbatches): k reference micro-batches per model pass with advantages and the KL
+    weight scaled by k.  The oracle loops over micro-batches of train_batch_size like the reference; includes a skipped
+    micro-batch (quirk Q1), a ragged last micro-batch (never fused) and prompts shared inside groups."""
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer, Learner
+    from distrl_llm_b200.policy import Policy
+    ocfg = lo.OracleConfig(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=4 if hd == 64 else 2, n_kv_heads=2 if hd == 64 else 1,
+                           head_dim=hd, lora_r=16, lora_alpha=16)
+    params, nf4 = lo.make_params(ocfg, seed=8, lora_b_std=0.05 if beta else 0.01)
+    P, T, B, N = 16, 40, 4, 22            # 6 micro-batches: 5 full + one of 2
+    rng = np.random.default_rng(5)
+    prompts, answers = [], []
+    for g in range((N + 3) // 4):
+        pr = rng.integers(1, ocfg.vocab, size=int(rng.integers(P // 2, P + 1))).tolist()
+        for _ in range(4):
+            prompts.append(pr)
+            answers.append(rng.integers(1, ocfg.vocab, size=int(rng.integers(T // 4, T + 1))).tolist())
+    prompts, answers = prompts[:N], answers[:N]
+    rewards = rng.normal(size=N)
+    rewards[5] = 0.0                        # micro-batch 1 is skipped by the reference's predicate
+    dparams = {k: (v.detach().to(cuda).requires_grad_(v.requires_grad)) for k, v in params.items()}
+    ids, am, ansm = lo.pad_batch(prompts, answers, P, T)
+    kw = {"kl_beta": beta} if beta else {}
+    ref_grads, ref_loss = lo.compute_gradients(dparams, ocfg, ids.to(cuda), am.to(cuda), ansm.to(cuda), rewards, P, B, kind, **kw)
+    pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, cuda, max_batch=3 * B, P=P, T=T)
+    cls = Learner if kind == "pg" else GRPOLearner
+    ln = cls(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5, "kl_beta": beta})
+    assert ln.fuse_microbatches == 3
+    grads, loss = ln._compute_gradients(prompts, answers, list(rewards))
+    tol = 4e-2 * sum(np.abs(rewards[i:i + B]).mean() for i in range(0, N, B)) + 2e-3 + (5e-2 * abs(ref_loss) if beta else 0)
+    assert abs(loss - ref_loss) <= tol, (loss, ref_loss)
+    _compare_grads(grads, ref_grads, ocfg, pol)
+    # one pass per micro-batch on the same policy: same gradient up to bf16 reassociation
+    ln.fuse_microbatches = 1
+    grads1, loss1 = ln._compute_gradients(prompts, answers, list(rewards))
+    assert abs(loss1 - loss) <= 1e-2 * max(1.0, abs(loss))
+    _compare_grads(grads, {f"l{i}.{m}.{ab}": grads1[pol.peft_name(i, m, ab)] for i in range(ocfg.n_layers)
+                           for m in lo.LORA_MODULES for ab in ("A", "B")}, ocfg, pol, cos_min=0.9995, rel_max=3e-2)
