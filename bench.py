@@ -363,7 +363,7 @@ def main():
                 "gemm_share_of_step": round(gemm["ms"] / max(sum(p["ms"] for p in prof.values()), 1e-9), 4),
                 "avg_launch_ms": round(gemm["ms"] / max(gemm["launches"], 1), 4),
                 "flops_per_launch": gemm["work"] / max(gemm["launches"], 1),
-                "step_model_tflops": round(step_flops * world / (ms_dev / 1e3) / 1e12 / world, 1),
+                "reference_layout_equiv_tflops": round(step_flops * world / (ms_dev / 1e3) / 1e12 / world, 1),  # SURVEY 8d FLOPs of the unpacked layout / our time
                 "how": "CUDA events between consecutive launches on the launching stream, one profiled step after the timed region"}
     h2d = int(sum(pk.h2d_bytes for pk in packed) + N * 8) if share else int(ids_h.numel() * 4 + am_h.numel() * 4 + ansm_h.numel() * 4 + N * 8)
     if rank == 0:
