@@ -186,9 +186,10 @@ bool gemm_fuse_supported(int M, int I);
 // and every K-range keeps >= 64 k-blocks -- measured on B200 (profiles/r1_run19*): with K = 3584 the spill / flag /
 // reload chain (~15 us) costs more than the quarter wave it saves, with K >= 18944 it saves 7-13 % of the GEMM.
 // Rasterisation group height.  The tiles in flight sweep n inside a group of gm m-blocks: B panels are shared by gm
-// tiles through L2, A panels are re-read once per n step.  If the whole A operand fits in L2 next to the streams
-// (ncu, packed config 2: the gate|up GEMM read B 3x from DRAM with gm = 8 because 18 m-blocks = 3 groups), one group
-// over all m-blocks streams B exactly once.  Otherwise a square-ish 8 x ~9 patch minimises (gm + gn) panels per wave.
+// tiles through L2, A panels are re-read once per n step.  Every group streams all of B once, so fewer, taller groups
+// cut the B traffic as long as a group's A panels stay L2-resident (ncu, packed config 2: with gm = 8 the gate|up GEMM
+// read B 3x from DRAM at 18 m-blocks and 4.4x at 35).  K-long operands (panels > 5 MB) keep the square-ish 8 x ~9 patch
+// that minimises (gm + gn) panels per wave.
 inline int raster_group(long long a_bytes, int num_m_blocks) {
   static int forced = -1;
   if (forced < 0) {
@@ -196,7 +197,14 @@ inline int raster_group(long long a_bytes, int num_m_blocks) {
     forced = e ? atoi(e) : 0;
   }
   if (forced > 0) return forced;
-  return a_bytes <= (48ll << 20) ? (num_m_blocks > 0 ? num_m_blocks : 1) : 8;
+  if (num_m_blocks <= 8) return num_m_blocks > 0 ? num_m_blocks : 1;
+  // m-blocks whose A panels stay L2-resident (40 MB budget: the 126 MB L2 is split over two dies and also carries the
+  // B stream and the C write-allocate traffic); balanced groups, never thinner than the square-ish 8
+  const long long panel = a_bytes / num_m_blocks;
+  const long long fit = panel > 0 ? (40ll << 20) / panel : num_m_blocks;
+  if (fit < 8) return 8;
+  const long long groups = (num_m_blocks + fit - 1) / fit;
+  return (int)((num_m_blocks + groups - 1) / groups);
 }
 
 inline int pair_tail_split(long long tiles, int clusters, int kb_total) {
