@@ -211,10 +211,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in this image) goes away
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL prints its version banner to stdout when the first communicator
+        # is created (NCCL_DEBUG=VERSION/WARN in this image), so fd 1 points at stderr until that has happened
+        sys.stdout.flush()
+        _saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(_saved_fd, 1)
+            os.close(_saved_fd)
     w = workload(args)
     cfg = LMConfig.qwen25_7b(lora_r=args.lora_rank)
     cfg.n_layers = args.layers
