@@ -163,7 +163,8 @@ def run_reference(args, rank, world):
 def config_dict(args):
     return {"workload": f"GRPO learner step, Qwen2.5-7B-shaped random-init NF4 base + rank-{args.lora_rank} LoRA, "
                         f"group_size={args.group_size}, {args.seqs} completions len={args.new_tokens} per GPU "
-                        f"(P={args.prompt_len}, micro-batch {args.micro_batch})",
+                        f"(P={args.prompt_len}, micro-batch {args.micro_batch})"
+                        + (", RAGGED lengths (prompt ~ U[P/2,P], completion ~ U[T/4,T]); value counts real completion tokens" if getattr(args, "ragged", False) else ""),
             "global_batch": args.seqs * args.gpus, "seq_len": args.prompt_len + args.new_tokens,
             "parallelism": f"dp{args.gpus}" if args.gpus > 1 else "single learner",
             "passes": f"{getattr(args, 'fuse_microbatches', 1)} reference micro-batches of 8 per model pass (gradient accumulation is linear: identical result)",
@@ -189,6 +190,7 @@ def main():
     ap.add_argument("--cpu_rows", type=int, default=2, help="sequences in the CPU sample micro-batch")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--fuse_microbatches", type=int, default=2, help="reference micro-batches per model pass (identical gradients; 1 = one pass per micro-batch like the reference)")
+    ap.add_argument("--ragged", action="store_true", help="ragged synthetic lengths (prompt ~ U[P/2,P], completion ~ U[T/4,T]); value counts REAL completion tokens")
     ap.add_argument("--no_share_prompts", action="store_true", help="classic [B, P+T] layout (every prompt recomputed per completion)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -243,7 +245,7 @@ def main():
 
     # synthetic batch: ids ~ U[1,V), full-length prompts/completions, rewards -> group advantages
     from distrl_llm_b200.trainer_prep import synthetic_candidates
-    cands, flat = synthetic_candidates(cfg.vocab, N, P, T, args.group_size, seed=1234 + rank)
+    cands, flat = synthetic_candidates(cfg.vocab, N, P, T, args.group_size, seed=1234 + rank, ragged=args.ragged)
     prompts, answers, adv = flat
     assert np.all(np.asarray(adv) != 0), "synthetic advantages must be non-zero (quirk Q1 would skip work)"
     nb = (N + B - 1) // B
@@ -348,7 +350,7 @@ def main():
     _capi.check(_capi.lib().b200rl_model_profile(pol.handle, 0))
     prof = {CATS[i]: {"ms": ms_c[i], "work": wk_c[i], "launches": cnt_c[i]} for i in range(9)}
 
-    tokens = N * T * world
+    tokens = N * T * world if not args.ragged else int(sum(len(a) for a in answers)) * world   # ragged: this rank's real tokens x N (same distribution)
     value = tokens / (ms_dev / 1e3)
     e2e_val = tokens / (ms_e2e / 1e3)
     peaks = {}

@@ -75,6 +75,8 @@ class BaseLearner:
         # packed shared-prompt layout (packing.py): identical results, each distinct prompt of a micro-batch is
         # processed once; needs the tcgen05 attention kernels (head_dim 128)
         self.share_prompts = bool(config.get("share_prompts", policy.cfg.head_dim == 128))
+        # packed layout only: do not store pad tokens at all (packing.py).  Same surviving rows, same positions.
+        self.ragged_rows = bool(config.get("ragged_rows", True))
         # Pass fusion: the reference accumulates gradients over micro-batches of train_batch_size sequences
         # (:354-389) because a pass has to fit a 24-80 GB GPU.  The accumulated gradient is linear in the per-sequence
         # coefficients, so k full micro-batches can go through the model as ONE pass with every advantage (and the KL
@@ -121,7 +123,8 @@ class BaseLearner:
         return lp, d_ansm
 
     def _pack(self, ids, am):
-        host = packing.pack_microbatch(ids.numpy(), am.numpy(), self.max_prompt_tokens, self.max_new_tokens)
+        host = packing.pack_microbatch(ids.numpy(), am.numpy(), self.max_prompt_tokens, self.max_new_tokens,
+                                       ragged=self.ragged_rows)
         return packing.PackedDevice(host, self.policy.device)
 
     # ---- loss + backward (:349-395 PG, :440-493 GRPO) ---------------------------------------------

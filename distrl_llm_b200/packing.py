@@ -14,6 +14,13 @@ b200rl_model_microbatch_packed / the tcgen05 attention kernels through block des
 
 Groups are runs of CONSECUTIVE sequences with identical padded prompt rows (ids and mask); a micro-batch without any
 repeated prompt degenerates to G = B (same code path, no saving).
+
+Ragged rows (`ragged=True`, the default): the pad tokens the reference feeds through the model (prompts left-padded to
+P, completions right-padded to T, distributed_actor.py:217-239) are masked out of attention and of the loss, so they
+influence nothing.  The packed layout simply does not store them: a prompt segment has its real length, a completion
+segment its real length, and every kept row carries its ORIGINAL position (index in the padded row) for RoPE, which
+keeps the arithmetic of the surviving rows identical.  Scored positions beyond a completion's length point at row 0
+and have coefficient 0.  SURVEY.md 8(f) N2: mean completion length is 450-500 of T = 1200 in the reference's runs.
 """
 from __future__ import annotations
 
@@ -46,6 +53,10 @@ class PackedHost:
     part_rows: int
     arrays: dict          # name -> np.int32 array
     seq_group: np.ndarray  # [B] group of every sequence
+    prompt_row0: object = None   # [G] first packed row of every prompt segment
+    prompt_ext: object = None    # [G] (first kept padded index, rows)
+    comp_row0: object = None     # [B] first packed row of every completion segment
+    comp_len: object = None      # [B] rows of every completion segment
 
     def blob(self):
         """Concatenate all arrays into one int32 vector; returns (blob, {name: (offset, length)})."""
@@ -62,7 +73,7 @@ class PackedHost:
         return np.concatenate(parts), offs
 
 
-def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int) -> PackedHost:
+def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int, ragged: bool = True) -> PackedHost:
     """ids / attn_mask: [B, P+T] (prompt left-padded to P, completion right-padded to T, reference layout)."""
     ids = np.asarray(ids, dtype=np.int32)
     am = np.asarray(attn_mask, dtype=np.int32)
@@ -78,43 +89,76 @@ def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int) -> P
         seq_group[i] = g
     G = g + 1
     first_of_group = [int(np.argmax(seq_group == k)) for k in range(G)]
-    rows = G * P + B * T
-    comp0 = G * P
-    p_ids = np.empty(rows, np.int32)
-    p_pos = np.empty(rows, np.int32)
-    p_km = np.empty(rows, np.int32)
+    # ---- segments: (first padded index kept, number of rows kept).  Ragged: the contiguous run of real tokens
+    # (left-padded prompt = suffix, right-padded completion = prefix); a mask with holes keeps the padded extent.
+    def extent(mask, left_padded):
+        if not ragged:
+            return 0, mask.size
+        nz = np.flatnonzero(mask)
+        if nz.size == 0:
+            return (mask.size, 0) if left_padded else (0, 0)
+        if left_padded:
+            return int(nz[0]), mask.size - int(nz[0])
+        return 0, int(nz[-1]) + 1
+    p_ext = [extent(am[first_of_group[k], :P], True) for k in range(G)]        # (start index in [0,P), rows)
+    c_ext = [extent(am[i, P:], False) for i in range(B)]                       # (0, rows)
+    p_row0 = np.zeros(G, np.int64)
+    c_row0 = np.zeros(B, np.int64)
+    r = 0
     for k in range(G):
-        i = first_of_group[k]
-        p_ids[k * P:(k + 1) * P] = ids[i, :P]
-        p_km[k * P:(k + 1) * P] = am[i, :P]
-        p_pos[k * P:(k + 1) * P] = np.arange(P)
+        p_row0[k] = r
+        r += p_ext[k][1]
     for i in range(B):
-        r0 = comp0 + i * T
-        p_ids[r0:r0 + T] = ids[i, P:]
-        p_km[r0:r0 + T] = am[i, P:]
-        p_pos[r0:r0 + T] = P + np.arange(T)
+        c_row0[i] = r
+        r += c_ext[i][1]
+    rows = max(int(r), 1)
+    p_ids = np.zeros(rows, np.int32)
+    p_pos = np.zeros(rows, np.int32)
+    p_km = np.zeros(rows, np.int32)
+    for k in range(G):
+        i, (st, n) = first_of_group[k], p_ext[k]
+        r0 = int(p_row0[k])
+        p_ids[r0:r0 + n] = ids[i, st:st + n]
+        p_km[r0:r0 + n] = am[i, st:st + n]
+        p_pos[r0:r0 + n] = st + np.arange(n)
+    for i in range(B):
+        r0, n = int(c_row0[i]), c_ext[i][1]
+        p_ids[r0:r0 + n] = ids[i, P:P + n]
+        p_km[r0:r0 + n] = am[i, P:P + n]
+        p_pos[r0:r0 + n] = P + np.arange(n)
     # ---- scored rows: the logit at original position P-1+t predicts completion token t (distributed_actor.py:245-249)
-    score_src = np.empty(B * T, np.int32)
-    for i in range(B):
-        score_src[i * T] = seq_group[i] * P + (P - 1)            # last prompt position (shared by the group)
-        score_src[i * T + 1:(i + 1) * T] = comp0 + i * T + np.arange(T - 1)
     targets = ids[:, P:].reshape(-1).astype(np.int32)
     answer_mask = am[:, P:].reshape(-1).astype(np.int32)
-    order = np.argsort(score_src, kind="stable")
-    counts = np.bincount(score_src, minlength=rows)
+    score_src = np.zeros(B * T, np.int32)
+    live = np.zeros(B * T, bool)            # scored positions that exist in the packed rows
+    for i in range(B):
+        gk = int(seq_group[i])
+        n = c_ext[i][1]
+        if p_ext[gk][1] > 0 and n > 0:      # t = 0 reads the last prompt row (shared by the group)
+            score_src[i * T] = p_row0[gk] + p_ext[gk][1] - 1
+            live[i * T] = True
+        if n > 1:
+            score_src[i * T + 1:i * T + n] = c_row0[i] + np.arange(n - 1)
+            live[i * T + 1:i * T + n] = True
+    # positions without a source row must not be trained on (they are pad positions: answer_mask is already 0 there,
+    # except when a sequence has an empty prompt, which the reference cannot produce)
+    answer_mask = np.where(live, answer_mask, 0).astype(np.int32)
+    live_idx = np.flatnonzero(live)
+    order = live_idx[np.argsort(score_src[live_idx], kind="stable")]
+    counts = np.bincount(score_src[live_idx], minlength=rows)
     sc_start = np.zeros(rows + 1, np.int32)
     sc_start[1:] = np.cumsum(counts)
     sc_list = order.astype(np.int32)
     # ---- attention block descriptors ----
-    segs = [(k * P, P, 0, 0) for k in range(G)]                                   # (row0, len, pre_row0, pre_len)
-    segs += [(comp0 + i * T, T, int(seq_group[i]) * P, P) for i in range(B)]
+    segs = [(int(p_row0[k]), p_ext[k][1], 0, 0) for k in range(G)]                # (row0, len, pre_row0, pre_len)
+    segs += [(int(c_row0[i]), c_ext[i][1], int(p_row0[seq_group[i]]), p_ext[int(seq_group[i])][1]) for i in range(B)]
     qb = []
     for (r0, ln, pr0, pl) in segs:
         for b0 in range(0, ln, 128):
             work = (pl + 127) // 128 + (min(b0 + 128, ln) + 127) // 128
             qb.append((work, [r0 + b0, min(128, ln - b0), b0, r0, ln, pr0, pl, r0 + b0]))
     qb.sort(key=lambda t: -t[0])                                                  # heavy blocks first
-    qblocks = np.array([t[1] for t in qb], np.int32)
+    qblocks = np.array([t[1] for t in qb], np.int32).reshape(-1, QB_FIELDS)
     kb, part_rows = [], 0
     red = [[] for _ in range(rows)]
     deps = [[] for _ in range(G)]
@@ -123,24 +167,27 @@ def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int) -> P
     for si, (r0, ln, pr0, pl) in enumerate(segs):
         qsegs = [(r0, ln, 1)]                                                     # own queries (causal)
         if si < G:
-            qsegs += [(comp0 + i * T, T, 0) for i in deps[si]]                    # every completion of the group
+            qsegs += [(int(c_row0[i]), c_ext[i][1], 0) for i in deps[si] if c_ext[i][1] > 0]   # the group's completions
         for b0 in range(0, ln, 128):
             k_rows = min(128, ln - b0)
             for (qr0, qlen, causal) in qsegs:
                 nqb = (qlen + 63) // 64 - (b0 // 64 if causal else 0)
                 kb.append((nqb, [r0 + b0, k_rows, b0, qr0, qlen, causal, qr0, part_rows]))
-                for r in range(k_rows):
-                    red[r0 + b0 + r].append(part_rows + r)
+                for rr in range(k_rows):
+                    red[r0 + b0 + rr].append(part_rows + rr)
                 part_rows += k_rows
     kb.sort(key=lambda t: -t[0])
-    kblocks = np.array([t[1] for t in kb], np.int32)
+    kblocks = np.array([t[1] for t in kb], np.int32).reshape(-1, KB_FIELDS)
     red_start = np.zeros(rows + 1, np.int32)
     red_start[1:] = np.cumsum([len(x) for x in red])
     red_list = np.array([x for lst in red for x in lst], np.int32)
     arrays = {"ids": p_ids, "pos": p_pos, "key_mask": p_km, "score_src": score_src, "targets": targets,
               "answer_mask": answer_mask, "sc_start": sc_start, "sc_list": sc_list, "qblocks": qblocks.reshape(-1),
               "kblocks": kblocks.reshape(-1), "red_start": red_start, "red_list": red_list}
-    return PackedHost(rows=rows, B=B, P=P, T=T, n_groups=G, part_rows=part_rows, arrays=arrays, seq_group=seq_group)
+    host = PackedHost(rows=rows, B=B, P=P, T=T, n_groups=G, part_rows=max(part_rows, 1), arrays=arrays, seq_group=seq_group)
+    host.prompt_row0, host.prompt_ext = p_row0, p_ext       # (first kept padded index, rows) per group
+    host.comp_row0, host.comp_len = c_row0, [e[1] for e in c_ext]
+    return host
 
 
 class PackedDevice:

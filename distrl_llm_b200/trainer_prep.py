@@ -48,7 +48,7 @@ def split_for_learners(problems, answers, rewards, n_learners):
     return chunks
 
 
-def synthetic_candidates(vocab, n_seq, P, T, group_size, seed=1234, device=None):
+def synthetic_candidates(vocab, n_seq, P, T, group_size, seed=1234, device=None, ragged=False):
     """Synthetic learner batch: token ids ~ U[1, V), full-length prompts and completions,
     rewards = format in {0,.1,.2} w.p. (.5,.3,.2) + accuracy ~ Bernoulli(.25) per candidate (degenerate groups
     redrawn), advantages by the GRPO rule.  Returns (candidates payload, (prompts, answers, advantages))."""
@@ -56,9 +56,11 @@ def synthetic_candidates(vocab, n_seq, P, T, group_size, seed=1234, device=None)
     n_prob = n_seq // group_size
     cand = {"answers": [], "problem": [], "rewards": []}
     for _ in range(n_prob):
-        prompt = rng.integers(1, vocab, size=P).tolist()
+        # ragged variant: prompt_len ~ U[P/2, P], completion_len ~ U[T/4, T]
+        prompt = rng.integers(1, vocab, size=int(rng.integers(P // 2, P + 1)) if ragged else P).tolist()
         cand["problem"].append([prompt] * group_size)
-        cand["answers"].append([rng.integers(1, vocab, size=T).tolist() for _ in range(group_size)])
+        cand["answers"].append([rng.integers(1, vocab, size=int(rng.integers(T // 4, T + 1)) if ragged else T).tolist()
+                                for _ in range(group_size)])
         while True:
             fmt = rng.choice([0.0, 0.1, 0.2], size=group_size, p=[0.5, 0.3, 0.2])
             acc = (rng.random(group_size) < 0.25).astype(np.float64)

@@ -484,8 +484,9 @@ def test_attention(cuda, attn_mode, B, L, nq, nkv, hd):
 # ------------------------------------------------------------------------------------------------
 # packed "shared-prompt" attention (tcgen05, head_dim 128): each distinct prompt stored once
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ragged", [True, False], ids=["ragged", "padded"])
 @pytest.mark.parametrize("groups,per_group,P,T", [(2, 3, 70, 130), (1, 8, 350, 512), (3, 1, 40, 64)])
-def test_attention_packed_shared_prompt(cuda, groups, per_group, P, T):
+def test_attention_packed_shared_prompt(cuda, groups, per_group, P, T, ragged):
     import ctypes as C
     from distrl_llm_b200 import _capi, packing
     nq, nkv, hd = 4, 2, 128
@@ -503,8 +504,10 @@ def test_attention_packed_shared_prompt(cuda, groups, per_group, P, T):
             n = int(rng.integers(T // 4, T + 1))
             ids[i, P:P + n] = rng.integers(1, 1000, size=n)
             am[i, P:P + n] = 1
-    host = packing.pack_microbatch(ids, am, P, T)
-    assert host.n_groups == groups and host.rows == groups * P + B * T
+    host = packing.pack_microbatch(ids, am, P, T, ragged=ragged)
+    assert host.n_groups == groups
+    assert host.rows == (int(am.sum() - am[:, :P].sum() + sum(am[np.argmax(host.seq_group == g), :P].sum() for g in range(groups)))
+                         if ragged else groups * P + B * T)
     pk = packing.PackedDevice(host, cuda)
     rows, cols = host.rows, (nq + 2 * nkv) * hd
     qkv = _rand((rows, cols), cuda, seed=1)
@@ -524,20 +527,20 @@ def test_attention_packed_shared_prompt(cuda, groups, per_group, P, T):
                                         c.qblocks, c.n_qblocks, c.kblocks, c.n_kblocks, c.red_start, c.red_list,
                                         _capi.stream()), "attn_seg_bwd")
     torch.cuda.synchronize()
-    # reference: expand the packed rows to the per-sequence [B, L] layout (gather), plain fp32 attention with autograd
-    comp0 = groups * P
-    idx = np.zeros((B, P + T), np.int64)
+    # reference: expand the packed rows to the per-sequence [B, L] layout (gather; dropped pad positions read a zero
+    # row and are masked as keys), plain fp32 attention with autograd
+    idx = np.full((B, P + T), rows, np.int64)                       # `rows` = index of the appended zero row
     for i in range(B):
-        idx[i, :P] = host.seq_group[i] * P + np.arange(P)
-        idx[i, P:] = comp0 + i * T + np.arange(T)
+        g = int(host.seq_group[i])
+        st, n = host.prompt_ext[g]
+        idx[i, st:st + n] = host.prompt_row0[g] + np.arange(n)
+        idx[i, P:P + host.comp_len[i]] = host.comp_row0[i] + np.arange(host.comp_len[i])
     idx_t = torch.from_numpy(idx).to(cuda)
     leaf = qkv.float().requires_grad_(True)
-    full = leaf[idx_t.view(-1)]                                     # [B*L, cols]
+    full = torch.cat([leaf, torch.zeros(1, cols, device=cuda)], 0)[idx_t.view(-1)]      # [B*L, cols]
     key_mask = torch.from_numpy(am).to(cuda)
     ref_full = _attn_ref(full, key_mask, B, P + T, nq, nkv, hd)     # [B*L, nq*hd]
-    # packed outputs: prompt rows from the first sequence of the group, completion rows from their own sequence
-    valid = torch.from_numpy(host.arrays["key_mask"]).to(cuda).bool()
-    got_full = out.float()[idx_t.view(-1)]
+    got_full = torch.cat([out.float(), torch.zeros(1, nq * hd, device=cuda)], 0)[idx_t.view(-1)]
     vq = key_mask.view(-1).bool()
     assert torch.isfinite(out.float()).all()
     assert _rel_err(got_full[vq], ref_full[vq]) < 8e-3
@@ -548,11 +551,11 @@ def test_attention_packed_shared_prompt(cuda, groups, per_group, P, T):
         w[i, P:] = 1.0
         if i in first:
             w[i, :P] = 1.0
-    dfull = dout.float()[idx_t.view(-1)] * w.view(-1, 1)
+    dfull = torch.cat([dout.float(), torch.zeros(1, nq * hd, device=cuda)], 0)[idx_t.view(-1)] * w.view(-1, 1)
     (ref_full * dfull).sum().backward()
     g_ref = leaf.grad                                               # already summed over the group through the gather
+    valid = torch.from_numpy(host.arrays["key_mask"]).to(cuda).bool()
     nqh = nq * hd
-    vrow = valid
     for name, sl in (("dq", slice(0, nqh)), ("dk", slice(nqh, nqh + nkv * hd)), ("dv", slice(nqh + nkv * hd, None))):
-        err = _rel_err(dqkv[:, sl][vrow], g_ref[:, sl][vrow])
+        err = _rel_err(dqkv[:, sl][valid], g_ref[:, sl][valid])
         assert err < 2e-2, f"{name} rel err {err}"

@@ -109,3 +109,73 @@ def test_two_rank_gradient_mean_and_step_matches_reference_golden():
     assert len(out) == world
     for rank in range(world):
         assert out[rank] < 2e-7, f"rank {rank}: {out[rank]}"   # every learner ends with the reference's merged step
+
+
+# ---------------------------------------------------------------------------------------------------
+# packed shared-prompt / ragged layout bookkeeping (distrl_llm_b200/packing.py) — pure integer logic
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ragged", [True, False])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_packing_descriptors_are_consistent(ragged, seed):
+    from distrl_llm_b200 import packing
+    rng = np.random.default_rng(seed)
+    P, T, groups, per = 150, 300, 3, 4
+    B = groups * per
+    ids = np.zeros((B, P + T), np.int32)
+    am = np.zeros_like(ids)
+    for g in range(groups):
+        plen = int(rng.integers(1, P + 1))
+        pr = rng.integers(1, 5000, size=plen)
+        for j in range(per):
+            i = g * per + j
+            ids[i, P - plen:P], am[i, P - plen:P] = pr, 1
+            n = int(rng.integers(0, T + 1)) if (i % 5) else 0          # some empty completions
+            ids[i, P:P + n], am[i, P:P + n] = rng.integers(1, 5000, size=n), 1
+    h = packing.pack_microbatch(ids, am, P, T, ragged=ragged)
+    a = h.arrays
+    assert h.n_groups == groups
+    real = int(am[:, P:].sum() + sum(am[g * per, :P].sum() for g in range(groups)))
+    assert h.rows == (max(real, 1) if ragged else groups * P + B * T)
+    assert int(a["key_mask"].sum()) == real
+    # every real token is stored once, with its ORIGINAL position (index in the padded row, reference :217-239)
+    for i in range(B):
+        g = int(h.seq_group[i])
+        st, n = h.prompt_ext[g]
+        r0 = int(h.prompt_row0[g])
+        assert np.array_equal(a["ids"][r0:r0 + n], ids[i, st:st + n]) and np.array_equal(a["pos"][r0:r0 + n], st + np.arange(n))
+        c0, cn = int(h.comp_row0[i]), h.comp_len[i]
+        assert np.array_equal(a["ids"][c0:c0 + cn], ids[i, P:P + cn]) and np.array_equal(a["pos"][c0:c0 + cn], P + np.arange(cn))
+        # scored positions: the logit at padded position P-1+t predicts completion token t (reference :245-249)
+        for t in range(T):
+            if a["answer_mask"][i * T + t]:
+                src = int(a["score_src"][i * T + t])
+                assert a["pos"][src] == P - 1 + t
+                assert a["targets"][i * T + t] == ids[i, P + t]
+                assert (r0 <= src < r0 + n) if t == 0 else (c0 <= src < c0 + cn)
+    assert np.array_equal(a["answer_mask"].reshape(B, T) != 0, (am[:, P:] != 0) & (am[:, :P].sum(1, keepdims=True) > 0))
+    # scatter CSR = inverse of score_src over the live positions
+    live = []
+    for r in range(h.rows):
+        for k in a["sc_list"][a["sc_start"][r]:a["sc_start"][r + 1]]:
+            assert a["score_src"][k] == r
+            live.append(int(k))
+    assert len(live) == len(set(live)) and set(np.flatnonzero(a["answer_mask"])) <= set(live)
+    # query blocks tile every stored row exactly once; key blocks' partial slabs are each reduced into exactly one row
+    qb = a["qblocks"].reshape(-1, packing.QB_FIELDS)
+    cover = np.zeros(h.rows + 128, np.int32)
+    for q_row0, q_rows, q_local0, own_row0, own_len, pre_row0, pre_len, stat0 in qb:
+        cover[q_row0:q_row0 + q_rows] += 1
+        assert q_row0 == own_row0 + q_local0 and q_local0 + q_rows <= own_len and stat0 == q_row0
+    stored = real if ragged else h.rows
+    assert (cover[:stored] == 1).all() and cover[stored:].sum() == 0
+    kbk = a["kblocks"].reshape(-1, packing.KB_FIELDS)
+    assert sum(int(k[1]) for k in kbk) == (h.part_rows if stored else 0)
+    used = np.zeros(h.part_rows, np.int32)
+    for r in range(h.rows):
+        for prow in a["red_list"][a["red_start"][r]:a["red_start"][r + 1]]:
+            used[prow] += 1
+    assert (used[:sum(int(k[1]) for k in kbk)] == 1).all()
+    for k_row0, k_rows, k_local0, q_row0, q_len, causal, stat0, out_row0 in kbk:
+        assert q_len > 0 and k_rows > 0
+        for rr in (0, k_rows - 1):   # the slab rows of this block are reduced into the block's own key rows
+            assert out_row0 + rr in a["red_list"][a["red_start"][k_row0 + rr]:a["red_start"][k_row0 + rr + 1]]
