@@ -216,6 +216,7 @@ inline int pair_tail_split(long long tiles, int clusters, int kb_total) {
   return S;
 }
 
+int gemm_dispatch(const GemmArgs& a, cudaStream_t stream);             // gemm_tcgen05.cu
 int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream);  // gemm2_tcgen05.cu
 void gemm_pair_set_tail_split(int enable);
 bool gemm_pair_enabled();

@@ -18,7 +18,7 @@
 //   (block diagonal).  Backward GEMMs read W / Acat / Bcat as stored through MN-major UMMA descriptors
 //   (no transposed copies, no transposed dequant).
 #include <stdlib.h>
-#include "common.cuh"
+#include "gemm_common.cuh"
 #include "b200rl.h"
 #include <vector>
 #include <string.h>
@@ -26,30 +26,8 @@
 
 namespace b200rl {
 
-// from the other translation units
-struct GemmArgs {
-  const void *A1, *B1, *A2, *B2;
-  long long lda1, ldb1, lda2, ldb2;
-  int K1, K2;
-  void* C;
-  long long ldc;
-  int c_fp32;
-  const void* bias;
-  const void* residual;
-  long long ldr;
-  float alpha;
-  int M, N;
-  int mn_major;
-  int splits;
-  long long c_split_stride;
-  int force_bn;
-  int max_ctas;
-  int fuse = 0;          // keep in sync with gemm_common.cuh
-  void* aux = nullptr;
-  long long ld_aux = 0;
-};
+// from the other translation units (GemmArgs / gemm_fuse_supported: gemm_common.cuh)
 int gemm_dispatch(const GemmArgs& a, cudaStream_t stream);
-bool gemm_fuse_supported(int M, int I);
 int dw_grouped_splits(int total_m_blocks, int kb_total);
 int dw_grouped_dispatch(int nprob, const void* const* Y, const long long* ldy, const int* rows, const void* const* U,
                         const long long* ldu, float* const* C, const long long* split_stride, int tokens, int splits,
