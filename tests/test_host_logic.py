@@ -179,3 +179,64 @@ def test_packing_descriptors_are_consistent(ragged, seed):
         assert q_len > 0 and k_rows > 0
         for rr in (0, k_rows - 1):   # the slab rows of this block are reduced into the block's own key rows
             assert out_row0 + rr in a["red_list"][a["red_start"][k_row0 + rr]:a["red_start"][k_row0 + rr + 1]]
+
+
+# ---------------------------------------------------------------------------------------------------
+# pass planning of compute_loss (learner.py): which sequences go into which model pass, with which scaling
+# ---------------------------------------------------------------------------------------------------
+class _RecordingPolicy:
+    """Stands in for Policy on a machine without a GPU: records every microbatch call of compute_loss."""
+
+    class _Cfg:
+        head_dim = 64
+
+    def __init__(self, max_batch):
+        self.cfg, self.max_batch, self.device = self._Cfg(), max_batch, torch.device("cpu")
+        self.loss_accum = torch.zeros(1, dtype=torch.float64)
+        self.calls = []
+
+    def zero_grad(self):
+        self.calls.append(("zero_grad",))
+
+    def microbatch(self, ids, am, ansm, adv, P, T, nb, grpo, backward, lp_out=None, lora_off=False, ref_lp=None, kl_beta=0.0):
+        self.calls.append(("mb", ids.clone(), None if adv is None else adv.clone(), nb, grpo, backward, lora_off, kl_beta))
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_compute_loss_pass_planning(k):
+    """reference loop: distributed_actor.py:354-389 / :452-487 (micro-batches of train_batch_size, skip predicate :367,
+    1/nb scaling with skipped batches still counted).  Fused passes carry k full micro-batches with advantages x k."""
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer
+    B, P, T, n = 4, 6, 8, 22                       # 6 micro-batches: 5 full + one of 2
+    rng = np.random.default_rng(0)
+    prompts = [rng.integers(1, 50, size=int(rng.integers(1, P + 1))).tolist() for _ in range(n)]
+    answers = [rng.integers(1, 50, size=int(rng.integers(1, T + 1))).tolist() for _ in range(n)]
+    rewards = rng.normal(size=n)
+    rewards[9] = 0.0                                # micro-batch 2 (sequences 8..11) is skipped (quirk Q1)
+    pol = _RecordingPolicy(max_batch=k * B)
+    ln = GRPOLearner(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5,
+                                           "share_prompts": False, "kl_beta": 0.5})
+    ln._h2d = lambda t: t.contiguous()              # no pinned memory without CUDA
+    assert ln.fuse_microbatches == k
+    ln.compute_loss(prompts, answers, list(rewards))
+    assert pol.calls[0] == ("zero_grad",)
+    ref_ids, _, _ = lo.pad_batch(prompts, answers, P, T)
+    seen, nb = [], 6
+    train = [c for c in pol.calls[1:] if c[5]]      # backward passes
+    score = [c for c in pol.calls[1:] if not c[5]]  # KL reference passes (adapter off), one per training pass
+    assert len(train) == len(score) and all(c[6] for c in score) and not any(c[6] for c in train)
+    for c in train:
+        _, ids, adv, nb_c, grpo, backward, lora_off, beta = c
+        rows = ids.shape[0]
+        kk = rows // B if rows % B == 0 else 1
+        assert nb_c == nb and grpo and kk <= k
+        # which sequences: match the padded rows back to the batch
+        idx = [int(np.flatnonzero((ref_ids.numpy() == ids[r].numpy()).all(1))[0]) for r in range(rows)]
+        assert idx == sorted(idx) and not (set(idx) & set(range(8, 12)))
+        assert all(len({j // B for j in idx[g * B:(g + 1) * B]}) == 1 for g in range(kk))   # whole micro-batches only
+        np.testing.assert_allclose(adv.numpy(), rewards[idx] * kk, rtol=0, atol=0)
+        assert beta == 0.5 * kk
+        seen += idx
+    assert sorted(seen) == [j for j in range(n) if not 8 <= j < 12]
+    # the ragged last micro-batch (2 sequences) is never fused
+    assert any(c[1].shape[0] == 2 for c in train)
