@@ -241,6 +241,13 @@ def main():
     group = None
     kw = {}
     FK = max(1, args.fuse_microbatches)
+    try:   # long-sequence configs (T = 2048: 38k rows per fused pass) may not leave room for 2 micro-batches per pass
+        from distrl_llm_b200.policy import largest_pass_that_fits
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        FK = largest_pass_that_fits(cfg, B, P, T, FK, free_b, reserve_bytes=24 << 30)   # NF4 + bf16 cache + lm_head/embed
+        args.fuse_microbatches = FK
+    except Exception as e:  # sizing is best-effort; the allocation itself still fails loudly
+        print(f"[bench] pass sizing skipped: {e}", file=sys.stderr)
     if world > 1:
         group, kw = P2PGroup.from_torch_distributed(cfg, FK * B, P, T, dev)
     pol = Policy.random_init(cfg, dev, FK * B, P, T, seed=1234, **kw)   # same base + LoRA on every learner

@@ -84,6 +84,24 @@ def tensor_from_ptr(ptr_, numel, dtype, device):
     return torch.as_tensor(_RawCuda(ptr_, nbytes), device=device).view(dtype)
 
 
+def workspace_bytes(cfg: "LMConfig", max_batch, P, T):
+    """Activation workspace a Policy(cfg, max_batch, P, T) allocates (b200rl_model_workspace_bytes; host-only call)."""
+    _capi.load_library()
+    L = P + T
+    ccfg = ModelConfig(cfg.vocab, cfg.hidden, cfg.inter, cfg.n_layers, cfg.n_q_heads, cfg.n_kv_heads, cfg.head_dim,
+                       cfg.lora_r, cfg.lora_scale, cfg.rms_eps, cfg.rope_theta, max_batch * L, max_batch, L, max_batch * T)
+    return int(lib().b200rl_model_workspace_bytes(C.byref(ccfg)))
+
+
+def largest_pass_that_fits(cfg: "LMConfig", micro_batch, P, T, want, free_bytes, reserve_bytes=0):
+    """Largest k <= want such that the workspace of k micro-batches per pass fits in 80 % of what is left of
+    free_bytes after reserve_bytes (weights, cache, optimizer state)."""
+    k = max(1, int(want))
+    while k > 1 and workspace_bytes(cfg, k * micro_batch, P, T) > 0.8 * (free_bytes - reserve_bytes):
+        k -= 1
+    return k
+
+
 class Policy:
     """NF4 base + LoRA causal LM on one GPU. `lora_flat` layout (fp32), matching csrc/model.cu:
     for layer in layers: for mod in (q,k,v,o,gate,up,down): A [r, in] then B [out, r]."""
