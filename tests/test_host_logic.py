@@ -240,3 +240,36 @@ def test_compute_loss_pass_planning(k):
     assert sorted(seen) == [j for j in range(n) if not 8 <= j < 12]
     # the ragged last micro-batch (2 sequences) is never fused
     assert any(c[1].shape[0] == 2 for c in train)
+
+
+def test_from_pretrained_reads_config_and_safetensors(tmp_path, monkeypatch):
+    """Policy.from_pretrained: config.json -> LMConfig, all *.safetensors shards merged, handed to from_hf_state_dict
+    (the GPU part — NF4 quantisation + model creation — is covered by test_hf_state_dict_loader_vs_transformers)."""
+    import json
+    from safetensors.torch import save_file
+    from distrl_llm_b200.policy import LMConfig, Policy
+    hf = {"vocab_size": 512, "hidden_size": 128, "intermediate_size": 256, "num_hidden_layers": 2,
+          "num_attention_heads": 2, "num_key_value_heads": 1, "rms_norm_eps": 1e-5,
+          "rope_parameters": {"rope_theta": 123456.0, "rope_type": "default"}}
+    (tmp_path / "config.json").write_text(json.dumps(hf))
+    save_file({"model.embed_tokens.weight": torch.zeros(512, 128), "model.norm.weight": torch.ones(128)},
+              str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file({"model.layers.0.self_attn.q_proj.weight": torch.zeros(128, 128)},
+              str(tmp_path / "model-00002-of-00002.safetensors"))
+    got = {}
+
+    def fake(cls, cfg, sd, device, max_batch, P, T, **kw):
+        got.update(cfg=cfg, keys=sorted(sd), device=device, mb=max_batch, P=P, T=T, kw=kw)
+        return "policy"
+
+    monkeypatch.setattr(Policy, "from_hf_state_dict", classmethod(fake))
+    pol, cfg = Policy.from_pretrained(str(tmp_path), "cuda:0", 4, 16, 32, lora_r=8, lora_alpha=32.0, lora_seed=3)
+    assert pol == "policy" and cfg is got["cfg"]
+    assert cfg == LMConfig(vocab=512, hidden=128, inter=256, n_layers=2, n_q_heads=2, n_kv_heads=1, head_dim=64,
+                           lora_r=8, lora_alpha=32.0, rms_eps=1e-5, rope_theta=123456.0)
+    assert got["keys"] == ["model.embed_tokens.weight", "model.layers.0.self_attn.q_proj.weight", "model.norm.weight"]
+    assert (got["mb"], got["P"], got["T"], got["kw"]) == (4, 16, 32, {"lora_seed": 3})
+    with pytest.raises(FileNotFoundError):
+        (tmp_path / "empty").mkdir()
+        (tmp_path / "empty" / "config.json").write_text(json.dumps(hf))
+        Policy.from_pretrained(str(tmp_path / "empty"), "cuda:0", 4, 16, 32)
