@@ -6,8 +6,10 @@ Contract: python bench.py --gpus N --steps K --warmup W [--impl reference]
 
 Workload (BASELINE.json configs[1]): GRPO learner, Qwen2.5-7B-shaped random-init NF4 base + rank-16
 LoRA, group_size 8, 64 completions of length 512 (P=350 prompt tokens, micro-batch 8 -> 8 micro-batches),
-per GPU.  A "step" = one learner update: zero_grad, 8x (forward, fused log-prob/loss, backward into LoRA
-grads), (P2P reduce +) Adam on the LoRA parameters, refresh of the bf16 LoRA operands.
+per GPU.  A "step" = one learner update: zero_grad, the 8 reference micro-batches (forward, fused log-prob/loss,
+backward into LoRA grads) as 4 model passes of 2 micro-batches each (--fuse_microbatches; gradient accumulation is
+linear, identical result) in the packed shared-prompt layout, (P2P reduce +) Adam on the LoRA parameters, refresh of
+the bf16 LoRA operands.
   value  : completion tokens scored+updated / s with the batch already resident in HBM
   e2e    : same through the reference-shaped public API GRPOLearner.train(candidates) with HOST
            token-id lists (CPU padding + pinned H2D copies + D2H of the loss inside the timed region)

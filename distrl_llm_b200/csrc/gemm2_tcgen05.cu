@@ -11,7 +11,8 @@
 //                                      both CTAs' TMA loads complete_tx on the LEADER's barrier
 //   empty[s]  (each CTA, count 1)    : tcgen05.commit.cta_group::2 ... multicast to both CTAs
 //   tmem_full[a]  (each CTA, count 1): multicast commit after the last k-block of a tile
-//   tmem_empty[a] (leader, count 8)  : one arrive per epilogue warp of both CTAs (peer arrives remotely)
+//   tmem_empty[a] (leader, count 2 EW): one arrive per epilogue warp of both CTAs (peer arrives remotely); EW = 4,
+//                                      or 8 for the fused SwiGLU epilogues (FUSE 1 / 2, see GemmArgs::fuse)
 //
 // Tail split: with T tiles on P CTA pairs the last wave holds r = T mod P tiles (Qwen2.5-7B, M = 4446: the N = 3584
 // GEMMs have 252 tiles on 74 pairs -> 3.4 waves, the 4th wave is 40 % full).  When 0 < r <= P/2 the last r tiles are

@@ -1,6 +1,8 @@
 // C++ host driver of the learner hot path: Qwen2-style causal LM (NF4 base + LoRA on
 // q,k,v,o,gate,up,down) forward -> per-token log-probs -> PG/GRPO loss -> backward into the flat
-// fp32 LoRA gradient buffer.  One call = one micro-batch of the reference's hot loop.
+// fp32 LoRA gradient buffer.  One call = one pass over k micro-batches of the reference's hot loop, in the classic
+// [B, P+T] layout (b200rl_model_microbatch) or the packed shared-prompt / ragged layout built by
+// distrl_llm_b200/packing.py (b200rl_model_microbatch_packed).
 //
 // Reference being replaced (file:line in /root/reference):
 //   BaseLearner.compute_current_policy_probs   distributed_actor.py:215-261
