@@ -238,14 +238,36 @@ class BaseLearner:
         return self.generator.generate(messages, sampling_params)
 
     def save_checkpoint(self, path):
-        """(:263-264) LoRA adapter state dict with PEFT names."""
+        """(:263-264) `self.policy.save_pretrained(path)` on a PEFT model = an adapter directory.  Written here in the
+        same on-disk format (adapter_model.safetensors with PEFT's saved key names + adapter_config.json), plus the
+        torch-pickled dict with the in-memory names the gradient exchange uses (T2)."""
         import os
         os.makedirs(path, exist_ok=True)
-        torch.save(self.policy.lora_state_dict(), os.path.join(path, "adapter_model.pt"))
+        sd = self.policy.lora_state_dict()
+        torch.save(sd, os.path.join(path, "adapter_model.pt"))
+        write_peft_adapter(path, sd, self.policy.cfg, base_model=getattr(self, "model_name", None))
 
     def save_adapter(self):
-        """(:84-86)"""
+        """(:84-86) `save_lora(self.policy, self.lora_save_path)`: the directory the generators' vLLM engines load the
+        current adapter from (`load_lora`, :150)."""
         self.save_checkpoint(self.lora_save_path)
+
+
+def write_peft_adapter(path, lora_state, cfg, base_model=None):
+    """PEFT adapter directory from {in-memory PEFT name: tensor}: `...lora_A.default.weight` is stored as
+    `...lora_A.weight` (PEFT strips the adapter name on save), fp32 tensors, and the adapter_config.json vLLM / PEFT
+    need to rebuild the LoRA (r, alpha, target modules; helper.py:25-45)."""
+    import json
+    import os
+    from safetensors.torch import save_file
+    tensors = {k.replace(".default.weight", ".weight"): v.detach().to(torch.float32).contiguous().cpu() for k, v in lora_state.items()}
+    save_file(tensors, os.path.join(path, "adapter_model.safetensors"), metadata={"format": "pt"})
+    conf = {"peft_type": "LORA", "task_type": "CAUSAL_LM", "base_model_name_or_path": base_model, "inference_mode": True,
+            "r": int(cfg.lora_r), "lora_alpha": float(cfg.lora_alpha), "lora_dropout": 0.0, "bias": "none",
+            "fan_in_fan_out": False, "init_lora_weights": True, "modules_to_save": None, "use_rslora": False,
+            "target_modules": ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"]}
+    with open(os.path.join(path, "adapter_config.json"), "w") as f:
+        json.dump(conf, f, indent=1)
 
 
 class Learner(BaseLearner):

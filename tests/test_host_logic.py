@@ -273,3 +273,27 @@ def test_from_pretrained_reads_config_and_safetensors(tmp_path, monkeypatch):
         (tmp_path / "empty").mkdir()
         (tmp_path / "empty" / "config.json").write_text(json.dumps(hf))
         Policy.from_pretrained(str(tmp_path / "empty"), "cuda:0", 4, 16, 32)
+
+
+def test_adapter_directory_is_peft_format(tmp_path):
+    """save_checkpoint / save_adapter (reference distributed_actor.py:84-86, :263-264): PEFT adapter directory."""
+    import json
+    from safetensors.torch import load_file
+    from distrl_llm_b200.learner import write_peft_adapter
+    from distrl_llm_b200.policy import LMConfig, Policy
+    cfg = LMConfig(vocab=64, hidden=128, inter=256, n_layers=2, n_q_heads=2, n_kv_heads=1, head_dim=64, lora_r=8, lora_alpha=32.0)
+    shapes = cfg.module_shapes()
+    sd = {}
+    for i in range(cfg.n_layers):
+        for m, (fin, fout) in shapes.items():
+            sd[Policy.peft_name(i, m, "A")] = torch.randn(cfg.lora_r, fin)
+            sd[Policy.peft_name(i, m, "B")] = torch.randn(fout, cfg.lora_r)
+    write_peft_adapter(str(tmp_path), sd, cfg, base_model="unsloth/Qwen2.5-7B-Instruct")
+    conf = json.load(open(tmp_path / "adapter_config.json"))
+    assert (conf["peft_type"], conf["r"], conf["lora_alpha"], conf["bias"]) == ("LORA", 8, 32.0, "none")
+    assert sorted(conf["target_modules"]) == sorted(["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"])
+    got = load_file(str(tmp_path / "adapter_model.safetensors"))
+    assert len(got) == 2 * 7 * cfg.n_layers
+    k = "base_model.model.model.layers.1.mlp.down_proj.lora_B.weight"
+    assert k in got and torch.equal(got[k], sd[Policy.peft_name(1, "down", "B")])
+    assert got["base_model.model.model.layers.0.self_attn.q_proj.lora_A.weight"].shape == (8, 128)
