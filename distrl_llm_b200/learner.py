@@ -247,10 +247,34 @@ class BaseLearner:
         torch.save(sd, os.path.join(path, "adapter_model.pt"))
         write_peft_adapter(path, sd, self.policy.cfg, base_model=getattr(self, "model_name", None))
 
+    def load_checkpoint(self, path):
+        """Resume the adapter from a directory written by save_checkpoint / PEFT (the reference has no resume path,
+        README TODO).  Optimizer moments restart from zero."""
+        sd, conf = read_peft_adapter(path)
+        if int(conf.get("r", self.policy.cfg.lora_r)) != self.policy.cfg.lora_r:
+            raise ValueError(f"adapter rank {conf.get('r')} != policy rank {self.policy.cfg.lora_r}")
+        self.policy.load_lora_state(sd)
+
     def save_adapter(self):
         """(:84-86) `save_lora(self.policy, self.lora_save_path)`: the directory the generators' vLLM engines load the
         current adapter from (`load_lora`, :150)."""
         self.save_checkpoint(self.lora_save_path)
+
+
+def read_peft_adapter(path):
+    """Inverse of write_peft_adapter: {in-memory PEFT name (`...lora_A.default.weight`): fp32 CPU tensor} and the
+    adapter_config dict, from a PEFT adapter directory (also one written by PEFT / the reference itself)."""
+    import json
+    import os
+    from safetensors.torch import load_file
+    conf = json.load(open(os.path.join(path, "adapter_config.json")))
+    raw = load_file(os.path.join(path, "adapter_model.safetensors"))
+    out = {}
+    for k, v in raw.items():
+        if k.endswith(".lora_A.weight") or k.endswith(".lora_B.weight"):
+            k = k[:-len("weight")] + "default.weight"
+        out[k] = v.to(torch.float32)
+    return out, conf
 
 
 def write_peft_adapter(path, lora_state, cfg, base_model=None):

@@ -397,5 +397,19 @@ class Policy:
             out[self.peft_name(i, m, ab)] = flat[off:off + shp[0] * shp[1]].view(*shp)
         return out
 
+    def load_lora_state(self, state: dict):
+        """Copy {PEFT name: tensor} into the flat fp32 master buffer (every LoRA tensor must be present, shapes must
+        match) and refresh the bf16 operand copies."""
+        views = self.named_views(self.lora_flat)
+        missing = [k for k in views if k not in state]
+        if missing:
+            raise KeyError(f"adapter state lacks {len(missing)} tensors, e.g. {missing[0]}")
+        for k, v in views.items():
+            t = state[k]
+            if tuple(t.shape) != tuple(v.shape):
+                raise ValueError(f"{k}: shape {tuple(t.shape)} != {tuple(v.shape)}")
+            v.copy_(t.to(device=v.device, dtype=torch.float32))
+        self.sync_lora()
+
     def lora_state_dict(self):
         return {k: v.detach().cpu().clone() for k, v in self.named_views(self.lora_flat).items()}

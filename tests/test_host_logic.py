@@ -297,3 +297,7 @@ def test_adapter_directory_is_peft_format(tmp_path):
     k = "base_model.model.model.layers.1.mlp.down_proj.lora_B.weight"
     assert k in got and torch.equal(got[k], sd[Policy.peft_name(1, "down", "B")])
     assert got["base_model.model.model.layers.0.self_attn.q_proj.lora_A.weight"].shape == (8, 128)
+    # round trip back to the in-memory names (load_checkpoint)
+    from distrl_llm_b200.learner import read_peft_adapter
+    back, conf2 = read_peft_adapter(str(tmp_path))
+    assert conf2["r"] == 8 and set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
