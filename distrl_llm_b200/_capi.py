@@ -78,6 +78,8 @@ SIGNATURES = {
     "b200rl_lora_reduce_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll,
                                          c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_void_p]),
     "b200rl_p2p_barrier": (c_int, [c_void_p, c_int, c_int, c_uint, c_void_p]),
+    "b200rl_p2p_barrier_timeout": (c_int, [c_void_p, c_int, c_int, c_uint, C.c_double, c_void_p]),
+    "b200rl_p2p_status": (c_int, [c_int]),
     "b200rl_p2p_alloc": (c_int, [c_ll, C.POINTER(c_void_p), c_void_p]),
     "b200rl_p2p_open": (c_int, [c_void_p, C.POINTER(c_void_p)]),
     "b200rl_p2p_close": (c_int, [c_void_p]),

@@ -38,21 +38,42 @@ struct AdamArgs {
   float neg_step;             // -(lr / (1 - beta1^t))
   float decay;                // 1 - lr * weight_decay (AdamW), 1.0 for Adam
   int zero_local_grad;        // world == 1: clear the gradient in the same pass
+  const volatile int* status; // world > 1: the group's status word; non-zero (a barrier timed out) = do nothing
 };
 
+// WORLD > 0: compile-time learner count, so that all WORLD peer loads of an element are in flight together (a remote
+// load is ~2 us of NVLink latency; issued one after the other they serialise).  WORLD == 0: generic loop.
+template <int WORLD>
 __global__ void __launch_bounds__(256) reduce_adam_kernel(const AdamArgs a) {
+  const int world = WORLD > 0 ? WORLD : a.world;
+  if (world > 1 && a.status) {   // a peer never arrived at the barrier: leave every buffer untouched
+    __shared__ int gave_up;
+    if (threadIdx.x == 0) gave_up = *a.status;   // host-mapped word: one PCIe read per block
+    __syncthreads();
+    if (gave_up != 0) return;
+  }
   const long long n4 = (a.hi - a.lo) / 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const long long e = a.lo + i * 4;
     // one-shot reduce: read this slice from every learner's gradient buffer (NVLink loads),
     // summed in rank order so every run gives the same bits
-    float4 g = *reinterpret_cast<const float4*>(a.g[0] + e);
-    for (int r = 1; r < a.world; ++r) {
-      const float4 t = *reinterpret_cast<const float4*>(a.g[r] + e);
-      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    float4 g;
+    if constexpr (WORLD > 0) {
+      float4 t[WORLD];
+#pragma unroll
+      for (int r = 0; r < WORLD; ++r) t[r] = *reinterpret_cast<const float4*>(a.g[r] + e);
+      g = t[0];
+#pragma unroll
+      for (int r = 1; r < WORLD; ++r) { g.x += t[r].x; g.y += t[r].y; g.z += t[r].z; g.w += t[r].w; }
+    } else {
+      g = *reinterpret_cast<const float4*>(a.g[0] + e);
+      for (int r = 1; r < world; ++r) {
+        const float4 t = *reinterpret_cast<const float4*>(a.g[r] + e);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
     }
-    if (a.world > 1) { g.x *= a.inv_world; g.y *= a.inv_world; g.z *= a.inv_world; g.w *= a.inv_world; }
+    if (world > 1) { g.x *= a.inv_world; g.y *= a.inv_world; g.z *= a.inv_world; g.w *= a.inv_world; }
     float4 p = *reinterpret_cast<float4*>(a.p + e);
     float4 m = *reinterpret_cast<float4*>(a.m + e);
     float4 v = *reinterpret_cast<float4*>(a.v + e);
@@ -68,9 +89,11 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const AdamArgs a) {
     }
     *reinterpret_cast<float4*>(a.m + e) = m;
     *reinterpret_cast<float4*>(a.v + e) = v;
-    if (a.world > 1) {
+    if (world > 1) {
       // all-gather by store: push the updated slice into every learner's parameter buffer
-      for (int r = 0; r < a.world; ++r) *reinterpret_cast<float4*>(a.p_peer[r] + e) = p;
+#pragma unroll
+      for (int r = 0; r < (WORLD > 0 ? WORLD : MAX_PEERS); ++r)
+        if (r < world) *reinterpret_cast<float4*>(a.p_peer[r] + e) = p;
     } else {
       *reinterpret_cast<float4*>(a.p + e) = p;
       if (a.zero_local_grad)
@@ -81,12 +104,22 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const AdamArgs a) {
 
 // Cross-GPU barrier on peer-mapped flag arrays. flags_peer[r] points at learner r's flag array
 // (uint32[MAX_PEERS]); learner `rank` writes `epoch` into slot `rank` of every peer, then waits
-// until all slots of its own array reached `epoch`.
+// until all slots of its own array reached `epoch`.  A peer that does not arrive within timeout_ns does NOT take the
+// CUDA context down: the waiter records (1 + the missing rank) in the group's status word (host-visible) and returns;
+// the following reduce kernel sees the word and leaves every buffer untouched, and the host turns the word into an
+// error at its next check (b200rl_p2p_status).
 struct BarrierArgs {
   unsigned int* flags_peer[MAX_PEERS];
   int world, rank;
   unsigned int epoch;
+  unsigned long long timeout_ns;
+  volatile int* status;
 };
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __global__ void p2p_barrier_kernel(const BarrierArgs a) {
   const int t = threadIdx.x;
   if (t < a.world) {
@@ -95,12 +128,15 @@ __global__ void p2p_barrier_kernel(const BarrierArgs a) {
     *dst = a.epoch;
     __threadfence_system();
     volatile unsigned int* mine = a.flags_peer[a.rank] + t;
-    long long t0 = clock64();
+    const unsigned long long t0 = global_ns();
+    unsigned int spins = 0;
     while ((int)(*mine - a.epoch) < 0) {
-      if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; fail instead of hanging the box
-        printf("b200rl: p2p barrier timed out (rank %d waiting for %d, epoch %u)\n", a.rank, t,
-               a.epoch);
-        __trap();
+      if ((++spins & 1023u) == 0) {
+        if (a.status && *a.status != 0) break;   // another lane / an earlier barrier already gave up
+        if (global_ns() - t0 > a.timeout_ns) {
+          if (a.status) *a.status = 1 + t;
+          break;
+        }
       }
     }
     __threadfence_system();
@@ -161,6 +197,31 @@ __global__ void lora_grad_accum_kernel(float* __restrict__ flat, const UnpackDes
 using namespace b200rl;
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
 
+// Status word of the multi-learner exchange: one per process, in mapped pinned host memory so that a timed-out barrier
+// kernel can report without killing the context.  0 = fine, k > 0 = learner k-1 never reached a barrier.
+static volatile int* g_p2p_status_host = nullptr;
+static int* g_p2p_status_dev = nullptr;
+static int p2p_status_init() {
+  if (g_p2p_status_host) return 0;
+  void* h = nullptr;
+  B200RL_CUDA_OK(cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(h, 0, 64);
+  void* d = nullptr;
+  B200RL_CUDA_OK(cudaHostGetDevicePointer(&d, h, 0));
+  g_p2p_status_host = (volatile int*)h;
+  g_p2p_status_dev = (int*)d;
+  return 0;
+}
+static double p2p_timeout_s() {
+  static double t = -1.0;
+  if (t < 0) {
+    const char* e = getenv("B200RL_P2P_TIMEOUT_S");
+    t = e ? atof(e) : 600.0;   // long enough for a peer that is still loading weights or running a long step
+    if (!(t > 0)) t = 600.0;
+  }
+  return t;
+}
+
 // Single- or multi-learner fused (reduce +) Adam(W). `grads` / `params_peer` are arrays of `world`
 // device pointers (host memory) in rank order; for world == 1 pass the local buffers.
 extern "C" int b200rl_lora_reduce_adamw(float* p, float* m, float* v, const float* const* grads,
@@ -179,6 +240,12 @@ extern "C" int b200rl_lora_reduce_adamw(float* p, float* m, float* v, const floa
     a.p_peer[r] = (r < world && params_peer) ? params_peer[r] : nullptr;
   }
   if (world > 1) B200RL_REQUIRE(params_peer != nullptr, "reduce_adamw: world > 1 needs params_peer");
+  a.status = nullptr;
+  if (world > 1) {
+    int rc = p2p_status_init();
+    if (rc) return rc;
+    a.status = g_p2p_status_dev;
+  }
   a.world = world;
   // owned slice: contiguous, 4-element aligned
   const long long n4 = n / 4;
@@ -201,21 +268,46 @@ extern "C" int b200rl_lora_reduce_adamw(float* p, float* m, float* v, const floa
     long long blocks = (work + 255) / 256;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    reduce_adam_kernel<<<(unsigned)blocks, 256, 0, STREAM>>>(a);
+    const unsigned g = (unsigned)blocks;
+    switch (world) {
+      case 1: reduce_adam_kernel<1><<<g, 256, 0, STREAM>>>(a); break;
+      case 2: reduce_adam_kernel<2><<<g, 256, 0, STREAM>>>(a); break;
+      case 4: reduce_adam_kernel<4><<<g, 256, 0, STREAM>>>(a); break;
+      case 8: reduce_adam_kernel<8><<<g, 256, 0, STREAM>>>(a); break;
+      default: reduce_adam_kernel<0><<<g, 256, 0, STREAM>>>(a); break;
+    }
     B200RL_LAUNCH_OK();
   }
   return 0;
 }
 
-extern "C" int b200rl_p2p_barrier(unsigned int* const* flags_peer, int world, int rank,
-                                  unsigned int epoch, void* stream) {
+extern "C" int b200rl_p2p_barrier_timeout(unsigned int* const* flags_peer, int world, int rank,
+                                          unsigned int epoch, double timeout_s, void* stream) {
   B200RL_REQUIRE(flags_peer && world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world,
                  "p2p_barrier: bad args");
+  int rc = p2p_status_init();
+  if (rc) return rc;
   BarrierArgs a;
   for (int r = 0; r < MAX_PEERS; ++r) a.flags_peer[r] = r < world ? flags_peer[r] : nullptr;
   a.world = world; a.rank = rank; a.epoch = epoch;
+  if (!(timeout_s > 0)) timeout_s = p2p_timeout_s();
+  a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  a.status = g_p2p_status_dev;
   p2p_barrier_kernel<<<1, 32, 0, STREAM>>>(a);
   B200RL_LAUNCH_OK();
+  return 0;
+}
+extern "C" int b200rl_p2p_barrier(unsigned int* const* flags_peer, int world, int rank,
+                                  unsigned int epoch, void* stream) {
+  return b200rl_p2p_barrier_timeout(flags_peer, world, rank, epoch, 0.0, stream);
+}
+// 0 = every barrier so far completed; k > 0 = learner k-1 did not arrive in time (an error is recorded and returned as
+// B200RL_ERR_STATE).  Reads a host-mapped word: call after a stream / event synchronisation.  reset != 0 clears it.
+extern "C" int b200rl_p2p_status(int reset) {
+  if (!g_p2p_status_host) return 0;
+  const int s = *g_p2p_status_host;
+  if (reset) *g_p2p_status_host = 0;
+  if (s != 0) return set_error(B200RL_ERR_STATE, "p2p barrier timed out waiting for learner %d", s - 1);
   return 0;
 }
 

@@ -92,7 +92,7 @@ class BaseLearner:
         self.p2p = None  # set by enable_p2p() / p2p_open_handles()
         self._p2p_group = None
         self._p2p_handles = None
-        self._pinned = {}
+        self._stager = packing.PinnedStager(policy.device)   # reusable pinned staging for the per-pass H2D copies
 
     # ---- tokenise + pad (:217-239) ------------------------------------------------------------
     def _encode(self, messages, answers):
@@ -106,7 +106,7 @@ class BaseLearner:
         return ids, am, tok_ans["attention_mask"].to(torch.int32)
 
     def _h2d(self, t):
-        return t.contiguous().pin_memory().to(self.policy.device, non_blocking=True)
+        return self._stager.to_device(t)
 
     def compute_current_policy_probs(self, policy, messages, answers):
         """(:215-261) -> (action_log_probs [B,T] fp32, answer_mask [B,T]) on the device; scoring only."""
@@ -125,7 +125,7 @@ class BaseLearner:
     def _pack(self, ids, am):
         host = packing.pack_microbatch(ids.numpy(), am.numpy(), self.max_prompt_tokens, self.max_new_tokens,
                                        ragged=self.ragged_rows)
-        return packing.PackedDevice(host, self.policy.device)
+        return packing.PackedDevice(host, self.policy.device, stager=self._stager)
 
     # ---- loss + backward (:349-395 PG, :440-493 GRPO) ---------------------------------------------
     def compute_loss(self, messages, answers, rewards):
@@ -220,14 +220,31 @@ class BaseLearner:
     def enable_p2p(self, group):
         self.p2p = group
 
-    # Ray flow: the policy was built on buffers from P2PGroup.alloc_local(); the driver
-    # gathers every learner's handles with p2p_export_handles() and broadcasts them to p2p_open_handles().
+    # Ray flow: create_for_p2p() builds the policy on IPC-exportable buffers; the driver gathers every
+    # learner's handles with p2p_export_handles() and broadcasts the list to p2p_open_handles().  Those two RPC rounds
+    # are also the host-side rendezvous that keeps the GPU flag barrier of attach() short.
+    @classmethod
+    def create_for_p2p(cls, rank, world, device, build_policy, tokenizer, config, numel, **kw):
+        """Learner `rank` of `world` for the fused P2P reduce + Adam exchange.  `numel` = p2p.lora_numel(cfg, ...);
+        `build_policy(lora_flat=..., lora_grad=...)` must construct the Policy on the given buffers (e.g.
+        `lambda **b: Policy.random_init(cfg, device, max_batch, P, T, **b)`)."""
+        from .p2p import P2PGroup
+        group = P2PGroup(rank, world, device)
+        handles, bufs = group.alloc_local(numel)
+        self = cls(build_policy(**bufs), tokenizer, config, gpu_id=rank, **kw)
+        self._p2p_group, self._p2p_handles = group, handles
+        return self
+
     def p2p_export_handles(self):
+        if self._p2p_handles is None:
+            raise RuntimeError("this learner was not built with create_for_p2p(): it has no exportable buffers")
         return self._p2p_handles
 
-    def p2p_open_handles(self, all_handles):
+    def p2p_open_handles(self, all_handles, host_rendezvous=None):
+        if self._p2p_group is None:
+            raise RuntimeError("this learner was not built with create_for_p2p()")
         self._p2p_group.open_peers(all_handles)
-        self._p2p_group.attach(self.policy)
+        self._p2p_group.attach(self.policy, host_rendezvous=host_rendezvous)
         self.p2p = self._p2p_group
 
     # ---- misc actor surface --------------------------------------------------------------------------

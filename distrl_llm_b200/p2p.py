@@ -43,6 +43,7 @@ class P2PGroup:
         self.peers = {}    # name -> [pointer on every rank]
         self._opened = []
         self.numel = 0
+        self.last_timing = None   # CUDA events of the last reduce_adam_step(timing=True)
 
     # ---- phase 1 ---------------------------------------------------------------------------------
     def alloc_local(self, numel):
@@ -76,6 +77,15 @@ class P2PGroup:
                     ptrs.append(q.value)
             self.peers[name] = ptrs
 
+    @staticmethod
+    def wire_same_process(groups):
+        """Several 'learners' living in ONE process on one device (tests: fake multi-GPU on a single GPU, one stream per
+        rank): peer pointers are the other groups' local pointers, no IPC handle involved."""
+        for g in groups:
+            assert g.world == len(groups)
+            for name in _NAMES:
+                g.peers[name] = [h.local[name] for h in groups]
+
     @classmethod
     def from_torch_distributed(cls, cfg, max_batch, P, T, device):
         """torchrun path (bench.py): exchange the handles with all_gather_object."""
@@ -87,34 +97,87 @@ class P2PGroup:
         g.open_peers(allh)
         return g, kw
 
-    def attach(self, policy: Policy):
+    def attach(self, policy: Policy, host_rendezvous=None):
+        """Called once every learner has built its policy on the buffers of alloc_local().  Learners reach this point at
+        very different times (weight loading, NF4 quantisation), so rendezvous on the HOST first when a host-side barrier
+        is available (`host_rendezvous` callable; default: torch.distributed's barrier when a process group exists; under
+        Ray the driver's two-phase RPC sequence of INTEGRATION.md is that rendezvous) and only then on the GPU flags."""
         assert policy.lora_flat.data_ptr() == self.local["params"]
+        if host_rendezvous is None:
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() == self.world:
+                    host_rendezvous = dist.barrier
+            except Exception:  # pragma: no cover
+                host_rendezvous = None
+        if host_rendezvous is not None:
+            torch.cuda.synchronize(self.device)
+            host_rendezvous()
         self.barrier()  # every learner finished initialising its parameters
 
     def _ptr_array(self, name):
         return (C.c_void_p * self.world)(*self.peers[name])
 
-    def barrier(self):
+    def barrier(self, timeout_s=0.0):
+        """GPU-side flag barrier on this stream.  A peer that does not arrive within timeout_s (0 = B200RL_P2P_TIMEOUT_S,
+        default 600 s) is reported by check() instead of trapping the CUDA context."""
         self.epoch += 1
-        check(lib().b200rl_p2p_barrier(C.cast(self._ptr_array("flags"), C.c_void_p), self.world, self.rank,
-                                       self.epoch, stream()), "p2p_barrier")
+        check(lib().b200rl_p2p_barrier_timeout(C.cast(self._ptr_array("flags"), C.c_void_p), self.world, self.rank,
+                                               self.epoch, float(timeout_s), stream()), "p2p_barrier")
 
-    def reduce_adam_step(self, policy: Policy, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+    def check(self, reset=False):
+        """Raise if a barrier of this process timed out (call after a synchronisation; the loss .item() of a step is one)."""
+        check(lib().b200rl_p2p_status(1 if reset else 0), "p2p_status")
+
+    def reduce_adam_step(self, policy: Policy, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, timing=False):
+        """barrier -> fused P2P reduce + Adam(W) + write-back -> barrier -> zero_grad + bf16 operand refresh.
+        timing=True records CUDA events around the three phases on this stream (read them with exchange_ms())."""
         policy.opt_step += 1
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timing else None
+        if ev:
+            ev[0].record()
         self.barrier()   # all learners' gradients are complete
+        if ev:
+            ev[1].record()
         check(lib().b200rl_lora_reduce_adamw(
             policy.lora_flat.data_ptr(), policy.adam_m.data_ptr(), policy.adam_v.data_ptr(),
             C.cast(self._ptr_array("grads"), C.c_void_p), C.cast(self._ptr_array("params"), C.c_void_p),
             self.world, self.rank, self.numel, policy.opt_step, lr, betas[0], betas[1], eps, weight_decay, 0,
             stream()), "lora_reduce_adamw")
         self.barrier()   # every peer has read my gradients and written its slice of my parameters
+        if ev:
+            ev[2].record()
         policy.lora_grad.zero_()
         policy.sync_lora()
+        if ev:
+            ev[3].record()
+            self.last_timing = ev
 
-    def close(self):
+    def exchange_ms(self):
+        """(wait for the slowest learner, reduce + Adam + write-back + closing barrier, zero_grad + operand refresh) in ms
+        for the last reduce_adam_step(timing=True); synchronises on the last event."""
+        ev = self.last_timing
+        if ev is None:
+            return None
+        ev[3].synchronize()
+        return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+
+    def nvlink_bytes_per_step(self):
+        """Bytes this learner moves over NVLink per step: loads of its slice from world-1 peers + stores to world-1 peers."""
+        lo, hi = owned_slice(self.numel, self.world, self.rank)
+        return 2 * (self.world - 1) * (hi - lo) * 4
+
+    def close(self, free_local=True):
+        """Unmap the peers' buffers and (free_local) release this learner's own allocations.  The policy built on them
+        must not be used afterwards."""
         for p in self._opened:
             lib().b200rl_p2p_close(p)
         self._opened = []
+        if free_local:
+            for name, p in list(self.local.items()):
+                lib().b200rl_p2p_free(p)
+            self.local = {}
+        self.peers = {}
 
 
 def owned_slice(n, world, rank):

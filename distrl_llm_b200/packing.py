@@ -160,7 +160,6 @@ def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int, ragg
     qb.sort(key=lambda t: -t[0])                                                  # heavy blocks first
     qblocks = np.array([t[1] for t in qb], np.int32).reshape(-1, QB_FIELDS)
     kb, part_rows = [], 0
-    red = [[] for _ in range(rows)]
     deps = [[] for _ in range(G)]
     for i in range(B):
         deps[int(seq_group[i])].append(i)
@@ -173,14 +172,25 @@ def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int, ragg
             for (qr0, qlen, causal) in qsegs:
                 nqb = (qlen + 63) // 64 - (b0 // 64 if causal else 0)
                 kb.append((nqb, [r0 + b0, k_rows, b0, qr0, qlen, causal, qr0, part_rows]))
-                for rr in range(k_rows):
-                    red[r0 + b0 + rr].append(part_rows + rr)
                 part_rows += k_rows
+    # reduction lists: key row r sums the partial rows of every (key block, query segment) unit that covers it, in the
+    # order the units were created (fixed order -> deterministic dK/dV).  Vectorised: one (row, partial row) pair per
+    # partial row, stable-sorted by key row.
+    red_start = np.zeros(rows + 1, np.int32)
+    if kb:
+        kb_arr = np.array([t[1] for t in kb], np.int64).reshape(-1, KB_FIELDS)
+        k_row0, k_rows_a, out0 = kb_arr[:, 0], kb_arr[:, 1], kb_arr[:, 7]
+        rep = np.repeat(np.arange(kb_arr.shape[0]), k_rows_a)
+        within = np.arange(int(k_rows_a.sum())) - np.repeat(np.cumsum(k_rows_a) - k_rows_a, k_rows_a)
+        key_row = k_row0[rep] + within
+        part_row = out0[rep] + within                                             # == arange(part_rows): creation order
+        order_r = np.argsort(key_row, kind="stable")
+        red_list = part_row[order_r].astype(np.int32)
+        red_start[1:] = np.cumsum(np.bincount(key_row, minlength=rows))
+    else:
+        red_list = np.zeros(0, np.int32)
     kb.sort(key=lambda t: -t[0])
     kblocks = np.array([t[1] for t in kb], np.int32).reshape(-1, KB_FIELDS)
-    red_start = np.zeros(rows + 1, np.int32)
-    red_start[1:] = np.cumsum([len(x) for x in red])
-    red_list = np.array([x for lst in red for x in lst], np.int32)
     arrays = {"ids": p_ids, "pos": p_pos, "key_mask": p_km, "score_src": score_src, "targets": targets,
               "answer_mask": answer_mask, "sc_start": sc_start, "sc_list": sc_list, "qblocks": qblocks.reshape(-1),
               "kblocks": kblocks.reshape(-1), "red_start": red_start, "red_list": red_list}
@@ -190,15 +200,55 @@ def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int, ragg
     return host
 
 
+class PinnedStager:
+    """Reusable pinned host staging buffers for the per-pass host->device copies (ids / masks / descriptors /
+    advantages).  `tensor.pin_memory()` allocates and registers fresh pinned memory on every call (~0.1-1 ms each);
+    here a small ring of buffers per power-of-two size class is allocated once, and a buffer is reused only after the
+    copy that last read it has completed (CUDA event)."""
+
+    def __init__(self, device, ring=4):
+        self.device = torch.device(device)
+        self.ring = ring
+        self._bufs = {}     # size class -> [(uint8 pinned tensor, event or None)]
+        self._next = {}
+
+    def to_device(self, arr):
+        """numpy array or CPU tensor -> new device tensor with the same dtype / shape (async copy on the current stream)."""
+        t = torch.from_numpy(np.ascontiguousarray(arr)) if isinstance(arr, np.ndarray) else arr.contiguous()
+        nbytes = t.numel() * t.element_size()
+        if nbytes == 0:
+            return t.to(self.device)
+        cls = 1 << max(12, (nbytes - 1).bit_length())
+        slots = self._bufs.setdefault(cls, [])
+        i = self._next.get(cls, 0)
+        if len(slots) < self.ring:
+            slots.append([torch.empty(cls, dtype=torch.uint8).pin_memory(), None])
+            i = len(slots) - 1
+        self._next[cls] = (i + 1) % self.ring
+        buf, ev = slots[i]
+        if ev is not None:
+            ev.synchronize()
+        stage = buf[:nbytes].view(t.dtype).view(t.shape)
+        stage.copy_(t)
+        out = stage.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slots[i][1] = ev
+        return out
+
+
 class PackedDevice:
     """Device-resident packed micro-batch: one int32 blob + the C descriptor struct pointing into it."""
 
-    def __init__(self, host: PackedHost, device, pinned=True):
+    def __init__(self, host: PackedHost, device, pinned=True, stager: "PinnedStager" = None):
         blob, offs = host.blob()
-        t = torch.from_numpy(blob)
-        if pinned:
-            t = t.pin_memory()
-        self.blob = t.to(device, non_blocking=True)
+        if stager is not None:
+            self.blob = stager.to_device(blob)
+        else:
+            t = torch.from_numpy(blob)
+            if pinned:
+                t = t.pin_memory()
+            self.blob = t.to(device, non_blocking=True)
         self.host = host
         self.h2d_bytes = blob.nbytes
         base = self.blob.data_ptr()

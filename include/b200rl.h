@@ -152,6 +152,13 @@ int b200rl_lora_reduce_adamw(float* p, float* m, float* v, const float* const* g
                              float weight_decay, int zero_local_grad, void* stream);
 int b200rl_p2p_barrier(unsigned int* const* flags_peer_host, int world, int rank, unsigned int epoch,
                        void* stream);
+/* same with an explicit timeout (seconds; <= 0 = env B200RL_P2P_TIMEOUT_S, default 600).  A peer that does not arrive
+ * does not trap the context: the waiter records it in a host-visible status word, later reduce kernels become no-ops,
+ * and b200rl_p2p_status() returns B200RL_ERR_STATE (reference equivalent: ray.get(..., timeout=240),
+ * distributed_trainer.py:200, :333). */
+int b200rl_p2p_barrier_timeout(unsigned int* const* flags_peer_host, int world, int rank, unsigned int epoch,
+                               double timeout_s, void* stream);
+int b200rl_p2p_status(int reset);
 int b200rl_p2p_alloc(long long bytes, void** ptr, void* handle64);
 int b200rl_p2p_open(const void* handle64, void** ptr);
 int b200rl_p2p_close(void* ptr);

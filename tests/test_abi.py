@@ -65,6 +65,6 @@ def test_no_fallback_when_library_missing(monkeypatch, tmp_path):
 def test_product_code_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "distrl_llm_b200")
     for fn in os.listdir(pkg):
-        if fn.endswith(".py") and fn != "_smoke.py":   # smoke() is allowed to use the oracle as a checker
+        if fn.endswith(".py"):   # no exception: smoke()'s checker lives in __graft_entry__.py, outside the package
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
