@@ -84,6 +84,7 @@ SIGNATURES = {
     "b200rl_p2p_open": (c_int, [c_void_p, C.POINTER(c_void_p)]),
     "b200rl_p2p_close": (c_int, [c_void_p]),
     "b200rl_p2p_free": (c_int, [c_void_p]),
+    "b200rl_p2p_enable_peer_access": (c_int, [c_int]),
     "b200rl_lora_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b200rl_lora_grad_accum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b200rl_sizeof_pack_desc": (c_int, []),

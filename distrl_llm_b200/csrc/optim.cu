@@ -337,6 +337,23 @@ extern "C" int b200rl_p2p_free(void* ptr) {
   B200RL_CUDA_OK(cudaFree(ptr));
   return 0;
 }
+// Learners that live in ONE process on different devices (the single-process trainer harness) exchange plain device
+// pointers instead of IPC handles; the current device then needs explicit peer access to `peer_device`.
+extern "C" int b200rl_p2p_enable_peer_access(int peer_device) {
+  int dev = 0;
+  B200RL_CUDA_OK(cudaGetDevice(&dev));
+  if (dev == peer_device) return 0;
+  int can = 0;
+  B200RL_CUDA_OK(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  B200RL_REQUIRE(can, "p2p_enable_peer_access: device %d cannot access device %d", dev, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  B200RL_CUDA_OK(e);
+  return 0;
+}
 
 extern "C" int b200rl_lora_pack(const float* flat, void* arena_bf16, const void* descs_dev,
                                 int n_desc, int max_elems, void* stream) {

@@ -92,6 +92,9 @@ class BaseLearner:
         self.p2p = None  # set by enable_p2p() / p2p_open_handles()
         self._p2p_group = None
         self._p2p_handles = None
+        self._publisher = None            # adapter_sync.AdapterPublisher once a generator asked for the adapter
+        self.adapter_sync = config.get("adapter_sync", "memory")   # "memory" (default once a publisher exists) | "file"
+        self.model_name = config.get("model")
         self._stager = packing.PinnedStager(policy.device)   # reusable pinned staging for the per-pass H2D copies
 
     # ---- tokenise + pad (:217-239) ------------------------------------------------------------
@@ -247,11 +250,37 @@ class BaseLearner:
         self._p2p_group.attach(self.policy, host_rendezvous=host_rendezvous)
         self.p2p = self._p2p_group
 
+    # same-process harness (actors.create_actor_and_learner without Ray): the groups exchange plain pointers
+    def p2p_local_group(self):
+        return self._p2p_group
+
+    def p2p_attach_local(self):
+        self._p2p_group.attach(self.policy, host_rendezvous=lambda: None)
+        self.p2p = self._p2p_group
+
+    def vocab_size(self):
+        return self.policy.cfg.vocab
+
+    # ---- adapter hand-off to the generators -------------------------------------------------------
+    def adapter_publisher(self):
+        """Create (once) the in-memory publisher of this learner's adapter and return its picklable description for the
+        generators' AdapterSubscriber (adapter_sync.py).  From then on save_adapter() publishes instead of writing files."""
+        if self._publisher is None:
+            from .adapter_sync import AdapterPublisher
+            self._publisher = AdapterPublisher(self.policy)
+            self._publisher.publish()
+        return self._publisher.describe()
+
     # ---- misc actor surface --------------------------------------------------------------------------
     def generate(self, messages, sampling_params=None):
-        """(:174-180) generation is the generator's job (vLLM or a stub), not part of the hot path."""
+        """(:174-180) generation is the generator's job (vLLM or a stub), not part of the hot path.  The reference's
+        Trainer always sends the learners a chunk of `learner_chunk_size` problems (distributed_trainer.py:187-197); a
+        learner without a generator accepts only the empty chunk (`--learner_chunk_size 0`)."""
         if self.generator is None:
-            raise RuntimeError("this learner has no generator attached")
+            if len(messages.get("problem", [])) == 0:
+                return dict(messages, answers=[], token_lengths=[])
+            raise RuntimeError("this learner has no generator attached: run the trainer with learner_chunk_size=0 "
+                               "(all problems go to the generators) or pass generator=... to the learner")
         return self.generator.generate(messages, sampling_params)
 
     def save_checkpoint(self, path):
@@ -273,9 +302,14 @@ class BaseLearner:
         self.policy.load_lora_state(sd)
 
     def save_adapter(self):
-        """(:84-86) `save_lora(self.policy, self.lora_save_path)`: the directory the generators' vLLM engines load the
-        current adapter from (`load_lora`, :150)."""
-        self.save_checkpoint(self.lora_save_path)
+        """(:84-86) `save_lora(self.policy, self.lora_save_path)`: makes the current adapter available to the generators
+        (`load_lora`, :150).  With an in-memory publisher (adapter_publisher()) that is one device-to-device copy and a
+        version bump; otherwise (or with config["adapter_sync"] == "file") the PEFT adapter directory vLLM loads."""
+        if self._publisher is not None and self.adapter_sync != "file":
+            return self._publisher.publish()
+        import os
+        os.makedirs(self.lora_save_path, exist_ok=True)
+        write_peft_adapter(self.lora_save_path, self.policy.lora_state_dict(), self.policy.cfg, base_model=self.model_name)
 
 
 def read_peft_adapter(path):

@@ -50,12 +50,13 @@ class P2PGroup:
         """Allocate the IPC-exportable buffers; returns ({name: 64-byte handle}, kwargs for Policy(...))."""
         self.numel = numel
         handles = {}
-        for name, nbytes in (("params", numel * 4), ("grads", numel * 4), ("flags", 64 * 4)):
-            p = C.c_void_p()
-            h = (C.c_ubyte * 64)()
-            check(lib().b200rl_p2p_alloc(nbytes, C.byref(p), h), "p2p_alloc")
-            self.local[name] = p.value
-            handles[name] = bytes(h)
+        with torch.cuda.device(self.device):   # cudaMalloc on THIS learner's device
+            for name, nbytes in (("params", numel * 4), ("grads", numel * 4), ("flags", 64 * 4)):
+                p = C.c_void_p()
+                h = (C.c_ubyte * 64)()
+                check(lib().b200rl_p2p_alloc(nbytes, C.byref(p), h), "p2p_alloc")
+                self.local[name] = p.value
+                handles[name] = bytes(h)
         kw = {"lora_flat": tensor_from_ptr(self.local["params"], numel, torch.float32, self.device),
               "lora_grad": tensor_from_ptr(self.local["grads"], numel, torch.float32, self.device)}
         return handles, kw
@@ -85,6 +86,10 @@ class P2PGroup:
             assert g.world == len(groups)
             for name in _NAMES:
                 g.peers[name] = [h.local[name] for h in groups]
+            with torch.cuda.device(g.device):   # plain pointers across devices need explicit peer access
+                for h in groups:
+                    if h.device != g.device:
+                        check(lib().b200rl_p2p_enable_peer_access(h.device.index), "p2p_enable_peer_access")
 
     @classmethod
     def from_torch_distributed(cls, cfg, max_batch, P, T, device):

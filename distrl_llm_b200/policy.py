@@ -72,6 +72,32 @@ class LMConfig:
                         head_dim=128, lora_r=lora_r, lora_alpha=lora_alpha)
 
 
+class LoraLayout:
+    """Names and offsets of every LoRA tensor inside the flat fp32 buffer, without a model behind it (what a generator
+    needs to view a pulled adapter under PEFT names; csrc/model.cu build_groups() is the authority for the order:
+    for layer: for module in (q,k,v,o,gate,up,down): A [r, in] then B [out, r]; total padded to a multiple of 4)."""
+
+    def __init__(self, cfg: "LMConfig"):
+        self.cfg = cfg
+        self.offsets = {}
+        off = 0
+        shapes = cfg.module_shapes()
+        for i in range(cfg.n_layers):
+            for m in LORA_MODULES:
+                fin, fout = shapes[m]
+                self.offsets[(i, m, "A")] = (off, (cfg.lora_r, fin)); off += cfg.lora_r * fin
+                self.offsets[(i, m, "B")] = (off, (fout, cfg.lora_r)); off += fout * cfg.lora_r
+        self.numel = (off + 3) // 4 * 4
+
+    @staticmethod
+    def peft_name(i, m, ab):
+        return f"base_model.model.model.layers.{i}.{_PEFT[m]}.lora_{ab}.default.weight"
+
+    def named_views(self, flat):
+        return {self.peft_name(i, m, ab): flat[off:off + shp[0] * shp[1]].view(*shp)
+                for (i, m, ab), (off, shp) in self.offsets.items()}
+
+
 class _RawCuda:
     """Wrap a raw device pointer (library-owned, e.g. an IPC-mapped peer buffer) as a torch tensor."""
 

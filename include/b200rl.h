@@ -163,6 +163,7 @@ int b200rl_p2p_alloc(long long bytes, void** ptr, void* handle64);
 int b200rl_p2p_open(const void* handle64, void** ptr);
 int b200rl_p2p_close(void* ptr);
 int b200rl_p2p_free(void* ptr);
+int b200rl_p2p_enable_peer_access(int peer_device); /* same-process learners on different devices (no IPC handle) */
 int b200rl_lora_pack(const float* flat, void* arena_bf16, const void* descs_dev, int n_desc,
                      int max_elems, void* stream);
 int b200rl_lora_grad_accum(float* flat, const void* descs_dev, int n_desc, int max_elems,
