@@ -26,6 +26,11 @@ class ModelConfig(C.Structure):
     ]
 
 
+class LossArgs(C.Structure):
+    _fields_ = [("nb", c_int), ("grpo", c_int), ("backward", c_int), ("lora_off", c_int),
+                ("ref_lp", c_void_p), ("kl_beta", C.c_double), ("old_lp", c_void_p), ("clip_eps", C.c_double)]
+
+
 class LayerWeights(C.Structure):
     _fields_ = [
         ("qkv_packed", c_void_p), ("qkv_absmax", c_void_p),
@@ -110,6 +115,13 @@ SIGNATURES = {
     "b200rl_model_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200rl_launch_count": (c_ll, []),
     "b200rl_set_pdl": (c_int, [c_int]),
+    "b200rl_logprob_clip": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_double, c_void_p, c_int,
+                                    c_int, c_int, c_void_p]),
+    "b200rl_loss_value_clip": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_double, c_void_p, C.c_double, c_void_p, c_int,
+                                       c_int, c_int, c_void_p]),
+    "b200rl_model_pass": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_void_p, c_void_p]),
+    "b200rl_model_pass_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200rl_model_microbatch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }

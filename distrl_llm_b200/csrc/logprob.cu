@@ -23,7 +23,8 @@ static constexpr float LN2 = 0.6931471805599453f;
 __global__ void __launch_bounds__(1024)
 logprob_kernel(bf16* __restrict__ logits, long long ld, const int* __restrict__ targets,
                const float* __restrict__ coef, const float* __restrict__ klw,
-               const float* __restrict__ ref_lp, float* __restrict__ lp_out, int V, int write_grad) {
+               const float* __restrict__ ref_lp, const float* __restrict__ old_lp, float clip_eps,
+               float* __restrict__ lp_out, int V, int write_grad) {
   __shared__ float red_m[32], red_s[32];
   __shared__ float s_lse2, s_max2;
   const size_t row = blockIdx.x;
@@ -84,6 +85,15 @@ logprob_kernel(bf16* __restrict__ logits, long long ld, const int* __restrict__ 
   const float zy = (y >= 0 && y < V) ? __bfloat162float(z[y]) : 0.f;
   const float lp = (y >= 0 && y < V) ? (zy * LOG2E - lse2) * LN2 : 0.f;
   float c = coef ? coef[row] : 0.f;
+  // optional clipped-ratio surrogate (not in the reference, whose ratio exp(lp - lp.detach()) is identically 1,
+  // distributed_actor.py:467): loss_t = -min(rho A, clip(rho, 1-eps, 1+eps) A) with rho = exp(lp - old_lp), so
+  // d loss_t / d lp = -A rho while the unclipped branch is the active minimum and 0 once rho has left the trust region in
+  // the direction the advantage pushes.  coef carries -A mask / (len Bm nb): its sign is that of -A.
+  if (old_lp && clip_eps > 0.f && c != 0.f) {
+    const float rho = __expf(lp - old_lp[row]);
+    const bool active = c < 0.f ? rho <= 1.f + clip_eps : rho >= 1.f - clip_eps;
+    c = active ? c * rho : 0.f;
+  }
   // optional KL(pi || pi_ref) term, k3 estimator exp(q-p) - (q-p) - 1 per token:
   // d k3 / d lp = 1 - exp(q - p); klw carries beta * mask / (len * Bm * nb)   (not in the reference: beta = 0)
   if (klw && ref_lp && klw[row] != 0.f) c += klw[row] * (1.f - __expf(ref_lp[row] - lp));
@@ -151,7 +161,8 @@ __global__ void loss_coef_kernel(const int* __restrict__ mask, const double* __r
 // The reference's returned scalar is the SUM of loss_m over micro-batches (quirk Q2) -> *accum += loss_m.
 __global__ void loss_value_kernel(const float* __restrict__ lp, const int* __restrict__ mask,
                                   const double* __restrict__ adv, const float* __restrict__ ref_lp,
-                                  double beta, double* __restrict__ accum, int Bm, int T, int grpo) {
+                                  double beta, const float* __restrict__ old_lp, double clip_eps,
+                                  double* __restrict__ accum, int Bm, int T, int grpo) {
   __shared__ double red[32];
   double total = 0.0;
   for (int i = 0; i < Bm; ++i) {
@@ -160,7 +171,14 @@ __global__ void loss_value_kernel(const float* __restrict__ lp, const int* __res
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
       if (mask[(size_t)i * T + t] != 0) {
         const double p = (double)lp[(size_t)i * T + t];
-        s += p;
+        if (old_lp && clip_eps > 0.0) {   // clipped surrogate: s accumulates min(rho A, clip(rho) A) instead of lp
+          const double rho = exp(p - (double)old_lp[(size_t)i * T + t]);
+          const double a = adv[i];
+          const double cl = fmin(fmax(rho, 1.0 - clip_eps), 1.0 + clip_eps);
+          s += fmin(rho * a, cl * a);
+        } else {
+          s += p;
+        }
         cnt += 1;
         if (ref_lp) {
           const double d = (double)ref_lp[(size_t)i * T + t] - p;
@@ -189,7 +207,8 @@ __global__ void loss_value_kernel(const float* __restrict__ lp, const int* __res
         kk += redk[w];
         cc += redc[w];
       }
-      if (cc > 0) total += (grpo ? adv[i] : adv[i] * (ss / (double)cc)) - beta * (kk / (double)cc);
+      const bool clipped = old_lp && clip_eps > 0.0;
+      if (cc > 0) total += (clipped ? ss / (double)cc : (grpo ? adv[i] : adv[i] * (ss / (double)cc))) - beta * (kk / (double)cc);
     }
     __syncthreads();
   }
@@ -208,7 +227,7 @@ extern "C" int b200rl_logprob_kl(void* logits, long long ld, const int* targets,
                  "logprob: bad args (rows=%d V=%d ld=%lld)", rows, V, ld);
   B200RL_REQUIRE(!write_grad || coef, "logprob: write_grad needs coef");
   const int threads = V >= 8192 ? 1024 : 256;
-  logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, klw, ref_lp, lp_out, V,
+  logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, klw, ref_lp, nullptr, 0.f, lp_out, V,
                                                write_grad);
   B200RL_LAUNCH_OK();
   return 0;
@@ -220,8 +239,8 @@ extern "C" int b200rl_logprob(void* logits, long long ld, const int* targets, co
                  "logprob: bad args (rows=%d V=%d ld=%lld)", rows, V, ld);
   B200RL_REQUIRE(!write_grad || coef, "logprob: write_grad needs coef");
   const int threads = V >= 8192 ? 1024 : 256;
-  logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, nullptr, nullptr, lp_out, V,
-                                               write_grad);
+  logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, nullptr, nullptr, nullptr, 0.f, lp_out,
+                                               V, write_grad);
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -245,7 +264,7 @@ extern "C" int b200rl_loss_coef(const int* mask, const double* adv, float* coef,
 extern "C" int b200rl_loss_value_kl(const float* lp, const int* mask, const double* adv, const float* ref_lp,
                                     double beta, double* accum, int Bm, int T, int grpo, void* stream) {
   B200RL_REQUIRE(lp && mask && adv && accum && Bm > 0 && T > 0, "loss_value: bad args");
-  loss_value_kernel<<<1, 256, 0, STREAM>>>(lp, mask, adv, ref_lp, beta, accum, Bm, T, grpo);
+  loss_value_kernel<<<1, 256, 0, STREAM>>>(lp, mask, adv, ref_lp, beta, nullptr, 0.0, accum, Bm, T, grpo);
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -253,7 +272,32 @@ extern "C" int b200rl_loss_value_kl(const float* lp, const int* mask, const doub
 extern "C" int b200rl_loss_value(const float* lp, const int* mask, const double* adv, double* accum,
                                  int Bm, int T, int grpo, void* stream) {
   B200RL_REQUIRE(lp && mask && adv && accum && Bm > 0 && T > 0, "loss_value: bad args");
-  loss_value_kernel<<<1, 256, 0, STREAM>>>(lp, mask, adv, nullptr, 0.0, accum, Bm, T, grpo);
+  loss_value_kernel<<<1, 256, 0, STREAM>>>(lp, mask, adv, nullptr, 0.0, nullptr, 0.0, accum, Bm, T, grpo);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
+// Clipped-ratio variants (not in the reference): old_lp [rows] = log-probs of the policy that
+// generated the batch, clip_eps = trust-region half width.  old_lp == NULL or clip_eps == 0 is the plain form above.
+extern "C" int b200rl_logprob_clip(void* logits, long long ld, const int* targets, const float* coef, const float* klw,
+                                   const float* ref_lp, const float* old_lp, double clip_eps, float* lp_out, int rows,
+                                   int V, int write_grad, void* stream) {
+  B200RL_REQUIRE(logits && targets && rows > 0 && V > 0 && V % 8 == 0 && ld % 8 == 0,
+                 "logprob: bad args (rows=%d V=%d ld=%lld)", rows, V, ld);
+  B200RL_REQUIRE(!write_grad || coef, "logprob: write_grad needs coef");
+  B200RL_REQUIRE(clip_eps >= 0.0, "logprob: clip_eps must be >= 0");
+  const int threads = V >= 8192 ? 1024 : 256;
+  logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, klw, ref_lp, old_lp, (float)clip_eps,
+                                               lp_out, V, write_grad);
+  B200RL_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200rl_loss_value_clip(const float* lp, const int* mask, const double* adv, const float* ref_lp,
+                                      double beta, const float* old_lp, double clip_eps, double* accum, int Bm, int T,
+                                      int grpo, void* stream) {
+  B200RL_REQUIRE(lp && mask && adv && accum && Bm > 0 && T > 0, "loss_value: bad args");
+  loss_value_kernel<<<1, 256, 0, STREAM>>>(lp, mask, adv, ref_lp, beta, old_lp, clip_eps, accum, Bm, T, grpo);
   B200RL_LAUNCH_OK();
   return 0;
 }

@@ -55,6 +55,8 @@ int b200rl_logprob(void*, long long, const int*, const float*, float*, int, int,
 int b200rl_loss_coef(const int*, const double*, float*, int*, int, int, int, void*);
 int b200rl_loss_value(const float*, const int*, const double*, double*, int, int, int, void*);
 int b200rl_logprob_kl(void*, long long, const int*, const float*, const float*, const float*, float*, int, int, int, void*);
+int b200rl_logprob_clip(void*, long long, const int*, const float*, const float*, const float*, const float*, double, float*, int, int, int, void*);
+int b200rl_loss_value_clip(const float*, const int*, const double*, const float*, double, const float*, double, double*, int, int, int, void*);
 int b200rl_loss_coef_kl(const int*, const double*, float*, float*, double, int*, int, int, int, void*);
 int b200rl_loss_value_kl(const float*, const int*, const double*, const float*, double, double*, int, int, int, void*);
 int b200rl_nf4_dequant(const void*, const float*, void*, int, int, int, void*);
@@ -751,7 +753,7 @@ static int base_weight(b200rl_model* m, cudaStream_t st, int l, int which, const
 
 static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv, float* lp_out, double* loss_accum,
                           int nb, int grpo, int backward, int lora_off, const float* ref_lp, double kl_beta,
-                          void* stream) {
+                          const float* old_lp, double clip_eps, void* stream) {
   const b200rl_model_config& c = m->cfg;
   const b200rl_packed_batch* pb = lay.pb;
   const int M = lay.M, B = lay.B, T = lay.T, L = lay.L, P = lay.P, R = B * T;
@@ -762,6 +764,8 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
   B200RL_REQUIRE(!(backward && lora_off), "model_microbatch: the adapter-off (reference policy) pass is forward only");
   B200RL_REQUIRE(kl_beta == 0.0 || ref_lp, "model_microbatch: kl_beta != 0 needs ref_lp");
   const bool use_kl = backward && kl_beta != 0.0 && ref_lp;
+  B200RL_REQUIRE(clip_eps >= 0.0, "model_microbatch: clip_eps must be >= 0");
+  const bool use_clip = old_lp && clip_eps > 0.0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int H = c.hidden, I = c.inter, QKV = m->QKV, QD = m->QD, V = c.vocab;
   const long long Mt = c.max_tokens;
@@ -840,11 +844,13 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
   if (backward) RC(b200rl_loss_coef_kl(answer_mask, adv, m->coef, use_kl ? m->klw : nullptr, kl_beta, m->lens, B, T, nb, stream));
   float* lp = lp_out ? lp_out : m->lp;
   PM(CAT_LOGPROB, (backward ? 2.0 : 1.0) * R * V * 2);
-  RC(b200rl_logprob_kl(m->logits, V, targets, backward ? m->coef : nullptr, use_kl ? m->klw : nullptr,
-                       use_kl ? ref_lp : nullptr, lp, R, V, backward ? 1 : 0, stream));
+  RC(b200rl_logprob_clip(m->logits, V, targets, backward ? m->coef : nullptr, use_kl ? m->klw : nullptr,
+                         use_kl ? ref_lp : nullptr, use_clip ? old_lp : nullptr, use_clip ? clip_eps : 0.0, lp, R, V,
+                         backward ? 1 : 0, stream));
   PM(CAT_MISC, 0);
   if (loss_accum && adv)
-    RC(b200rl_loss_value_kl(lp, answer_mask, adv, use_kl ? ref_lp : nullptr, use_kl ? kl_beta : 0.0, loss_accum, B, T, grpo, stream));
+    RC(b200rl_loss_value_clip(lp, answer_mask, adv, use_kl ? ref_lp : nullptr, use_kl ? kl_beta : 0.0,
+                              use_clip ? old_lp : nullptr, use_clip ? clip_eps : 0.0, loss_accum, B, T, grpo, stream));
   if (!backward) {
     PM(CAT_END, 0);
     return 0;
@@ -988,11 +994,10 @@ extern "C" int b200rl_model_profile_read(b200rl_model* m, double* ms, double* wo
   return 0;
 }
 
-extern "C" int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const int* attn_mask,
-                                          const int* answer_mask, const double* adv, float* lp_out,
-                                          double* loss_accum, int B, int P, int T, int nb, int grpo,
-                                          int backward, int lora_off, const float* ref_lp, double kl_beta,
-                                          void* stream) {
+static int classic_pass(b200rl_model* m, const int* ids, const int* attn_mask, const int* answer_mask, const double* adv,
+                        float* lp_out, double* loss_accum, int B, int P, int T, int nb, int grpo, int backward,
+                        int lora_off, const float* ref_lp, double kl_beta, const float* old_lp, double clip_eps,
+                        void* stream) {
   B200RL_REQUIRE(m && ids && attn_mask && answer_mask, "model_microbatch: null pointer");
   const b200rl_model_config& c = m->cfg;
   const int L = P + T;
@@ -1002,7 +1007,16 @@ extern "C" int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const
   Layout lay;
   lay.M = B * L; lay.B = B; lay.T = T; lay.L = L; lay.P = P;
   lay.ids = ids; lay.key_mask = attn_mask; lay.answer_mask = answer_mask; lay.pb = nullptr;
-  return run_microbatch(m, lay, adv, lp_out, loss_accum, nb, grpo, backward, lora_off, ref_lp, kl_beta, stream);
+  return run_microbatch(m, lay, adv, lp_out, loss_accum, nb, grpo, backward, lora_off, ref_lp, kl_beta, old_lp, clip_eps, stream);
+}
+
+extern "C" int b200rl_model_microbatch_ex(b200rl_model* m, const int* ids, const int* attn_mask,
+                                          const int* answer_mask, const double* adv, float* lp_out,
+                                          double* loss_accum, int B, int P, int T, int nb, int grpo,
+                                          int backward, int lora_off, const float* ref_lp, double kl_beta,
+                                          void* stream) {
+  return classic_pass(m, ids, attn_mask, answer_mask, adv, lp_out, loss_accum, B, P, T, nb, grpo, backward, lora_off, ref_lp,
+                      kl_beta, nullptr, 0.0, stream);
 }
 
 extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const int* attn_mask,
@@ -1013,9 +1027,9 @@ extern "C" int b200rl_model_microbatch(b200rl_model* m, const int* ids, const in
                                     backward, 0, nullptr, 0.0, stream);
 }
 
-extern "C" int b200rl_model_microbatch_packed(b200rl_model* m, const b200rl_packed_batch* pb, const double* adv,
-                                              float* lp_out, double* loss_accum, int nb, int grpo, int backward,
-                                              int lora_off, const float* ref_lp, double kl_beta, void* stream) {
+static int packed_pass(b200rl_model* m, const b200rl_packed_batch* pb, const double* adv, float* lp_out,
+                       double* loss_accum, int nb, int grpo, int backward, int lora_off, const float* ref_lp,
+                       double kl_beta, const float* old_lp, double clip_eps, void* stream) {
   B200RL_REQUIRE(m && pb, "model_microbatch_packed: null pointer");
   const b200rl_model_config& c = m->cfg;
   B200RL_REQUIRE(c.head_dim == 128, "model_microbatch_packed: the packed layout needs head_dim 128 (tcgen05 attention)");
@@ -1030,5 +1044,26 @@ extern "C" int b200rl_model_microbatch_packed(b200rl_model* m, const b200rl_pack
   Layout lay;
   lay.M = pb->rows; lay.B = pb->B; lay.T = pb->T; lay.L = pb->max_pos; lay.P = 0;
   lay.ids = pb->ids; lay.key_mask = pb->key_mask; lay.answer_mask = pb->answer_mask; lay.pb = pb;
-  return run_microbatch(m, lay, adv, lp_out, loss_accum, nb, grpo, backward, lora_off, ref_lp, kl_beta, stream);
+  return run_microbatch(m, lay, adv, lp_out, loss_accum, nb, grpo, backward, lora_off, ref_lp, kl_beta, old_lp, clip_eps, stream);
+}
+
+extern "C" int b200rl_model_microbatch_packed(b200rl_model* m, const b200rl_packed_batch* pb, const double* adv,
+                                              float* lp_out, double* loss_accum, int nb, int grpo, int backward,
+                                              int lora_off, const float* ref_lp, double kl_beta, void* stream) {
+  return packed_pass(m, pb, adv, lp_out, loss_accum, nb, grpo, backward, lora_off, ref_lp, kl_beta, nullptr, 0.0, stream);
+}
+
+// general forms: the loss terms in one argument block (include/b200rl.h b200rl_loss_args)
+extern "C" int b200rl_model_pass(b200rl_model* m, const int* ids, const int* attn_mask, const int* answer_mask,
+                                 const double* adv, float* lp_out, double* loss_accum, int B, int P, int T,
+                                 const b200rl_loss_args* a, void* stream) {
+  B200RL_REQUIRE(a != nullptr, "model_pass: null args");
+  return classic_pass(m, ids, attn_mask, answer_mask, adv, lp_out, loss_accum, B, P, T, a->nb, a->grpo, a->backward,
+                      a->lora_off, a->ref_lp, a->kl_beta, a->old_lp, a->clip_eps, stream);
+}
+extern "C" int b200rl_model_pass_packed(b200rl_model* m, const b200rl_packed_batch* pb, const double* adv, float* lp_out,
+                                        double* loss_accum, const b200rl_loss_args* a, void* stream) {
+  B200RL_REQUIRE(a != nullptr, "model_pass_packed: null args");
+  return packed_pass(m, pb, adv, lp_out, loss_accum, a->nb, a->grpo, a->backward, a->lora_off, a->ref_lp, a->kl_beta,
+                     a->old_lp, a->clip_eps, stream);
 }

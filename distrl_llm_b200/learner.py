@@ -72,6 +72,12 @@ class BaseLearner:
         self.lr = config["lr"]                                    # :210
         self.weight_decay = config.get("weight_decay", 0.0)       # commented out in the reference (:210)
         self.kl_beta = float(config.get("kl_beta", 0.0))          # KL-to-reference weight; 0 = reference behaviour
+        # SURVEY.md 8(f) N4 (absent from the reference, whose ratio exp(lp - lp.detach()) is identically 1, :467):
+        # clipped-ratio surrogate against the log-probs of the policy that generated the batch, over `inner_epochs`
+        # optimizer steps per batch.  Defaults (0, 1) are exactly the reference's single step.
+        self.clip_eps = float(config.get("clip_eps", 0.0))
+        self.inner_epochs = max(1, int(config.get("inner_epochs", 1)))
+        self.last_epoch_losses = []
         # packed shared-prompt layout (packing.py): identical results, each distinct prompt of a micro-batch is
         # processed once; needs the tcgen05 attention kernels (head_dim 128)
         self.share_prompts = bool(config.get("share_prompts", policy.cfg.head_dim == 128))
@@ -131,9 +137,12 @@ class BaseLearner:
         return packing.PackedDevice(host, self.policy.device, stager=self._stager)
 
     # ---- loss + backward (:349-395 PG, :440-493 GRPO) ---------------------------------------------
-    def compute_loss(self, messages, answers, rewards):
+    def compute_loss(self, messages, answers, rewards, old_lp=None, lp_capture=None):
+        """old_lp [n, T] f32 device tensor (+ self.clip_eps > 0): clipped-ratio surrogate; lp_capture [n, T]: filled with
+        the current per-token log-probs of every trained sequence (the next inner epoch's old_lp).  Both None = reference."""
         rewards = np.asarray([float(r) for r in rewards], dtype=np.float64)   # :350 / :441 (float64)
         n = len(messages)
+        clip = self.clip_eps if old_lp is not None else 0.0
         nb = (n + self.update_batch_size - 1) // self.update_batch_size      # :354-356
         pol = self.policy
         pol.zero_grad()                                                       # :358 / :450
@@ -163,6 +172,9 @@ class BaseLearner:
             r = rewards[idx] * float(k)          # see __init__: k fused micro-batches
             beta = self.kl_beta * k
             ids, am, ansm = self._encode(msgs, answ)
+            didx = torch.as_tensor(idx, device=pol.device) if (old_lp is not None or lp_capture is not None) else None
+            olp = old_lp.index_select(0, didx).contiguous() if old_lp is not None else None
+            lp_now = torch.empty(len(idx), self.max_new_tokens, device=pol.device, dtype=torch.float32) if lp_capture is not None else None
             if self.share_prompts:
                 pk = self._pack(ids, am)
                 ref_lp = None
@@ -170,18 +182,38 @@ class BaseLearner:
                     ref_lp = torch.empty(len(idx), self.max_new_tokens, device=pol.device, dtype=torch.float32)
                     pol.microbatch_packed(pk, None, 1, False, backward=False, lp_out=ref_lp, lora_off=True)
                 pol.microbatch_packed(pk, self._h2d(torch.from_numpy(r)), nb, grpo, backward=True, ref_lp=ref_lp,
-                                      kl_beta=beta)
-                continue
-            d_ids, d_am, d_ansm = self._h2d(ids), self._h2d(am), self._h2d(ansm)
-            ref_lp = None
-            if self.kl_beta != 0.0:
-                # reference policy = the frozen base with the adapter disabled (one extra forward, no backward)
-                ref_lp = torch.empty(len(idx), self.max_new_tokens, device=pol.device, dtype=torch.float32)
-                pol.microbatch(d_ids, d_am, d_ansm, None, self.max_prompt_tokens, self.max_new_tokens, 1, False,
-                               backward=False, lp_out=ref_lp, lora_off=True)
-            pol.microbatch(d_ids, d_am, d_ansm, self._h2d(torch.from_numpy(r)), self.max_prompt_tokens,
-                           self.max_new_tokens, nb, grpo, backward=True, ref_lp=ref_lp, kl_beta=beta)
+                                      kl_beta=beta, lp_out=lp_now, old_lp=olp, clip_eps=clip)
+            else:
+                d_ids, d_am, d_ansm = self._h2d(ids), self._h2d(am), self._h2d(ansm)
+                ref_lp = None
+                if self.kl_beta != 0.0:
+                    # reference policy = the frozen base with the adapter disabled (one extra forward, no backward)
+                    ref_lp = torch.empty(len(idx), self.max_new_tokens, device=pol.device, dtype=torch.float32)
+                    pol.microbatch(d_ids, d_am, d_ansm, None, self.max_prompt_tokens, self.max_new_tokens, 1, False,
+                                   backward=False, lp_out=ref_lp, lora_off=True)
+                pol.microbatch(d_ids, d_am, d_ansm, self._h2d(torch.from_numpy(r)), self.max_prompt_tokens,
+                               self.max_new_tokens, nb, grpo, backward=True, ref_lp=ref_lp, kl_beta=beta, lp_out=lp_now,
+                               old_lp=olp, clip_eps=clip)
+            if lp_capture is not None:
+                lp_capture.index_copy_(0, didx, lp_now)
         return float(pol.loss_accum.item())   # sum of per-micro-batch losses (quirk Q2), one sync
+
+    def _train_epochs(self, problems, answers, rewards):
+        """One optimizer step per inner epoch on the same batch (reference: exactly one, :407-415 / :507-513).  Epoch 0 is
+        the reference's step (ratio == 1) and records the per-token log-probs; later epochs use them as the old policy of
+        the clipped surrogate.  Returns the first epoch's loss (the number the reference returns)."""
+        old = None
+        self.last_epoch_losses = []
+        for epoch in range(self.inner_epochs):
+            capture = None
+            if epoch == 0 and self.inner_epochs > 1 and self.clip_eps > 0:
+                capture = torch.zeros(len(problems), self.max_new_tokens, device=self.policy.device, dtype=torch.float32)
+            loss = self.compute_loss(problems, answers, rewards, old_lp=old, lp_capture=capture)
+            self.policy.optimizer_step(self.lr, weight_decay=self.weight_decay)
+            self.last_epoch_losses.append(loss)
+            if capture is not None:
+                old = capture
+        return self.last_epoch_losses[0]
 
     # ---- gradient export / merge (:283-333) --------------------------------------------------------
     def export_gradients(self):
@@ -286,20 +318,47 @@ class BaseLearner:
     def save_checkpoint(self, path):
         """(:263-264) `self.policy.save_pretrained(path)` on a PEFT model = an adapter directory.  Written here in the
         same on-disk format (adapter_model.safetensors with PEFT's saved key names + adapter_config.json), plus the
-        torch-pickled dict with the in-memory names the gradient exchange uses (T2)."""
+        torch-pickled dict with the in-memory names the gradient exchange uses (T2) and — what the reference lacks
+        (no resume path, README TODO) — the optimizer state: Adam moments and the step counter."""
         import os
         os.makedirs(path, exist_ok=True)
         sd = self.policy.lora_state_dict()
         torch.save(sd, os.path.join(path, "adapter_model.pt"))
-        write_peft_adapter(path, sd, self.policy.cfg, base_model=getattr(self, "model_name", None))
+        write_peft_adapter(path, sd, self.policy.cfg, base_model=self.model_name)
+        pol = self.policy
+        torch.save({"adam_m": pol.adam_m.detach().cpu(), "adam_v": pol.adam_v.detach().cpu(), "opt_step": int(pol.opt_step),
+                    "lr": self.lr, "weight_decay": self.weight_decay, "betas": (0.9, 0.999), "eps": 1e-8,
+                    "lora_numel": int(pol.lora_numel)}, os.path.join(path, "optimizer_state.pt"))
 
     def load_checkpoint(self, path):
-        """Resume the adapter from a directory written by save_checkpoint / PEFT (the reference has no resume path,
-        README TODO).  Optimizer moments restart from zero."""
+        """Resume from a directory written by save_checkpoint (adapter + optimizer state) or by PEFT / the reference itself
+        (adapter only: the Adam moments and the step counter then restart from zero, as for a fresh optimizer).
+        In multi-learner mode call it on every learner (they hold identical replicas)."""
+        import os
         sd, conf = read_peft_adapter(path)
-        if int(conf.get("r", self.policy.cfg.lora_r)) != self.policy.cfg.lora_r:
-            raise ValueError(f"adapter rank {conf.get('r')} != policy rank {self.policy.cfg.lora_r}")
+        cfg = self.policy.cfg
+        if int(conf.get("r", cfg.lora_r)) != cfg.lora_r:
+            raise ValueError(f"adapter rank {conf.get('r')} != policy rank {cfg.lora_r}")
+        if "lora_alpha" in conf and float(conf["lora_alpha"]) != float(cfg.lora_alpha):
+            raise ValueError(f"adapter lora_alpha {conf['lora_alpha']} != policy lora_alpha {cfg.lora_alpha} (the scale alpha/r would change silently)")
+        want = {"q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"}
+        if "target_modules" in conf and set(conf["target_modules"]) != want:
+            raise ValueError(f"adapter target_modules {sorted(conf['target_modules'])} != {sorted(want)} (helper.py:29-37)")
         self.policy.load_lora_state(sd)
+        pol = self.policy
+        opt = os.path.join(path, "optimizer_state.pt")
+        if os.path.exists(opt):
+            st = torch.load(opt, map_location="cpu")
+            if int(st["lora_numel"]) != int(pol.lora_numel):
+                raise ValueError("optimizer state belongs to a different adapter layout")
+            pol.adam_m.copy_(st["adam_m"].to(pol.device))
+            pol.adam_v.copy_(st["adam_v"].to(pol.device))
+            pol.opt_step = int(st["opt_step"])
+        else:
+            pol.adam_m.zero_()
+            pol.adam_v.zero_()
+            pol.opt_step = 0
+        pol.lora_grad.zero_()
 
     def save_adapter(self):
         """(:84-86) `save_lora(self.policy, self.lora_save_path)`: makes the current adapter available to the generators
@@ -358,9 +417,7 @@ class Learner(BaseLearner):
                 problems.extend(p)
                 answers.extend(a)
                 rewards.extend(np.asarray(r) - b)
-        loss = self.compute_loss(problems, answers, rewards)
-        self.policy.optimizer_step(self.lr, weight_decay=self.weight_decay)
-        return loss
+        return self._train_epochs(problems, answers, rewards)
 
 
 class GRPOLearner(BaseLearner):
@@ -376,9 +433,7 @@ class GRPOLearner(BaseLearner):
                 problems.extend(p)
                 answers.extend(a)
                 rewards.extend(r)
-        loss = self.compute_loss(problems, answers, rewards)
-        self.policy.optimizer_step(self.lr, weight_decay=self.weight_decay)
-        return loss
+        return self._train_epochs(problems, answers, rewards)
 
 
 RemoteLearner = _remote(Learner) if ray is not None else Learner

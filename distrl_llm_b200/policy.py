@@ -372,24 +372,28 @@ class Policy:
     def sync_lora(self):
         check(lib().b200rl_model_sync_lora(self.handle, stream()), "model_sync_lora")
 
+    @staticmethod
+    def _loss_args(nb, grpo, backward, lora_off, ref_lp, kl_beta, old_lp, clip_eps):
+        return _capi.LossArgs(int(nb), 1 if grpo else 0, 1 if backward else 0, 1 if lora_off else 0, ptr(ref_lp),
+                              float(kl_beta), ptr(old_lp), float(clip_eps))
+
     def microbatch(self, ids, attn_mask, answer_mask, adv, P, T, nb, grpo, backward, lp_out=None,
-                   lora_off=False, ref_lp=None, kl_beta=0.0):
+                   lora_off=False, ref_lp=None, kl_beta=0.0, old_lp=None, clip_eps=0.0):
         """One micro-batch through the C++ driver. ids/attn_mask [B, P+T] int32, answer_mask [B,T] int32,
         adv [B] float64 (all on this device). Accumulates into lora_grad and self.loss_accum.
-        lora_off: adapter-disabled scoring pass (reference policy); ref_lp + kl_beta: optional KL term."""
+        lora_off: adapter-disabled scoring pass (reference policy); ref_lp + kl_beta: optional KL term;
+        old_lp [B,T] + clip_eps: optional clipped-ratio surrogate (b200rl_loss_args)."""
         B = ids.shape[0]
-        check(lib().b200rl_model_microbatch_ex(self.handle, ptr(ids), ptr(attn_mask), ptr(answer_mask), ptr(adv),
-                                               ptr(lp_out), ptr(self.loss_accum), B, P, T, nb, 1 if grpo else 0,
-                                               1 if backward else 0, 1 if lora_off else 0, ptr(ref_lp),
-                                               float(kl_beta), stream()), "model_microbatch")
+        a = self._loss_args(nb, grpo, backward, lora_off, ref_lp, kl_beta, old_lp, clip_eps)
+        check(lib().b200rl_model_pass(self.handle, ptr(ids), ptr(attn_mask), ptr(answer_mask), ptr(adv), ptr(lp_out),
+                                      ptr(self.loss_accum), B, P, T, C.byref(a), stream()), "model_pass")
 
     def microbatch_packed(self, packed, adv, nb, grpo, backward, lp_out=None, lora_off=False, ref_lp=None,
-                          kl_beta=0.0):
+                          kl_beta=0.0, old_lp=None, clip_eps=0.0):
         """Same as microbatch() on the packed shared-prompt layout (`packed`: packing.PackedDevice)."""
-        check(lib().b200rl_model_microbatch_packed(self.handle, C.byref(packed.c), ptr(adv), ptr(lp_out),
-                                                   ptr(self.loss_accum), nb, 1 if grpo else 0, 1 if backward else 0,
-                                                   1 if lora_off else 0, ptr(ref_lp), float(kl_beta), stream()),
-              "model_microbatch_packed")
+        a = self._loss_args(nb, grpo, backward, lora_off, ref_lp, kl_beta, old_lp, clip_eps)
+        check(lib().b200rl_model_pass_packed(self.handle, C.byref(packed.c), ptr(adv), ptr(lp_out), ptr(self.loss_accum),
+                                             C.byref(a), stream()), "model_pass_packed")
 
     def debug_tensor(self, name, layer, shape, dtype=torch.bfloat16):
         p = lib().b200rl_model_debug_ptr(self.handle, name.encode(), layer)

@@ -134,6 +134,15 @@ int b200rl_loss_coef_kl(const int* mask, const double* adv, float* coef, float* 
 int b200rl_loss_value_kl(const float* lp, const int* mask, const double* adv, const float* ref_lp, double beta,
                          double* accum, int Bm, int T, int grpo, void* stream);
 
+/* clipped-ratio surrogate (the reference's ratio is identically 1, distributed_actor.py:467):
+ * old_lp [rows] f32 = log-probs under the policy that generated the batch; clip_eps > 0 turns the per-token loss into
+ * -min(rho A, clip(rho, 1-eps, 1+eps) A), rho = exp(lp - old_lp).  old_lp NULL or clip_eps 0 = the plain forms above. */
+int b200rl_logprob_clip(void* logits, long long ld, const int* targets, const float* coef, const float* klw,
+                        const float* ref_lp, const float* old_lp, double clip_eps, float* lp_out, int rows, int V,
+                        int write_grad, void* stream);
+int b200rl_loss_value_clip(const float* lp, const int* mask, const double* adv, const float* ref_lp, double beta,
+                           const float* old_lp, double clip_eps, double* accum, int Bm, int T, int grpo, void* stream);
+
 /* ---- G9: group-relative advantages + top-k (distributed_trainer.py:262-294) ---------------- */
 int b200rl_group_advantage_topk(const double* rewards, double* values, double* baselines,
                                 int* topk_idx, double* topk_val, int G, int C, int k, int grpo,
@@ -256,6 +265,24 @@ typedef struct b200rl_packed_batch {
 int b200rl_model_microbatch_packed(b200rl_model* m, const b200rl_packed_batch* pb, const double* adv, float* lp_out,
                                    double* loss_accum, int nb, int grpo, int backward, int lora_off,
                                    const float* ref_lp, double kl_beta, void* stream);
+
+/* General form of the two calls above: every optional term of the loss in one argument block.
+ *   lora_off   adapter-disabled scoring pass (pi_ref); forward only
+ *   ref_lp / kl_beta     KL(pi || pi_ref) term, k3 estimator (north_star; absent from the reference)
+ *   old_lp / clip_eps    clipped-ratio surrogate against the generating policy's log-probs
+ * ref_lp / old_lp are [B*T] f32 device arrays or NULL.  All zero / NULL = exactly the reference's loss
+ * (distributed_actor.py:375, :467-470). */
+typedef struct b200rl_loss_args {
+  int nb, grpo, backward, lora_off;
+  const float* ref_lp;
+  double kl_beta;
+  const float* old_lp;
+  double clip_eps;
+} b200rl_loss_args;
+int b200rl_model_pass(b200rl_model* m, const int* ids, const int* attn_mask, const int* answer_mask, const double* adv,
+                      float* lp_out, double* loss_accum, int B, int P, int T, const b200rl_loss_args* args, void* stream);
+int b200rl_model_pass_packed(b200rl_model* m, const b200rl_packed_batch* pb, const double* adv, float* lp_out,
+                             double* loss_accum, const b200rl_loss_args* args, void* stream);
 
 /* per-op CUDA-event profiling of the driver (categories: 0 gemm, 1 skinny LoRA gemm, 2 dW gemm, 3 nf4
  * dequant, 4 attn fwd, 5 attn bwd, 6 row kernels, 7 logprob, 8 misc); read() returns sums since the last

@@ -15,7 +15,9 @@ What is NOT pinned by the reference (arithmetic lives in un-vendored dependencie
     blocksize=64)` published format (no double quantisation) — "parity unpinned" vs real bnb files;
   * optimizer: bnb Adam8bit is restated as fp32 torch.optim.Adam (8-bit state not reproducible) —
     post-step weights "parity unpinned";
-  * KL-to-reference term: absent from the reference (beta=0 reproduces it exactly).
+  * KL-to-reference term: absent from the reference (beta=0 reproduces it exactly);
+  * clipped-ratio surrogate / inner epochs (old_lp, clip_eps): absent from the reference (its ratio is identically 1);
+    clip_eps=0 or old_lp=None reproduces it exactly — the oracle restates THIS repo's definition, "parity unpinned".
 """
 from __future__ import annotations
 
@@ -181,7 +183,7 @@ def compute_current_policy_probs(params, cfg, ids, attn_mask, P, dtype=torch.flo
 
 
 def compute_loss(params, cfg, ids, attn_mask, answer_mask, rewards, P, train_batch_size, learner="pg",
-                 dtype=torch.float32, reference_quirks=True, kl_beta=0.0):
+                 dtype=torch.float32, reference_quirks=True, kl_beta=0.0, old_lp=None, clip_eps=0.0, lp_capture=None):
     """Learner.compute_loss (distributed_actor.py:349-395) / GRPOLearner.compute_loss (:440-493).
     Accumulates .grad on the LoRA tensors of `params` (those with requires_grad) and returns the float
     the reference returns: the SUM over micro-batches of the per-micro-batch mean loss (quirk Q2)."""
@@ -196,12 +198,24 @@ def compute_loss(params, cfg, ids, attn_mask, answer_mask, rewards, P, train_bat
             continue
         lp = compute_current_policy_probs(params, cfg, ids[sl], attn_mask[sl], P, dtype)
         m = answer_mask[sl]
-        if learner == "pg":
+        if lp_capture is not None:
+            lp_capture[sl] = lp.detach()
+        if old_lp is not None and clip_eps > 0:
+            # NOT in the reference (its ratio is exp(lp - lp.detach()) == 1, :467; parity unpinned):
+            # PPO / GRPO clipped surrogate against the log-probs of the policy that generated the batch,
+            #   min(rho * A, clip(rho, 1-eps, 1+eps) * A),  rho = exp(lp - old_lp),
+            # normalised like the reference's loss (mask, / len, mean over the micro-batch)
+            rho = torch.exp(lp - old_lp[sl].to(lp.device))
+            a = r[:, None].to(lp.dtype)
+            surr = torch.minimum(rho * a, torch.clamp(rho, 1 - clip_eps, 1 + clip_eps) * a)
+            loss = -((surr * m).sum(-1) / m.sum(-1)).mean()
+        elif learner == "pg":
             per_seq = (lp * m).sum(-1) / m.sum(-1)  # :375
+            loss = -(per_seq * r).mean()
         else:
             imp = torch.exp(lp - lp.detach())  # :467
             per_seq = (imp * m).sum(-1) / m.sum(-1)  # :470
-        loss = -(per_seq * r).mean()
+            loss = -(per_seq * r).mean()
         if kl_beta:
             # NOT in the reference (parity unpinned): KL(pi||pi_ref) with the k3 estimator, pi_ref = adapter off,
             # normalised exactly like the policy term (mask, /len, mean over the micro-batch)

@@ -416,3 +416,98 @@ def test_adapter_save_and_resume(cuda, tmp_path):
     assert torch.equal(ln.policy.lora_flat, flat0)
     lp2, _ = ln.compute_current_policy_probs(ln.policy, prompts, answers)
     assert torch.equal(lp2, lp0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clipped-ratio surrogate, inner epochs, optimizer state in checkpoints.  The reference has none of
+# these (ratio identically 1, one step per batch, no resume): the oracle restates THIS repo's definition — parity unpinned.
+# ---------------------------------------------------------------------------------------------------
+def _n4_setup(cuda, hd=128, lr=5e-3, **cfgkw):
+    ocfg = lo.OracleConfig(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=2 if hd == 128 else 4,
+                           n_kv_heads=1 if hd == 128 else 2, head_dim=hd, lora_r=16, lora_alpha=16)
+    params, nf4 = lo.make_params(ocfg, seed=13, lora_b_std=0.05)
+    P, T, B, N = 12, 36, 4, 8
+    prompts, answers, rewards = lo.make_batch(ocfg, N, P, T, seed=6, ragged=True, group_size=4, learner="grpo")
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer
+    from distrl_llm_b200.policy import Policy
+    pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, cuda, max_batch=2 * B, P=P, T=T)
+    ln = GRPOLearner(pol, IdTokenizer(), dict({"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": lr}, **cfgkw))
+    return ocfg, params, ln, prompts, answers, rewards, (P, T, B, N)
+
+
+@pytest.mark.parametrize("hd", [64, 128])
+def test_clipped_ratio_vs_oracle(cuda, hd):
+    eps = 0.1
+    ocfg, params, ln, prompts, answers, rewards, (P, T, B, N) = _n4_setup(cuda, hd=hd, clip_eps=eps)
+    ids, am, ansm = lo.pad_batch(prompts, answers, P, T)
+    ids, am, ansm = ids.to(cuda), am.to(cuda), ansm.to(cuda)
+    # "old policy" log-probs: the current ones shifted by a per-token perturbation large enough to leave the trust region
+    lp_a, mask_a = ln.compute_current_policy_probs(ln.policy, prompts[:B], answers[:B])
+    lp_b, mask_b = ln.compute_current_policy_probs(ln.policy, prompts[B:], answers[B:])
+    lp0 = torch.cat([lp_a, lp_b]) * torch.cat([mask_a, mask_b]).float()
+    g = torch.Generator(device=cuda).manual_seed(0)
+    old = (lp0 + 0.25 * torch.randn(lp0.shape, generator=g, device=cuda)) * ansm.float()
+    loss = ln.compute_loss(prompts, answers, list(rewards), old_lp=old)
+    grads = ln.export_gradients()
+    dparams = {k: (v.detach().to(cuda).requires_grad_(v.requires_grad)) for k, v in params.items()}
+    ref_grads, ref_loss = lo.compute_gradients(dparams, ocfg, ids, am, ansm, rewards, P, B, "grpo", old_lp=old, clip_eps=eps)
+    g_plain, loss_plain = lo.compute_gradients(dparams, ocfg, ids, am, ansm, rewards, P, B, "grpo")
+    assert abs(ref_loss - loss_plain) > 1e-3, "the clipping must be active in this test"
+    assert abs(loss - ref_loss) <= 5e-2 * abs(ref_loss) + 5e-3, (loss, ref_loss)
+    # clipping zeroes the gradient of whole tokens: a token whose ratio sits within bf16 error of the trust-region edge
+    # may fall on either side, so the global tolerance is looser than for the smooth losses
+    _compare_grads(grads, ref_grads, ocfg, ln.policy, cos_min=0.995, rel_max=1e-1)
+    # old_lp given but clip_eps = 0 -> exactly the reference loss
+    ln.clip_eps = 0.0
+    assert abs(ln.compute_loss(prompts, answers, list(rewards), old_lp=old) - loss_plain) < 1e-9
+
+
+def test_inner_epochs_equal_manual_steps(cuda):
+    """train() with inner_epochs = 2: epoch 0 is the reference's step and records the log-probs, epoch 1 is a clipped step
+    against them — bit-identical to the same two steps issued by hand."""
+    cand = lambda a, p, r: [{"answers": [a], "problem": [p], "rewards": [r]}]
+    _, _, ln, prompts, answers, rewards, (P, T, B, N) = _n4_setup(cuda, clip_eps=0.2, inner_epochs=2)
+    ln.train(cand(answers, prompts, rewards))
+    assert ln.policy.opt_step == 2 and len(ln.last_epoch_losses) == 2
+    _, _, m, _, _, _, _ = _n4_setup(cuda, clip_eps=0.2, inner_epochs=1)
+    old = torch.zeros(N, T, device=cuda)
+    m.compute_loss(prompts, answers, list(rewards), lp_capture=old)
+    m.policy.optimizer_step(m.lr)
+    m.compute_loss(prompts, answers, list(rewards), old_lp=old)
+    m.policy.optimizer_step(m.lr)
+    assert torch.equal(ln.policy.lora_flat, m.policy.lora_flat)
+    # and with the defaults (clip 0, 1 epoch) train() is the reference's single step
+    _, _, r1, _, _, _, _ = _n4_setup(cuda)
+    _, _, r2, _, _, _, _ = _n4_setup(cuda, inner_epochs=1, clip_eps=0.0)
+    r1.train(cand(answers, prompts, rewards))
+    r2.compute_loss(prompts, answers, list(rewards))
+    r2.policy.optimizer_step(r2.lr)
+    assert torch.equal(r1.policy.lora_flat, r2.policy.lora_flat) and r1.policy.opt_step == 1
+
+
+def test_checkpoint_carries_optimizer_state(cuda, tmp_path):
+    """save -> step -> load restores adapter, Adam moments and step counter; training on from the checkpoint equals
+    uninterrupted training bit for bit.  A PEFT-only directory (no optimizer_state.pt) resets the optimizer."""
+    import os
+    cand = lambda a, p, r: [{"answers": [a], "problem": [p], "rewards": [r]}]
+    _, _, ln, prompts, answers, rewards, _ = _n4_setup(cuda, lr=1e-3)
+    ln.train(cand(answers, prompts, rewards))
+    ln.train(cand(answers, prompts, rewards))
+    ln.save_checkpoint(str(tmp_path))
+    m0, v0, p0 = ln.policy.adam_m.clone(), ln.policy.adam_v.clone(), ln.policy.lora_flat.clone()
+    ln.train(cand(answers, prompts, rewards))
+    after3 = ln.policy.lora_flat.clone()
+    ln.load_checkpoint(str(tmp_path))
+    assert ln.policy.opt_step == 2 and torch.equal(ln.policy.adam_m, m0) and torch.equal(ln.policy.adam_v, v0)
+    assert torch.equal(ln.policy.lora_flat, p0)
+    ln.train(cand(answers, prompts, rewards))
+    assert torch.equal(ln.policy.lora_flat, after3), "resumed training must continue exactly where it stopped"
+    os.remove(os.path.join(str(tmp_path), "optimizer_state.pt"))
+    ln.load_checkpoint(str(tmp_path))
+    assert ln.policy.opt_step == 0 and float(ln.policy.adam_m.abs().max()) == 0.0 and float(ln.policy.adam_v.abs().max()) == 0.0
+    import json
+    conf = json.load(open(os.path.join(str(tmp_path), "adapter_config.json")))
+    conf["lora_alpha"] = 64.0
+    json.dump(conf, open(os.path.join(str(tmp_path), "adapter_config.json"), "w"))
+    with pytest.raises(ValueError, match="lora_alpha"):
+        ln.load_checkpoint(str(tmp_path))

@@ -198,7 +198,8 @@ class _RecordingPolicy:
     def zero_grad(self):
         self.calls.append(("zero_grad",))
 
-    def microbatch(self, ids, am, ansm, adv, P, T, nb, grpo, backward, lp_out=None, lora_off=False, ref_lp=None, kl_beta=0.0):
+    def microbatch(self, ids, am, ansm, adv, P, T, nb, grpo, backward, lp_out=None, lora_off=False, ref_lp=None, kl_beta=0.0,
+                   old_lp=None, clip_eps=0.0):
         self.calls.append(("mb", ids.clone(), None if adv is None else adv.clone(), nb, grpo, backward, lora_off, kl_beta))
 
 
