@@ -54,12 +54,16 @@ def create_actor_and_learner(number_of_actors=1, number_of_learners=1, model_nam
     share = bool(config.get("stub_generators_share_gpus", n_gpu < need))
     if not share and n_gpu < need:
         raise RuntimeError(f"Not enough GPUs available. Available: {n_gpu}, Required: {need}")
-    if n_gpu < number_of_learners:
+    if n_gpu < number_of_learners and not config.get("learner_gpus"):
         raise RuntimeError(f"Not enough GPUs for the learners. Available: {n_gpu}, Required: {number_of_learners}")
     # reference: actors on the first GPUs, learners on the next ones (:533-537); stub generators only need a GPU for the
     # adapter pull, so on a small box they share the learners' GPUs
     learner_gpus = list(range(number_of_learners)) if share else list(range(number_of_actors, need))
+    if config.get("learner_gpus"):   # explicit placement (tests: several learners on one GPU, each on its own stream)
+        learner_gpus = list(config["learner_gpus"])
+        assert len(learner_gpus) == number_of_learners
     actor_gpus = [learner_gpus[i % len(learner_gpus)] for i in range(number_of_actors)] if share else list(range(number_of_actors))
+    shared_dev = len(set(learner_gpus)) < len(learner_gpus)
     assert config["learner"] in ("grpo", "pg"), "Learner can be only 'pg' or 'grpo'!"
     cls = GRPOLearner if config["learner"] == "grpo" else Learner
     r, alpha = config["max_lora_rank"], config["lora_alpha"]
@@ -79,7 +83,7 @@ def create_actor_and_learner(number_of_actors=1, number_of_learners=1, model_nam
             return cls(build(), IdTokenizer(), config, gpu_id=learner_gpus[rank])
         return make, dev
 
-    learners = [local_rpc.ActorHandle(*learner_factory(i)) for i in range(number_of_learners)]
+    learners = [local_rpc.ActorHandle(*learner_factory(i), own_stream=shared_dev) for i in range(number_of_learners)]
     if number_of_learners > 1:   # same-process peers: plain pointers + peer access instead of IPC handles
         groups = local_rpc.get([l.p2p_local_group.remote() for l in learners])
         P2PGroup.wire_same_process(groups)

@@ -28,6 +28,10 @@ class StubGenerator:
     def attach_adapter(self, subscriber):
         self.adapter = subscriber
 
+    def stats(self):
+        return {"adapter_version": self.adapter_version, "generated_tokens": self.generated_tokens,
+                "adapter_checksum": None if self.adapter is None else float(self.adapter.flat.double().sum().item())}
+
     def generate(self, task, sampling_params=None):
         """task: {"problem": [prompt, ...], "solution": [...], <other dataset columns>} (a chunk made by
         Trainer.split_dict_lists).  Returns the task dict extended like distributed_actor.py:165-172."""

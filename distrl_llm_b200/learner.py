@@ -293,6 +293,13 @@ class BaseLearner:
     def vocab_size(self):
         return self.policy.cfg.vocab
 
+    def export_flat(self):
+        """The flat fp32 adapter on the host (tests / debugging)."""
+        torch.cuda.synchronize(self.policy.device)
+        if self.p2p is not None:
+            self.p2p.check()
+        return self.policy.lora_flat.detach().cpu().clone()
+
     # ---- adapter hand-off to the generators (SURVEY.md 8(f) N1) -------------------------------------------------------
     def adapter_publisher(self):
         """Create (once) the in-memory publisher of this learner's adapter and return its picklable description for the

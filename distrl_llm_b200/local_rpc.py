@@ -19,10 +19,14 @@ class _Method:
 
 
 class ActorHandle:
-    def __init__(self, factory, device=None):
-        """factory() builds the actor object INSIDE the actor's thread (so CUDA state belongs to that thread)."""
+    def __init__(self, factory, device=None, own_stream=False):
+        """factory() builds the actor object INSIDE the actor's thread (so CUDA state belongs to that thread).
+        own_stream: give the thread its own CUDA stream (torch's current stream is per thread) — needed when several
+        actors share one GPU, else their kernels would serialise on the default stream (and a learner spinning in the
+        P2P flag barrier would block the peer it is waiting for)."""
         self._pool = cf.ThreadPoolExecutor(max_workers=1)
         self._device = device
+        self._own_stream = own_stream
         self._obj = None
         self._pool.submit(self._init, factory).result()
 
@@ -30,6 +34,8 @@ class ActorHandle:
         if self._device is not None:
             import torch
             torch.cuda.set_device(self._device)
+            if self._own_stream:
+                torch.cuda.set_stream(torch.cuda.Stream(self._device))
         self._obj = factory()
 
     def _call(self, name, args, kwargs):
