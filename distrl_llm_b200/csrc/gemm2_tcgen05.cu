@@ -110,12 +110,20 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int BN, bool B_MN>
+// NT = 256-column sub-tiles per cluster tile.  NT = 1: one 256 x BN tile per work unit, accumulators double-buffered in
+// TMEM (the epilogue of tile i overlaps the mainloop of tile i+1).  NT = 2 (BN = 256 only): a 256 x 512 "wide" tile —
+// every k-block stages the A tile ONCE and two B sub-tiles, and issues two N = 256 UMMAs into the two TMEM accumulators.
+// Per flop this moves 25 % fewer bytes from L2 into shared memory (48 KB instead of 64 KB per CTA per 2 x 256 x 256 x 64
+// MACs): the 256 x 256 mainloop sits at the L2 -> SM fill limit, so the operand bytes, not the tensor
+// pipe, set its speed.  Price: both accumulators belong to the same tile, so a sub-tile's epilogue only overlaps the
+// next tile's mainloop from the moment ITS accumulator has been drained (tmem_empty per sub-tile).
+template <int BN, bool B_MN, int NT = 1>
 struct PairCfg {
-  static constexpr int BH = BN / 2;                      // B columns staged per CTA
+  static_assert(NT == 1 || BN == 256, "wide tiles are 2 x 256 columns");
+  static constexpr int BH = BN / 2;                      // B columns staged per CTA (per sub-tile)
   static constexpr int B_SLABS = (BH + 63) / 64;         // MN-major: 64-column swizzle slabs (the last may be partly used)
   static constexpr int B_TILE_BYTES = B_MN ? B_SLABS * 8192 : BH * BK * 2;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;  // per CTA
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + NT * B_TILE_BYTES;  // per CTA
   static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int STAGES_RAW = (220 * 1024) / STAGE_BYTES;
@@ -125,12 +133,12 @@ struct PairCfg {
 
 // EW = epilogue warps per CTA (4 or 8): the fused SwiGLU epilogues use 8, two per TMEM lane quadrant, each pair
 // splitting the accumulator columns.
-template <int BN, bool B_MN, int FUSE, int EW>
+template <int BN, bool B_MN, int FUSE, int EW, int NT>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const GemmParams p) {
-  using C = PairCfg<BN, B_MN>;
+  using C = PairCfg<BN, B_MN, NT>;
   constexpr int STAGES = C::STAGES;
   constexpr int BM2 = 2 * BM;  // rows per pair tile
   extern __shared__ uint8_t smem_raw[];
@@ -184,24 +192,28 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
       tile_coords(tile, p.num_m_blocks, p.num_n_blocks, p.gm, m_blk, n_blk);
       const int row0 = m_blk * BM2 + (int)rank * BM;
-      // FUSE 1: CTA 0 stages 128 gate rows of the weight, CTA 1 the 128 up rows with the same index
-      const int col0 = FUSE == 1 ? n_blk * C::BH + (int)rank * p.fuse_I : n_blk * BN + (int)rank * C::BH;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = smem_gen + stage * C::STAGE_BYTES;
-        uint8_t* sb = sa + A_TILE_BYTES;
         const bool seg2 = kb >= p.kb1;
         const CUtensorMap* ta = seg2 ? &tmA2 : &tmA1;
         const CUtensorMap* tb = seg2 ? &tmB2 : &tmB1;
         const int k0 = (seg2 ? kb - p.kb1 : kb) * BK;
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
         tma_load_2d_pair(sa, ta, &full_bar[stage], k0, row0);
-        if constexpr (!B_MN) {
-          tma_load_2d_pair(sb, tb, &full_bar[stage], k0, col0);
-        } else {
 #pragma unroll
-          for (int h = 0; h < C::B_SLABS; ++h)
-            tma_load_2d_pair(sb + h * 8192, tb, &full_bar[stage], col0 + h * 64, k0);
+        for (int t = 0; t < NT; ++t) {
+          const int n_sub = n_blk * NT + t;
+          // FUSE 1: CTA 0 stages 128 gate rows of the weight, CTA 1 the 128 up rows with the same index
+          const int col0 = FUSE == 1 ? n_sub * C::BH + (int)rank * p.fuse_I : n_sub * BN + (int)rank * C::BH;
+          uint8_t* sb = sa + A_TILE_BYTES + t * C::B_TILE_BYTES;
+          if constexpr (!B_MN) {
+            tma_load_2d_pair(sb, tb, &full_bar[stage], k0, col0);
+          } else {
+#pragma unroll
+            for (int h = 0; h < C::B_SLABS; ++h)
+              tma_load_2d_pair(sb + h * 8192, tb, &full_bar[stage], col0 + h * 64, k0);
+          }
         }
         if (!leader) mbar_arrive_remote(&full_bar[stage], 0);
         if (++stage == STAGES) {
@@ -221,22 +233,33 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++local) {
       int tile, kb_begin, kb_end, part, sidx;
       unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
-      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+      // accumulator slot / barrier phase: NT = 1 alternates the two slots tile by tile; NT = 2 uses slot t for
+      // sub-tile t of every tile
+      const int acc0 = NT == 1 ? (local & 1) : 0;
+      const uint32_t acc_phase = NT == 1 ? ((local >> 1) & 1) : (local & 1);
+      if constexpr (NT == 1) {
+        mbar_wait(&tmem_empty_bar[acc0], acc_phase ^ 1u);
+        tc_fence_after();
+      }
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-        const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
-                                   : make_smem_desc(sb + k * 32, 16, 1024);
-          umma_bf16_pair(tmem_d, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        for (int t = 0; t < NT; ++t) {
+          if (NT == 2 && kb == kb_begin) {   // sub-tile t may start as soon as the epilogue drained ITS accumulator
+            mbar_wait(&tmem_empty_bar[t], acc_phase ^ 1u);
+            tc_fence_after();
+          }
+          const uint32_t tmem_d = tmem_base + (acc0 + t) * C::ACC_STRIDE;
+          const uint32_t sb = sa + A_TILE_BYTES + t * C::B_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
+                                     : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16_pair(tmem_d, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit_pair(&empty_bar[stage]);
         if (++stage == STAGES) {
@@ -244,7 +267,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           phase ^= 1u;
         }
       }
-      umma_commit_pair(&tmem_full_bar[acc]);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) umma_commit_pair(&tmem_full_bar[acc0 + t]);
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
@@ -256,15 +280,43 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       int tile, kb_begin, kb_end, part, sidx, m_blk, n_blk;
       unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
       tile_coords(tile, p.num_m_blocks, p.num_n_blocks, p.gm, m_blk, n_blk);
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
       const int row = m_blk * BM2 + (int)rank * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
+      if (part == 0) {
+        // K-range 0 of a tail tile: wait for the same warp (rank, quad) of every other K-range of this tile
+        if (lane == 0) {
+          for (int s = 1; s < p.tail_split; ++s) {
+            const int* f = p.tail_flags + (sidx * p.tail_split + s) * 8 + rank * 4 + quad;
+            long long t0 = clock64();
+            while (ld_acquire_gpu(f) != p.tail_epoch) {
+              if (clock64() - t0 > 40000000000LL) {
+                printf("b200rl: gemm tail-split flag wait timed out (block %d)\n", blockIdx.x);
+                __trap();
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int t = 0; t < NT; ++t) {
+      const int acc = NT == 1 ? (local & 1) : t;
+      const uint32_t acc_phase = NT == 1 ? ((local >> 1) & 1) : (local & 1);
+      const int n_sub = n_blk * NT + t;   // 256-column sub-tile index along N (== n_blk for NT = 1)
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
       if constexpr (FUSE == 1) {
-        // accumulator columns [0,128) = gate(j0..), [128,256) = up(j0..) with j0 = n_blk * 128
+        if (n_sub * 128 >= p.fuse_I) {   // second sub-tile of the last wide tile when I / 128 is odd: nothing to store
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+            else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+          }
+          continue;
+        }
+        // accumulator columns [0,128) = gate(j0..), [128,256) = up(j0..) with j0 = n_sub * 128
         bf16* gu_row = reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc;
         bf16* act_row = p.aux_out + (long long)row * p.ld_aux;
 #pragma unroll 1
@@ -276,7 +328,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           if (row_ok) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const int col = n_blk * 128 + c * 32 + g * 8;
+              const int col = n_sub * 128 + c * 32 + g * 8;
               float a[8], b[8], o[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -300,7 +352,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         for (int c = half * (BN / 32 / NH); c < (half + 1) * (BN / 32 / NH); ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr0 + c * 32, r);
-          const int colc = n_blk * BN + c * 32;
+          const int colc = n_sub * BN + c * 32;
           bf16x8 gq[4], uq[4];
           if (row_ok) {
 #pragma unroll
@@ -332,7 +384,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       } else
       if (part > 0) {
         // K-range 1..S-1 of a tail tile: raw fp32 accumulators -> workspace, then raise this warp's flag
-        float* ws = p.tail_ws + ((long long)(sidx * (p.tail_split - 1) + (part - 1)) * 2 + rank) * (BM * BN);
+        float* ws = p.tail_ws + (((long long)(sidx * (p.tail_split - 1) + (part - 1)) * 2 + rank) * NT + t) * (BM * BN);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
@@ -344,26 +396,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             dst[g] = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
                                  __uint_as_float(r[4 * g + 3]));
         }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release_gpu(p.tail_flags + (sidx * p.tail_split + part) * 8 + rank * 4 + quad, p.tail_epoch);
-      } else {
-        if (part == 0) {
-          // wait for the same warp (rank, quad) of every other K-range of this tile
-          if (lane == 0) {
-            for (int s = 1; s < p.tail_split; ++s) {
-              const int* f = p.tail_flags + (sidx * p.tail_split + s) * 8 + rank * 4 + quad;
-              long long t0 = clock64();
-              while (ld_acquire_gpu(f) != p.tail_epoch) {
-                if (clock64() - t0 > 40000000000LL) {
-                  printf("b200rl: gemm tail-split flag wait timed out (block %d)\n", blockIdx.x);
-                  __trap();
-                }
-              }
-            }
-          }
+        if (t == NT - 1) {   // every sub-tile of this K-range is in the workspace: raise this warp's flag
+          __threadfence();
           __syncwarp();
+          if (lane == 0) st_release_gpu(p.tail_flags + (sidx * p.tail_split + part) * 8 + rank * 4 + quad, p.tail_epoch);
         }
+      } else {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
@@ -372,7 +410,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           if (part == 0) {
             for (int s = 1; s < p.tail_split; ++s) {
               const float4* src = reinterpret_cast<const float4*>(
-                  p.tail_ws + ((long long)(sidx * (p.tail_split - 1) + (s - 1)) * 2 + rank) * (BM * BN) +
+                  p.tail_ws + (((long long)(sidx * (p.tail_split - 1) + (s - 1)) * 2 + rank) * NT + t) * (BM * BN) +
                   ((c * 4 + quad) * 32 + lane) * 32);
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
@@ -384,7 +422,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
               }
             }
           }
-          if (row_ok) epilogue_store32(p, r, row, n_blk * BN + c * 32, 0);
+          if (row_ok) epilogue_store32(p, r, row, n_sub * BN + c * 32, 0);
         }
       }
       tc_fence_before();
@@ -393,6 +431,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         if (leader) mbar_arrive(&tmem_empty_bar[acc]);
         else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
       }
+      }  // sub-tile loop
     }
   }
 
@@ -448,16 +487,16 @@ static int tail_workspace(cudaStream_t stream, size_t bytes, TailWs** out) {
   return 0;
 }
 
-template <int BN, bool B_MN, int FUSE = 0, int EW = 4>
+template <int BN, bool B_MN, int FUSE = 0, int EW = 4, int NT = 1>
 static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
-  using C = PairCfg<BN, B_MN>;
+  using C = PairCfg<BN, B_MN, NT>;
   GemmParams p;
   p.M = a.M;
   p.N = a.N;
   p.kb1 = (a.K1 + BK - 1) / BK;
   p.kb2 = (a.K2 + BK - 1) / BK;
   p.num_m_blocks = (a.M + 2 * BM - 1) / (2 * BM);
-  p.num_n_blocks = FUSE == 1 ? a.N / BN : (a.N + BN - 1) / BN;
+  p.num_n_blocks = FUSE == 1 ? (a.N / BN + NT - 1) / NT : (a.N + BN * NT - 1) / (BN * NT);
   p.splits = 1;
   p.kb_per_split = p.kb1 + p.kb2;
   p.C = a.C;
@@ -486,7 +525,7 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
     tA2 = tA1;
     tB2 = tB1;
   }
-  auto kern = gemm_pair_kernel<BN, B_MN, FUSE, EW>;
+  auto kern = gemm_pair_kernel<BN, B_MN, FUSE, EW, NT>;
   static bool attr_set = false;
   if (!attr_set) {
     B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -505,7 +544,7 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   if (S > 1) {
     const int rem = tiles % clusters;
     TailWs* w = nullptr;
-    int rc2 = tail_workspace(stream, (size_t)rem * (S - 1) * 2 * BM * BN * sizeof(float), &w);
+    int rc2 = tail_workspace(stream, (size_t)rem * (S - 1) * 2 * NT * BM * BN * sizeof(float), &w);
     if (rc2) return rc2;
     p.tail_first = tiles - rem;
     p.tail_split = S;
@@ -545,18 +584,38 @@ static int fuse_epilogue_warps() {
 
 bool gemm_fuse_supported(int M, int I) { return gemm_pair_enabled() && M > BM && I % 128 == 0; }
 
+// Wide (256 x 512) tiles: -1 = env B200RL_GEMM_WIDE (default on), 0 / 1 = forced by b200rl_gemm_set_wide (tests, A/B runs).
+static int g_wide = -1;
+bool gemm_pair_wide_enabled() {
+  if (g_wide < 0) {
+    const char* e = getenv("B200RL_GEMM_WIDE");
+    g_wide = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_wide != 0;
+}
+// Wide tiles pay when there is enough work to keep every CTA pair busy with them: at least one wide tile per pair.
+static bool want_wide(const GemmArgs& a, int n_cols) {
+  if (!gemm_pair_wide_enabled()) return false;
+  const long long mb = (a.M + 2 * BM - 1) / (2 * BM);
+  const long long wide_tiles = mb * ((n_cols + 511) / 512);
+  return n_cols >= 512 && wide_tiles >= num_sms() / 2;
+}
+
 int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream) {
   const bool b_mn = (a.mn_major & 2) != 0;
   if (a.fuse == 1) {
     B200RL_REQUIRE(!b_mn && !a.c_fp32 && !a.bias && !a.residual && a.aux && a.N % 256 == 0 && a.ld_aux % 8 == 0,
                    "gemm(fused swiglu fwd): needs TN layout, bf16 C, N = 2I with I %% 128 == 0, no bias/residual");
+    if (want_wide(a, a.N)) return launch_pair<256, false, 1, 8, 2>(a, stream);
     return fuse_epilogue_warps() == 8 ? launch_pair<256, false, 1, 8>(a, stream) : launch_pair<256, false, 1, 4>(a, stream);
   }
   if (a.fuse == 2) {
     B200RL_REQUIRE(b_mn && !a.c_fp32 && !a.bias && !a.residual && a.aux && a.N % 8 == 0 && a.ld_aux % 8 == 0,
                    "gemm(fused swiglu bwd): needs dX layout, bf16 C, no bias/residual");
+    if (want_wide(a, a.N)) return launch_pair<256, true, 2, 8, 2>(a, stream);
     return fuse_epilogue_warps() == 8 ? launch_pair<256, true, 2, 8>(a, stream) : launch_pair<256, true, 2, 4>(a, stream);
   }
+  if (bn == 512) return b_mn ? launch_pair<256, true, 0, 4, 2>(a, stream) : launch_pair<256, false, 0, 4, 2>(a, stream);
   if (bn == 256) return b_mn ? launch_pair<256, true>(a, stream) : launch_pair<256, false>(a, stream);
   if (bn == 224) return b_mn ? launch_pair<224, true>(a, stream) : launch_pair<224, false>(a, stream);
   if (bn == 192) return b_mn ? launch_pair<192, true>(a, stream) : launch_pair<192, false>(a, stream);
@@ -569,6 +628,11 @@ int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream) {
 // test / bisection switch: 1 = use CTA-pair kernels where applicable (default), 0 = single-CTA only
 extern "C" int b200rl_gemm_set_cta_pair(int enable) {
   b200rl::g_pair_enabled = enable ? 1 : 0;
+  return 0;
+}
+// test / A-B switch for the wide (256 x 512) pair tiles: 1 = use them where applicable (default), 0 = 256 x 256 only
+extern "C" int b200rl_gemm_set_wide(int enable) {
+  b200rl::g_wide = enable ? 1 : 0;
   return 0;
 }
 // test / bisection switch for the K-split of the last partial wave (default on; env B200RL_GEMM_TAIL_SPLIT=0 disables)

@@ -220,5 +220,6 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream);             // gemm_t
 int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream);  // gemm2_tcgen05.cu
 void gemm_pair_set_tail_split(int enable);
 bool gemm_pair_enabled();
+bool gemm_pair_wide_enabled();   // 256 x 512 "wide" pair tiles (gemm2_tcgen05.cu, PairCfg NT = 2)
 
 }  // namespace b200rl

@@ -286,11 +286,16 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
   }
   // CTA-pair kernel (cta_group::2, 256-row tiles) for the large activation x weight GEMMs
   if (gemm_pair_enabled() && a.splits <= 1 && a.M > BM && a.N >= 256 &&
-      (a.force_bn == 0 || a.force_bn == 128 || a.force_bn == 192 || a.force_bn == 224 || a.force_bn == 256)) {
+      (a.force_bn == 0 || a.force_bn == 128 || a.force_bn == 192 || a.force_bn == 224 || a.force_bn == 256 ||
+       a.force_bn == 512)) {
     // Pair tiles are 256 x BN.  256 x 256 is the most efficient per flop (the 128-wide pair tile is smem-bound
     // again, measured 630-750 TFLOP/s), but N = 3584 (14 tiles of 256) leaves the last of 3.4 waves 40 % full on
     // 74 CTA pairs: pick the width in {256, 224, 192} with the lowest waves x per-tile cost.
     int pbn = a.force_bn;
+    // wide 256 x 512 tiles (25 % fewer operand bytes per flop) when every CTA pair gets at least one of them
+    if (pbn == 0 && gemm_pair_wide_enabled() && a.N >= 512 &&
+        (long long)((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + 511) / 512) >= num_sms() / 2)
+      pbn = 512;
     if (pbn == 0) {
       const int clusters = num_sms() / 2;
       const long long mb = (a.M + 2 * BM - 1) / (2 * BM);

@@ -44,6 +44,7 @@ int b200rl_gemm(const void* A1, long long lda1, const void* B1, long long ldb1, 
 int b200rl_gemm_set_cta_pair(int enable);
 /* 1 (default) = the CTA-pair GEMM splits the tiles of its last, partially filled wave along K (gemm2_tcgen05.cu) */
 int b200rl_gemm_set_tail_split(int enable);
+int b200rl_gemm_set_wide(int enable); /* 1 (default): 256 x 512 CTA-pair tiles where every pair gets one; 0: 256 x 256 only */
 /* G1 + G5 fused (CTA-pair kernel; needs M > 128 and I % 128 == 0, else B200RL_ERR_*):
  * mode 1: gu[M,2I] = A1.B1^T + A2.B2^T (gate rows then up rows of the weight, Qwen2MLP gate_proj|up_proj) and
  *         aux = act[M,I] = silu(gate)*up written by the same epilogue;

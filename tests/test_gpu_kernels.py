@@ -45,6 +45,12 @@ GEMM_SHAPES = [
     (600, 3584, 512, 64, 224),    # 224-wide pair tile (N = 16 x 224)
     (900, 1000, 320, 64, 224),    # ragged N with the 224 tile
     (4446, 3584, 1024, 64, 192),
+    # wide 256 x 512 pair tiles (force_bn = 512): full tiles, ragged N with a partly and a fully out-of-range sub-tile
+    (4446, 3584, 1024, 64, 512),
+    (8892, 4608, 3584, 64, 512),
+    (600, 1024, 512, 64, 512),
+    (900, 1000, 320, 64, 512),
+    (700, 600, 192, 0, 512),
 ]
 
 
@@ -59,8 +65,8 @@ def gemm_mode(request, cuda):
 
 @pytest.mark.parametrize("M,N,K1,K2,bn", GEMM_SHAPES)
 def test_gemm_tn(cuda, gemm_mode, M, N, K1, K2, bn):
-    if bn == 224 and not gemm_mode:
-        pytest.skip("224-wide tiles exist only in the CTA-pair kernel")
+    if bn in (224, 512) and not gemm_mode:
+        pytest.skip("224-wide and 512-wide tiles exist only in the CTA-pair kernel")
     from distrl_llm_b200 import ops
     a1 = _rand((M, K1), cuda, seed=1)
     b1 = _rand((N, K1), cuda, seed=2)
@@ -85,7 +91,8 @@ def test_gemm_tn(cuda, gemm_mode, M, N, K1, K2, bn):
                                         (8892, 3584, 152064, True),    # same with the ragged last m-block
                                         (8892, 3584, 37888, True),     # gate|up dX: K = 2 x inter (+ 64 LoRA)
                                         (4446, 3584, 37888, True)])    # one micro-batch per pass
-def test_gemm_tail_split(cuda, M, N, K1, b_mn):
+@pytest.mark.parametrize("bn", [256, 512], ids=["tile256", "wide512"])
+def test_gemm_tail_split(cuda, M, N, K1, b_mn, bn):
     """CTA-pair GEMM with the last partial wave split along K (gemm2_tcgen05.cu): same result as with the split
     disabled, up to the fp32 summation order of the K-ranges; fp32 output compared tightly against torch."""
     from distrl_llm_b200 import _capi, ops
@@ -107,8 +114,8 @@ def test_gemm_tail_split(cuda, M, N, K1, b_mn):
         for en in (1, 0):
             _capi.lib().b200rl_gemm_set_tail_split(en)
             for _ in range(3):   # repeated launches reuse the workspace with a new epoch
-                o32 = ops.gemm(a1, b1, a2, b2, bias=bias, residual=res, alpha=0.25, out_fp32=True, force_bn=256, b_mn=b_mn)
-            o16 = ops.gemm(a1, b1, a2, b2, bias=bias, residual=res, alpha=0.25, force_bn=256, b_mn=b_mn)
+                o32 = ops.gemm(a1, b1, a2, b2, bias=bias, residual=res, alpha=0.25, out_fp32=True, force_bn=bn, b_mn=b_mn)
+            o16 = ops.gemm(a1, b1, a2, b2, bias=bias, residual=res, alpha=0.25, force_bn=bn, b_mn=b_mn)
             torch.cuda.synchronize()
             # fp32 accumulation over K: 2e-5 up to K = 16k; the K = 152064 reduction is allowed 1e-4
             assert _rel_err(o32, ref) < (2e-5 if K1 <= 16384 else 1e-4) and _rel_err(o16, ref) < 4e-3
@@ -118,14 +125,17 @@ def test_gemm_tail_split(cuda, M, N, K1, b_mn):
     assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-3 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("M,I,H", [(300, 256, 192), (4446, 1024, 512), (700, 18944, 256)])
-def test_gemm_swiglu_fused_is_bit_identical(cuda, M, I, H):
-    """G1+G5 fusion (gemm2_tcgen05.cu FUSE 1/2): the fused epilogues give exactly the bits of GEMM + row kernel."""
+@pytest.mark.parametrize("wide", [1, 0], ids=["wide512", "tile256"])
+@pytest.mark.parametrize("M,I,H", [(300, 256, 192), (4446, 1024, 512), (700, 18944, 256), (4446, 1152, 512), (8892, 18944, 128)])
+def test_gemm_swiglu_fused_is_bit_identical(cuda, M, I, H, wide):
+    """G1+G5 fusion (gemm2_tcgen05.cu FUSE 1/2): the fused epilogues give exactly the bits of GEMM + row kernel, with the
+    256 x 512 wide tiles (I / 128 = 9 exercises the skipped second sub-tile of the last wide tile) and without."""
     from distrl_llm_b200 import _capi, ops
     lib = _capi.lib()
     K2 = 64
     st = _capi.stream()
     try:
+        lib.b200rl_gemm_set_wide(wide)
         lib.b200rl_gemm_set_tail_split(0)      # same K summation order in both paths
         # forward: gu = h.Wgu^T + u.Bgu^T ; act = silu(gate)*up
         h, u = _rand((M, H), cuda, seed=1), _rand((M, K2), cuda, seed=2)
@@ -151,6 +161,27 @@ def test_gemm_swiglu_fused_is_bit_identical(cuda, M, I, H):
         assert torch.equal(dgu.view(torch.int16), dgu_ref.view(torch.int16))
     finally:
         lib.b200rl_gemm_set_tail_split(1)
+        lib.b200rl_gemm_set_wide(1)
+
+
+@pytest.mark.parametrize("b_mn", [False, True], ids=["tn", "dx"])
+def test_gemm_wide_tile_is_bit_identical_to_256(cuda, b_mn):
+    """256 x 512 pair tiles (two N = 256 UMMAs per k-step sharing the A stage) vs 256 x 256 tiles: every output element is
+    the same K-ordered fp32 accumulation, so the results agree bit for bit (tail split off: it changes the K order)."""
+    from distrl_llm_b200 import _capi, ops
+    M, N, K1, K2 = 2300, 3584, 2048, 64
+    a1, a2 = _rand((M, K1), cuda, seed=1), _rand((M, K2), cuda, seed=3)
+    b1 = _rand((K1, N) if b_mn else (N, K1), cuda, seed=2)
+    b2 = _rand((K2, N) if b_mn else (N, K2), cuda, seed=4)
+    res = _rand((M, N), cuda, seed=6)
+    try:
+        _capi.lib().b200rl_gemm_set_tail_split(0)
+        o256 = ops.gemm(a1, b1, a2, b2, residual=res, force_bn=256, b_mn=b_mn)
+        o512 = ops.gemm(a1, b1, a2, b2, residual=res, force_bn=512, b_mn=b_mn)
+        torch.cuda.synchronize()
+    finally:
+        _capi.lib().b200rl_gemm_set_tail_split(1)
+    assert torch.equal(o256.view(torch.int16), o512.view(torch.int16))
 
 
 @pytest.mark.parametrize("tokens,splits", [(4446, 2), (700, 1), (1000, 4)])
@@ -201,10 +232,12 @@ def test_gemm_epilogues(cuda, gemm_mode):
                                            (640, 3584, 4608, 64, 256), (4100, 1024, 2048, 64, 192),
                                            (512, 384, 256, 128, 128), (6896, 3584, 1024, 64, 0),
                                            (600, 3584, 512, 64, 224), (900, 1000, 320, 64, 224),
-                                           (700, 1000, 320, 64, 192)])
+                                           (700, 1000, 320, 64, 192),
+                                           (4446, 3584, 4608, 64, 512), (900, 1000, 320, 64, 512), (700, 600, 192, 0, 512),
+                                           (8892, 3584, 18944, 64, 512)])
 def test_gemm_dx_form(cuda, gemm_mode, M, N, K1, K2, bn):
-    if bn == 224 and not gemm_mode:
-        pytest.skip("224-wide tiles exist only in the CTA-pair kernel")
+    if bn in (224, 512) and not gemm_mode:
+        pytest.skip("224-wide and 512-wide tiles exist only in the CTA-pair kernel")
     """dX form: C = A1 @ B1 + A2 @ B2 with the B operands stored [K, N] (weights as stored [out, in])."""
     from distrl_llm_b200 import ops
     a1 = _rand((M, K1), cuda, seed=1)
