@@ -52,6 +52,9 @@ SIGNATURES = {
     "b200rl_gemm_set_cta_pair": (c_int, [c_int]),
     "b200rl_gemm_set_tail_split": (c_int, [c_int]),
     "b200rl_gemm_set_wide": (c_int, [c_int]),
+    "b200rl_gemm_set_ext": (c_int, [c_int]),
+    "b200rl_gemm_lora": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_float, c_void_p, c_ll, c_void_p, c_ll,
+                                 c_int, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "b200rl_gemm_dw_grouped": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                        c_void_p]),
     "b200rl_gemm_swiglu": (c_int, [c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int,

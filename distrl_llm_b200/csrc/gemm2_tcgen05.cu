@@ -137,7 +137,7 @@ template <int BN, bool B_MN, int FUSE, int EW, int NT>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmExt, const GemmParams p) {
   using C = PairCfg<BN, B_MN, NT>;
   constexpr int STAGES = C::STAGES;
   constexpr int BM2 = 2 * BM;  // rows per pair tile
@@ -168,6 +168,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     tma_prefetch_desc(&tmB1);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB2);
+    tma_prefetch_desc(&tmExt);
   }
   if (warp == 2) tmem_alloc2(&tmem_base_smem, C::TMEM_COLS);
   tc_fence_before();
@@ -181,21 +182,65 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int num_clusters = gridDim.x >> 1;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;  // num_m_blocks counts 256-row pair tiles
   const int kb_total = p.kb1 + p.kb2;
-  const int num_units = num_tiles <= p.tail_first ? num_tiles : p.tail_first + (num_tiles - p.tail_first) * p.tail_split;
+  // work units: [0, n_ext) ext units (LoRA intermediate of m-block `unit`), then the tiles / tail K-ranges
+  const int n_ext = p.n_ext;
+  const int num_units = n_ext + (num_tiles <= p.tail_first ? num_tiles : p.tail_first + (num_tiles - p.tail_first) * p.tail_split);
+  // bytes one CTA stages per k-block of an ext unit: its 128 rows of A + its half of the ext operand
+  const uint32_t ext_b_bytes = B_MN ? ((p.ext_n / 2 + 63) / 64) * 8192u : (uint32_t)(p.ext_n / 2) * BK * 2;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
     for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      if (unit < n_ext) {
+        // ---- ext unit: A rows of m-block `unit` x the whole ext operand, over K1 ----
+        const int row0 = unit * BM2 + (int)rank * BM;
+        for (int kb = 0; kb < p.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem_gen + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_TILE_BYTES + ext_b_bytes));
+          tma_load_2d_pair(sa, &tmA1, &full_bar[stage], kb * BK, row0);
+          if constexpr (!B_MN) {
+            tma_load_2d_pair(sb, &tmExt, &full_bar[stage], kb * BK, (int)rank * (p.ext_n / 2));
+          } else {
+            for (int h = 0; h < (p.ext_n / 2 + 63) / 64; ++h)
+              tma_load_2d_pair(sb + h * 8192, &tmExt, &full_bar[stage], (int)rank * (p.ext_n / 2) + h * 64, kb * BK);
+          }
+          if (!leader) mbar_arrive_remote(&full_bar[stage], 0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        continue;
+      }
       int tile, kb_begin, kb_end, part, sidx, m_blk, n_blk;
-      unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
+      unit_decode(p, unit - n_ext, kb_total, tile, kb_begin, kb_end, part, sidx);
       tile_coords(tile, p.num_m_blocks, p.num_n_blocks, p.gm, m_blk, n_blk);
       const int row0 = m_blk * BM2 + (int)rank * BM;
+      bool ext_ready = n_ext == 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = smem_gen + stage * C::STAGE_BYTES;
         const bool seg2 = kb >= p.kb1;
+        if (seg2 && !ext_ready) {
+          // the K-extension reads U rows of this CTA, written by the four epilogue warps of the same rank of the ext unit
+          // of this m-block (a lower-numbered unit: it is running or done, never queued behind this one)
+          const int* f = p.ext_flags + (m_blk * 2 + (int)rank) * 4;
+          for (int q = 0; q < 4; ++q) {
+            long long t0 = clock64();
+            while (ld_acquire_gpu(f + q) != p.ext_epoch) {
+              if (clock64() - t0 > 40000000000LL) {
+                printf("b200rl: gemm ext-unit flag wait timed out (block %d, m-block %d)\n", blockIdx.x, m_blk);
+                __trap();
+              }
+            }
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes of U -> this thread's TMA (async proxy) reads
+          ext_ready = true;
+        }
         const CUtensorMap* ta = seg2 ? &tmA2 : &tmA1;
         const CUtensorMap* tb = seg2 ? &tmB2 : &tmB1;
         const int k0 = (seg2 ? kb - p.kb1 : kb) * BK;
@@ -227,16 +272,47 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     // instruction M = 256 (both CTAs), N = BN
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((B_MN ? 1u : 0u) << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
+    const uint32_t idesc_ext = (1u << 4) | (1u << 7) | (1u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                               ((uint32_t)(p.ext_n >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
-    int local = 0;
+    int local = 0;    // units processed so far (NT = 1: accumulator slot = local & 1; NT = 2: uses of slot 0)
+    int local1 = 0;   // NT = 2: uses of slot 1 (ext units only touch slot 0)
     for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++local) {
+      if (unit < n_ext) {
+        const int acc = NT == 1 ? (local & 1) : 0;
+        const uint32_t ph = NT == 1 ? ((local >> 1) & 1) : (local & 1);
+        mbar_wait(&tmem_empty_bar[acc], ph ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+        for (int kb = 0; kb < p.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
+                                     : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16_pair(tmem_d, da, db, idesc_ext, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_pair(&tmem_full_bar[acc]);
+        continue;
+      }
       int tile, kb_begin, kb_end, part, sidx;
-      unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
-      // accumulator slot / barrier phase: NT = 1 alternates the two slots tile by tile; NT = 2 uses slot t for
-      // sub-tile t of every tile
+      unit_decode(p, unit - n_ext, kb_total, tile, kb_begin, kb_end, part, sidx);
+      // accumulator slot / barrier phase: NT = 1 alternates the two slots unit by unit; NT = 2 uses slot t for
+      // sub-tile t of every tile (slot 0 also serves the ext units, hence one use counter per slot)
       const int acc0 = NT == 1 ? (local & 1) : 0;
       const uint32_t acc_phase = NT == 1 ? ((local >> 1) & 1) : (local & 1);
+      const uint32_t acc_phase1 = local1 & 1;
       if constexpr (NT == 1) {
         mbar_wait(&tmem_empty_bar[acc0], acc_phase ^ 1u);
         tc_fence_after();
@@ -248,7 +324,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           if (NT == 2 && kb == kb_begin) {   // sub-tile t may start as soon as the epilogue drained ITS accumulator
-            mbar_wait(&tmem_empty_bar[t], acc_phase ^ 1u);
+            mbar_wait(&tmem_empty_bar[t], (t == 0 ? acc_phase : acc_phase1) ^ 1u);
             tc_fence_after();
           }
           const uint32_t tmem_d = tmem_base + (acc0 + t) * C::ACC_STRIDE;
@@ -269,16 +345,55 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       }
 #pragma unroll
       for (int t = 0; t < NT; ++t) umma_commit_pair(&tmem_full_bar[acc0 + t]);
+      ++local1;
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;  // 0, or 1 for the second warp of a quadrant (EW == 8)
     constexpr int NH = EW / 4;          // column shares
-    int local = 0;
+    int local = 0, local1 = 0;
     for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++local) {
+      if (unit < n_ext) {
+        // ---- ext unit: U[rows of m-block `unit`, ext_n] = ext_alpha * accumulator, bf16; then raise this warp's flag ----
+        const int acc = NT == 1 ? (local & 1) : 0;
+        const uint32_t ph = NT == 1 ? ((local >> 1) & 1) : (local & 1);
+        mbar_wait(&tmem_full_bar[acc], ph);
+        tc_fence_after();
+        if (half == 0) {
+          const int row = unit * BM2 + (int)rank * BM + quad * 32 + lane;
+          const uint32_t taddr0 = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+          for (int c = 0; c < p.ext_n / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr0 + c * 32, r);
+            tmem_ld_wait();
+            if (row < p.M) {
+              bf16* dst = p.ext_out + (long long)row * p.ld_ext + c * 32;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * p.ext_alpha;
+                *reinterpret_cast<bf16x8*>(dst + g * 8) = pack8(v);
+              }
+            }
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");   // U is read back through TMA (async proxy) by the consumers
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) st_release_gpu(p.ext_flags + (unit * 2 + (int)rank) * 4 + quad, p.ext_epoch);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+          else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+        }
+        continue;
+      }
       int tile, kb_begin, kb_end, part, sidx, m_blk, n_blk;
-      unit_decode(p, unit, kb_total, tile, kb_begin, kb_end, part, sidx);
+      unit_decode(p, unit - n_ext, kb_total, tile, kb_begin, kb_end, part, sidx);
       tile_coords(tile, p.num_m_blocks, p.num_n_blocks, p.gm, m_blk, n_blk);
       const int row = m_blk * BM2 + (int)rank * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
@@ -301,7 +416,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 #pragma unroll 1
       for (int t = 0; t < NT; ++t) {
       const int acc = NT == 1 ? (local & 1) : t;
-      const uint32_t acc_phase = NT == 1 ? ((local >> 1) & 1) : (local & 1);
+      const uint32_t acc_phase = NT == 1 ? ((local >> 1) & 1) : ((t == 0 ? local : local1) & 1);
       const int n_sub = n_blk * NT + t;   // 256-column sub-tile index along N (== n_blk for NT = 1)
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -432,6 +547,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
       }
       }  // sub-tile loop
+      ++local1;
     }
   }
 
@@ -459,7 +575,10 @@ struct TailWs {
   int* flags = nullptr;
   size_t ws_bytes = 0;
   int epoch = 0;
+  int* ext_flags = nullptr;   // ext units: [EXT_MAX_MBLOCKS][2][4]
+  int ext_epoch = 0;
 };
+static constexpr int EXT_MAX_MBLOCKS = 4096;   // 1M rows per launch
 static std::mutex g_tail_mu;
 static std::map<std::pair<int, cudaStream_t>, TailWs> g_tail_ws;
 static int g_tail_enabled = -1;
@@ -472,7 +591,7 @@ static int tail_workspace(cudaStream_t stream, size_t bytes, TailWs** out) {
   B200RL_CUDA_OK(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_tail_mu);
   TailWs& w = g_tail_ws[std::make_pair(dev, stream)];
-  if (w.ws_bytes < bytes) {
+  if (bytes > 0 && w.ws_bytes < bytes) {
     if (w.ws) B200RL_CUDA_OK(cudaFree(w.ws));  // synchronises: no kernel still uses the old buffer
     w.ws = nullptr;
     w.ws_bytes = 0;
@@ -482,6 +601,10 @@ static int tail_workspace(cudaStream_t stream, size_t bytes, TailWs** out) {
   if (!w.flags) {
     B200RL_CUDA_OK(cudaMalloc(&w.flags, TAIL_MAX_FLAGS * sizeof(int)));
     B200RL_CUDA_OK(cudaMemset(w.flags, 0, TAIL_MAX_FLAGS * sizeof(int)));
+  }
+  if (!w.ext_flags) {
+    B200RL_CUDA_OK(cudaMalloc(&w.ext_flags, EXT_MAX_MBLOCKS * 8 * sizeof(int)));
+    B200RL_CUDA_OK(cudaMemset(w.ext_flags, 0, EXT_MAX_MBLOCKS * 8 * sizeof(int)));
   }
   *out = &w;
   return 0;
@@ -514,7 +637,7 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
     p.aux_out = reinterpret_cast<bf16*>(a.aux);
     p.ld_aux = a.ld_aux;
   }
-  CUtensorMap tA1, tB1, tA2, tB2;
+  CUtensorMap tA1, tB1, tA2, tB2, tExt;
   int rc;
   if ((rc = make_map(&tA1, a.A1, a.K1, a.M, a.lda1, BK, BM))) return rc;
   if ((rc = B_MN ? make_map(&tB1, a.B1, a.N, a.K1, a.ldb1, 64, BK) : make_map(&tB1, a.B1, a.K1, a.N, a.ldb1, BK, C::BH))) return rc;
@@ -525,6 +648,21 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
     tA2 = tA1;
     tB2 = tB1;
   }
+  const bool ext = a.ext_B != nullptr;
+  if (ext) {
+    B200RL_REQUIRE(a.K2 == 64 || a.K2 == 128, "gemm(ext): the LoRA intermediate must be 64 or 128 wide (K2=%d)", a.K2);
+    B200RL_REQUIRE(p.num_m_blocks <= EXT_MAX_MBLOCKS, "gemm(ext): too many row blocks (%d)", p.num_m_blocks);
+    // forward: Acat [K2, K1] K-major, each CTA stages K2/2 rows; dX form: Bcat [K1, K2] MN-major, 64-column slabs
+    if ((rc = B_MN ? make_map(&tExt, a.ext_B, a.K2, a.K1, a.ld_ext_b, 64, BK)
+                   : make_map(&tExt, a.ext_B, a.K1, a.K2, a.ld_ext_b, BK, a.K2 / 2))) return rc;
+    p.n_ext = p.num_m_blocks;
+    p.ext_n = a.K2;
+    p.ext_out = reinterpret_cast<bf16*>(const_cast<void*>(a.A2));
+    p.ld_ext = a.lda2;
+    p.ext_alpha = a.ext_alpha;
+  } else {
+    tExt = tB1;
+  }
   auto kern = gemm_pair_kernel<BN, B_MN, FUSE, EW, NT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -532,17 +670,28 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int slots = tiles + p.n_ext;   // work units before any tail split
   int clusters = num_sms() / 2;
   if (a.max_ctas > 0 && a.max_ctas / 2 < clusters) clusters = a.max_ctas / 2 > 0 ? a.max_ctas / 2 : 1;
-  if (tiles < clusters) clusters = tiles;
+  if (slots < clusters) clusters = slots;
   if (g_tail_enabled < 0) {
     const char* e = getenv("B200RL_GEMM_TAIL_SPLIT");
     g_tail_enabled = (e && e[0] == '0') ? 0 : 1;
   }
   const int kb_total = p.kb1 + p.kb2;
-  const int S = (g_tail_enabled && FUSE == 0) ? pair_tail_split(tiles, clusters, kb_total) : 1;
+  // the K-ranges of a tail tile must be co-resident (range 0 waits for the others): with ext units in front, the last
+  // round holds (tiles + n_ext) mod clusters units
+  int S = (g_tail_enabled && FUSE == 0) ? pair_tail_split(slots, clusters, kb_total) : 1;
+  if (S > 1 && slots % clusters > tiles) S = 1;
+  TailWs* wx = nullptr;
+  if (ext) {
+    int rc2 = tail_workspace(stream, 0, &wx);
+    if (rc2) return rc2;
+    p.ext_flags = wx->ext_flags;
+    p.ext_epoch = ++wx->ext_epoch;
+  }
   if (S > 1) {
-    const int rem = tiles % clusters;
+    const int rem = slots % clusters;
     TailWs* w = nullptr;
     int rc2 = tail_workspace(stream, (size_t)rem * (S - 1) * 2 * NT * BM * BN * sizeof(float), &w);
     if (rc2) return rc2;
@@ -567,7 +716,7 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl_enabled ? 2 : 1;
-  B200RL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tA1, tB1, tA2, tB2, p));
+  B200RL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tA1, tB1, tA2, tB2, tExt, p));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -583,6 +732,17 @@ static int fuse_epilogue_warps() {
 }
 
 bool gemm_fuse_supported(int M, int I) { return gemm_pair_enabled() && M > BM && I % 128 == 0; }
+
+// LoRA-in-kernel: -1 = env B200RL_GEMM_EXT (default on), 0 / 1 forced by b200rl_gemm_set_ext (tests, A/B runs)
+static int g_ext = -1;
+bool gemm_ext_supported(int M, int N, int K2) {
+  if (g_ext < 0) {
+    const char* e = getenv("B200RL_GEMM_EXT");
+    g_ext = (e && e[0] == '0') ? 0 : 1;
+  }
+  // needs the CTA-pair kernel (same condition as gemm_dispatch) and a 64- or 128-wide intermediate
+  return g_ext != 0 && gemm_pair_enabled() && M > BM && N >= 256 && (K2 == 64 || K2 == 128);
+}
 
 // Wide (256 x 512) tiles: -1 = env B200RL_GEMM_WIDE (default on), 0 / 1 = forced by b200rl_gemm_set_wide (tests, A/B runs).
 static int g_wide = -1;
@@ -628,6 +788,11 @@ int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream) {
 // test / bisection switch: 1 = use CTA-pair kernels where applicable (default), 0 = single-CTA only
 extern "C" int b200rl_gemm_set_cta_pair(int enable) {
   b200rl::g_pair_enabled = enable ? 1 : 0;
+  return 0;
+}
+// test / A-B switch for the LoRA-in-kernel ext units (model driver): 1 = default, 0 = separate skinny GEMM + reduce
+extern "C" int b200rl_gemm_set_ext(int enable) {
+  b200rl::g_ext = enable ? 1 : 0;
   return 0;
 }
 // test / A-B switch for the wide (256 x 512) pair tiles: 1 = use them where applicable (default), 0 = 256 x 256 only

@@ -37,6 +37,17 @@ struct GemmParams {
   bf16* aux_out = nullptr;
   long long ld_aux = 0;
   int fuse_I = 0;
+  // CTA-pair kernel only: LoRA intermediate computed INSIDE the launch (GemmArgs::ext_B).  The first n_ext work units
+  // ("ext units", one per 256-row m-block) compute U[m rows, ext_n] = ext_alpha * A1[m rows] . Bext^T over the whole K1
+  // into ext_out and raise ext_flags (value = ext_epoch); every ordinary tile waits for the flags of its m-block right
+  // before it stages the K-extension segment (A2 == ext_out).
+  int n_ext = 0;
+  int ext_n = 0;               // 64 or 128 columns (= the group's K2)
+  bf16* ext_out = nullptr;
+  long long ld_ext = 0;
+  float ext_alpha = 1.f;
+  int* ext_flags = nullptr;    // [num_m_blocks][2 CTAs][4 warps]
+  int ext_epoch = 0;
 };
 
 // ---- descriptors ---------------------------------------------------------------------------
@@ -178,7 +189,15 @@ struct GemmArgs {
   int fuse = 0;
   void* aux = nullptr;
   long long ld_aux = 0;
+  // LoRA-in-kernel (CTA-pair kernel; the caller checks gemm_ext_supported()): the LoRA intermediate that the K-extension
+  // segment consumes is produced by the same launch.  ext_B = Acat [ext_n, K1] K-major (forward: U = s x.Acat^T) or
+  // Bcat [K1, ext_n] MN-major (dX form: dU = s dY.Bcat), following mn_major bit 1 like B1.  The result (bf16, scaled by
+  // ext_alpha) is written to A2 [M, K2 == ext_n] (lda2), which the K-extension then reads back through TMA.
+  const void* ext_B = nullptr;
+  long long ld_ext_b = 0;
+  float ext_alpha = 1.f;
 };
+bool gemm_ext_supported(int M, int N, int K2);
 bool gemm_fuse_supported(int M, int I);
 
 

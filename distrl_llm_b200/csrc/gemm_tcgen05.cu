@@ -271,6 +271,10 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
     B200RL_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15u) == 0, "gemm: bias must be 16-byte aligned");
   int bn = a.force_bn;
   const bool a_mn = (a.mn_major & 1) != 0, b_mn = (a.mn_major & 2) != 0;
+  if (a.ext_B)
+    B200RL_REQUIRE(!a_mn && a.splits <= 1 && a.A2 && a.B2 && gemm_ext_supported(a.M, a.N, a.K2) &&
+                       (a.force_bn == 0 || a.force_bn == 256 || a.force_bn == 512),
+                   "gemm(ext): the in-kernel LoRA intermediate needs the CTA-pair kernel (M > 128, N >= 256, K2 in {64, 128})");
   if (a_mn) {
     B200RL_REQUIRE(b_mn, "gemm: A MN-major with B K-major is not instantiated");
     B200RL_REQUIRE(a.M % 8 == 0, "gemm(dW form): M must be a multiple of 8");
@@ -296,6 +300,7 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
     if (pbn == 0 && gemm_pair_wide_enabled() && a.N >= 512 &&
         (long long)((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + 511) / 512) >= num_sms() / 2)
       pbn = 512;
+    if (pbn == 0 && a.ext_B) pbn = 256;   // ext units are instantiated for the 256-column (sub-)tiles only
     if (pbn == 0) {
       const int clusters = num_sms() / 2;
       const long long mb = (a.M + 2 * BM - 1) / (2 * BM);
@@ -377,6 +382,29 @@ extern "C" int b200rl_gemm(const void* A1, long long lda1, const void* B1, long 
   a.alpha = alpha; a.M = M; a.N = N;
   a.mn_major = mn_major; a.splits = splits; a.c_split_stride = c_split_stride;
   a.force_bn = force_bn; a.max_ctas = max_ctas;
+  return gemm_dispatch(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Base + LoRA projection with the LoRA intermediate produced by the same launch (CTA-pair kernel, "ext units"):
+//   U[M,K2] = ext_alpha * A1 . Bext^T   (bf16, written to `U`)     then     C = A1.B1^T + U.B2^T (+bias) (+residual)
+// mn_major 0: B1 [N,K1], Bext [K2,K1], B2 [N,K2] (forward y = x W^T + s (x A^T) B^T, distributed_actor.py:241-243 through
+// PEFT's LoRA formula); mn_major 2 (dX form): B1 [K1,N], Bext [K1,K2], B2 [K2,N] (dx = dy W + s (dy B) A).
+extern "C" int b200rl_gemm_lora(const void* A1, long long lda1, const void* B1, long long ldb1, int K1,
+                                const void* Bext, long long ld_ext, float ext_alpha, void* U, long long ldu,
+                                const void* B2, long long ldb2, int K2, void* C, long long ldc, const void* bias,
+                                const void* residual, long long ldr, int M, int N, int mn_major, int force_bn, void* stream) {
+  B200RL_REQUIRE(mn_major == 0 || mn_major == 2, "gemm_lora: mn_major must be 0 (forward) or 2 (dX form)");
+  B200RL_REQUIRE(Bext && U, "gemm_lora: null LoRA operand");
+  GemmArgs a;
+  a.A1 = A1; a.B1 = B1; a.A2 = U; a.B2 = B2;
+  a.lda1 = lda1; a.ldb1 = ldb1; a.lda2 = ldu; a.ldb2 = ldb2;
+  a.K1 = K1; a.K2 = K2;
+  a.C = C; a.ldc = ldc; a.c_fp32 = 0;
+  a.bias = bias; a.residual = residual; a.ldr = ldr;
+  a.alpha = 1.f; a.M = M; a.N = N;
+  a.mn_major = mn_major; a.splits = 1; a.c_split_stride = 0;
+  a.force_bn = force_bn; a.max_ctas = 0;
+  a.ext_B = Bext; a.ld_ext_b = ld_ext; a.ext_alpha = ext_alpha;
   return gemm_dispatch(a, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -561,7 +561,8 @@ namespace {
 int gemm_l(b200rl_model* m, int cat, int layout, cudaStream_t st, const bf16* A1, long long lda1, const bf16* B1, long long ldb1, int K1,
             const bf16* A2, long long lda2, const bf16* B2, long long ldb2, int K2, bf16* C,
             long long ldc, const bf16* bias, const bf16* residual, long long ldr, float alpha, int M,
-            int N, int fuse = 0, void* aux = nullptr, long long ld_aux = 0) {
+            int N, int fuse = 0, void* aux = nullptr, long long ld_aux = 0, const bf16* extB = nullptr,
+            long long ld_ext = 0, float ext_alpha = 1.f) {
   GemmArgs a;
   a.A1 = A1; a.B1 = B1; a.A2 = A2; a.B2 = B2;
   a.lda1 = lda1; a.ldb1 = ldb1; a.lda2 = lda2; a.ldb2 = ldb2;
@@ -570,7 +571,8 @@ int gemm_l(b200rl_model* m, int cat, int layout, cudaStream_t st, const bf16* A1
   a.M = M; a.N = N; a.mn_major = layout; a.splits = 1; a.c_split_stride = 0;
   a.force_bn = 0; a.max_ctas = 0;
   a.fuse = fuse; a.aux = aux; a.ld_aux = ld_aux;
-  PM(cat, 2.0 * M * N * K1 + (K2 ? 2.0 * M * N * m->cfg.lora_r : 0.0));
+  a.ext_B = extB; a.ld_ext_b = ld_ext; a.ext_alpha = ext_alpha;   // LoRA intermediate A2 produced inside this launch
+  PM(cat, 2.0 * M * N * K1 + (K2 ? 2.0 * M * N * m->cfg.lora_r : 0.0) + (extB ? 2.0 * M * K2 * (double)K1 : 0.0));
   if (cat == CAT_GEMM_SKINNY) {
     // rank-r LoRA intermediates (N = K2 <= 192): only ceil(M/128) output tiles, so split K across CTAs
     // into fp32 slabs (deterministic order) and reduce to bf16 in a second, tiny kernel
@@ -794,37 +796,41 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     bf16* xn = m->X + (long long)(l + 1) * Mt * H;
     PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(x, w.ln1_w, a.h1, a.rstd1, M, H, c.rms_eps, stream));
-    if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    // LoRA intermediates u = s x A^T: produced by the "ext units" of the big GEMM itself when the CTA-pair kernel runs it
+    // (gemm2_tcgen05.cu), else by a separate split-K skinny GEMM
+    const bool xq = lora && gemm_ext_supported(M, QKV, gq.K2), xo = lora && gemm_ext_supported(M, H, go.K2);
+    const bool xg = lora && gemm_ext_supported(M, 2 * I, gg.K2), xd = lora && gemm_ext_supported(M, H, gd.K2);
+    if (lora && !xq) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
     RC(base_weight(m, st, l, 0, &Wd));
     RC(gemm_l(m, CAT_GEMM, 0, st, a.h1, H, Wd, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, lora ? gq.K2 : 0, a.qkv, QKV,
-               (const bf16*)w.qkv_bias, nullptr, 0, 1.f, M, QKV));
+               (const bf16*)w.qkv_bias, nullptr, 0, 1.f, M, QKV, 0, nullptr, 0, xq ? ar + gq.acat : nullptr, H, s));
     PM(CAT_ROW, 2.0 * M * (c.n_q_heads + c.n_kv_heads) * c.head_dim * 2);
     if (pb) RC(b200rl_rope_pos(a.qkv, m->rope_cs, pb->pos, M, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 0, stream));
     else RC(b200rl_rope(a.qkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 0, stream));
     PM(CAT_ATTN_FWD, 2.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
     if (pb) RC(b200rl_attn_seg_fwd(a.qkv, attn_mask, a.attn_o, a.lse, M, c.n_q_heads, c.n_kv_heads, attn_scale, pb->qblocks, pb->n_qblocks, stream));
     else RC(b200rl_attn_fwd(a.qkv, attn_mask, a.attn_o, a.lse, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
-    if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    if (lora && !xo) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
     RC(base_weight(m, st, l, 1, &Wd));
     RC(gemm_l(m, CAT_GEMM, 0, st, a.attn_o, QD, Wd, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, lora ? go.K2 : 0, a.x_mid, H,
-               nullptr, x, H, 1.f, M, H));
+               nullptr, x, H, 1.f, M, H, 0, nullptr, 0, xo ? ar + go.acat : nullptr, QD, s));
     PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(a.x_mid, w.ln2_w, a.h2, a.rstd2, M, H, c.rms_eps, stream));
-    if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    if (lora && !xg) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
     RC(base_weight(m, st, l, 2, &Wd));
     if (fuse_swiglu) {  // gate|up GEMM whose epilogue also writes act = silu(gate)*up
       RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, Wd, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, lora ? gg.K2 : 0, a.gu, 2 * I,
-                 nullptr, nullptr, 0, 1.f, M, 2 * I, 1, a.act, I));
+                 nullptr, nullptr, 0, 1.f, M, 2 * I, 1, a.act, I, xg ? ar + gg.acat : nullptr, H, s));
     } else {
       RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, Wd, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, lora ? gg.K2 : 0, a.gu, 2 * I,
-                 nullptr, nullptr, 0, 1.f, M, 2 * I));
+                 nullptr, nullptr, 0, 1.f, M, 2 * I, 0, nullptr, 0, xg ? ar + gg.acat : nullptr, H, s));
       PM(CAT_ROW, 3.0 * M * I * 2);
       RC(b200rl_swiglu_fwd(a.gu, a.act, M, I, stream));
     }
-    if (lora) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    if (lora && !xd) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
     RC(base_weight(m, st, l, 3, &Wd));
     RC(gemm_l(m, CAT_GEMM, 0, st, a.act, I, Wd, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, lora ? gd.K2 : 0, xn, H, nullptr,
-               a.x_mid, H, 1.f, M, H));
+               a.x_mid, H, 1.f, M, H, 0, nullptr, 0, xd ? ar + gd.acat : nullptr, I, s));
   }
   // head: only the T scored positions (rows P-1 .. L-2) go through the final norm and lm_head
   bf16* xf = m->X + (long long)c.n_layers * Mt * H;
@@ -881,29 +887,36 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     bf16* du_o = m->du + 2 * Mt * m->K2max;
     bf16* du_q = m->du + 3 * Mt * m->K2max;
     // ---- down projection:  X[l+1] = x_mid + act.Wd^T + u_d.Bd^T
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + gd.bcat, gd.K2, H, nullptr, 0, nullptr, 0, 0, du_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
+    // du = s dY B: inside the dX GEMM (ext units) when it runs on the CTA-pair kernel and the grouped dW launch (which is
+    // the only other consumer of du) comes after it; else the separate skinny GEMM
+    const bool yd = grouped && gemm_ext_supported(M, I, gd.K2), yg = grouped && gemm_ext_supported(M, H, gg.K2);
+    const bool yo = grouped && gemm_ext_supported(M, QD, go.K2), yq = grouped && l > 0 && gemm_ext_supported(M, H, gq.K2);
+    if (!yd) RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + gd.bcat, gd.K2, H, nullptr, 0, nullptr, 0, 0, du_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
     if (!grouped) RC(lora_dw(m, st, gd, m->dx, H, a.u_d, a.act, I, du_d, M));
     RC(base_weight(m, st, l, 3, &Wd));
     if (fuse_swiglu) {  // dact never reaches HBM: the epilogue turns it into dgate|dup
       RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, du_d, gd.K2, ar + gd.acat, I, gd.K2, m->dgu, 2 * I, nullptr, nullptr, 0, 1.f, M, I,
-                 2, a.gu, 2 * I));
+                 2, a.gu, 2 * I, yd ? ar + gd.bcat : nullptr, gd.K2, s));
     } else {
-      RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, du_d, gd.K2, ar + gd.acat, I, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I));
+      RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, du_d, gd.K2, ar + gd.acat, I, gd.K2, m->dact, I, nullptr, nullptr, 0, 1.f, M, I,
+                 0, nullptr, 0, yd ? ar + gd.bcat : nullptr, gd.K2, s));
       PM(CAT_ROW, 5.0 * M * I * 2);
       RC(b200rl_swiglu_bwd(a.gu, m->dact, m->dgu, M, I, stream));
     }
     // ---- gate|up:  gu = h2.Wgu^T + u_gu.Bgu^T
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dgu, 2 * I, ar + gg.bcat, gg.K2, 2 * I, nullptr, 0, nullptr, 0, 0, du_g, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
+    if (!yg) RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dgu, 2 * I, ar + gg.bcat, gg.K2, 2 * I, nullptr, 0, nullptr, 0, 0, du_g, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
     if (!grouped) RC(lora_dw(m, st, gg, m->dgu, 2 * I, a.u_gu, a.h2, H, du_g, M));
     RC(base_weight(m, st, l, 2, &Wd));
-    RC(gemm_l(m, CAT_GEMM, 2, st, m->dgu, 2 * I, Wd, H, 2 * I, du_g, gg.K2, ar + gg.acat, H, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+    RC(gemm_l(m, CAT_GEMM, 2, st, m->dgu, 2 * I, Wd, H, 2 * I, du_g, gg.K2, ar + gg.acat, H, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H,
+               0, nullptr, 0, yg ? ar + gg.bcat : nullptr, gg.K2, s));
     PM(CAT_ROW, 4.0 * M * H * 2);
     RC(b200rl_rmsnorm_bwd(m->dh, a.x_mid, w.ln2_w, a.rstd2, m->dx, m->dx2, M, H, stream));
     // ---- o projection:  x_mid = x + attn_o.Wo^T + u_o.Bo^T
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx2, H, ar + go.bcat, go.K2, H, nullptr, 0, nullptr, 0, 0, du_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
+    if (!yo) RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx2, H, ar + go.bcat, go.K2, H, nullptr, 0, nullptr, 0, 0, du_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
     if (!grouped) RC(lora_dw(m, st, go, m->dx2, H, a.u_o, a.attn_o, QD, du_o, M));
     RC(base_weight(m, st, l, 1, &Wd));
-    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx2, H, Wd, QD, H, du_o, go.K2, ar + go.acat, QD, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD));
+    RC(gemm_l(m, CAT_GEMM, 2, st, m->dx2, H, Wd, QD, H, du_o, go.K2, ar + go.acat, QD, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD,
+               0, nullptr, 0, yo ? ar + go.bcat : nullptr, go.K2, s));
     // ---- attention + rope
     PM(CAT_ATTN_BWD, 4.0 * B * c.n_q_heads * (double)L * L * c.head_dim);
     if (pb) RC(b200rl_attn_seg_bwd(a.qkv, attn_mask, a.attn_o, m->dattn, a.lse, m->delta, m->dqkv, m->kvpart, M, c.n_q_heads, c.n_kv_heads, attn_scale,
@@ -913,8 +926,13 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     if (pb) RC(b200rl_rope_pos(m->dqkv, m->rope_cs, pb->pos, M, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 1, stream));
     else RC(b200rl_rope(m->dqkv, m->rope_cs, M, L, QKV, c.n_q_heads + c.n_kv_heads, c.head_dim, 1, stream));
     // ---- qkv projection:  qkv = h1.Wqkv^T + u_qkv.Bqkv^T + bias
-    RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dqkv, QKV, ar + gq.bcat, gq.K2, QKV, nullptr, 0, nullptr, 0, 0, du_q, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
+    if (!yq) RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dqkv, QKV, ar + gq.bcat, gq.K2, QKV, nullptr, 0, nullptr, 0, 0, du_q, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
     if (!grouped) RC(lora_dw(m, st, gq, m->dqkv, QKV, a.u_qkv, a.h1, H, du_q, M));
+    if (yq) {   // the qkv dX GEMM produces du_q: it has to run before the grouped dW launch that consumes it
+      RC(base_weight(m, st, l, 0, &Wd));
+      RC(gemm_l(m, CAT_GEMM, 2, st, m->dqkv, QKV, Wd, H, QKV, du_q, gq.K2, ar + gq.acat, H, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H,
+                 0, nullptr, 0, ar + gq.bcat, gq.K2, s));
+    }
     if (grouped) {
       // all eight dB / dA GEMMs of the layer in one launch, all their blocks accumulated by one more
       const Group* gs[4] = {&gd, &gg, &go, &gq};
@@ -927,8 +945,10 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
       RC(lora_dw_grouped(m, st, gs, dYs, ldYs, us, xs, ldXs, dus, M));
     }
     if (l > 0) {  // embeddings are frozen: layer 0 needs no input gradient
-      RC(base_weight(m, st, l, 0, &Wd));
-      RC(gemm_l(m, CAT_GEMM, 2, st, m->dqkv, QKV, Wd, H, QKV, du_q, gq.K2, ar + gq.acat, H, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+      if (!yq) {
+        RC(base_weight(m, st, l, 0, &Wd));
+        RC(gemm_l(m, CAT_GEMM, 2, st, m->dqkv, QKV, Wd, H, QKV, du_q, gq.K2, ar + gq.acat, H, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
+      }
       PM(CAT_ROW, 4.0 * M * H * 2);
       RC(b200rl_rmsnorm_bwd(m->dh, x, w.ln1_w, a.rstd1, m->dx2, m->dx, M, H, stream));
     }

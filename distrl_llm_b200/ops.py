@@ -36,6 +36,22 @@ def gemm(a1, b1, a2=None, b2=None, *, bias=None, residual=None, alpha=1.0, out=N
     return out
 
 
+def gemm_lora(a1, b1, bext, b2, *, scale=1.0, bias=None, residual=None, b_mn=False, force_bn=0):
+    """Base + LoRA projection in one launch: U = scale * a1 @ bext.T (bf16), C = a1 @ b1.T + U @ b2.T (+bias) (+residual).
+    b_mn=True: dX-form layouts (b1 [K1,N], bext [K1,K2], b2 [K2,N]).  Returns (C, U)."""
+    M, K1 = a1.shape
+    N = b1.shape[1] if b_mn else b1.shape[0]
+    K2 = bext.shape[1] if b_mn else bext.shape[0]
+    assert b2.shape == ((K2, N) if b_mn else (N, K2))
+    out = torch.empty(M, N, device=a1.device, dtype=BF16)
+    u = torch.empty(M, K2, device=a1.device, dtype=BF16)
+    check(lib().b200rl_gemm_lora(ptr(a1), a1.stride(0), ptr(b1), b1.stride(0), K1, ptr(bext), bext.stride(0), float(scale),
+                                 ptr(u), u.stride(0), ptr(b2), b2.stride(0), K2, ptr(out), out.stride(0), ptr(bias),
+                                 ptr(residual), residual.stride(0) if residual is not None else 0, M, N, 2 if b_mn else 0,
+                                 force_bn, stream()), "gemm_lora")
+    return out, u
+
+
 def gemm_dw(y, u, *, splits=1, force_bn=0):
     """dW form: returns fp32 slabs [splits, Ny, Nu] whose sum over dim 0 is y.T @ u.
     y: [tokens, Ny], u: [tokens, Nu] (bf16, row-major)."""

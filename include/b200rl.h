@@ -45,6 +45,16 @@ int b200rl_gemm_set_cta_pair(int enable);
 /* 1 (default) = the CTA-pair GEMM splits the tiles of its last, partially filled wave along K (gemm2_tcgen05.cu) */
 int b200rl_gemm_set_tail_split(int enable);
 int b200rl_gemm_set_wide(int enable); /* 1 (default): 256 x 512 CTA-pair tiles where every pair gets one; 0: 256 x 256 only */
+int b200rl_gemm_set_ext(int enable);  /* 1 (default): the model driver computes the LoRA intermediates inside the big GEMMs */
+/* Base + LoRA projection in ONE launch (north_star: "LoRA A/B resident in SMEM"): U[M,K2] = ext_alpha * A1.Bext^T is
+ * produced by the first work units of the launch ("ext units", one per 256-row block, its own TMEM accumulator) and
+ * consumed by the K-extension segment of every tile of that row block: C = A1.B1^T + U.B2^T (+bias) (+residual).
+ * mn_major 0 = forward operand layouts (B1 [N,K1], Bext [K2,K1], B2 [N,K2]); 2 = dX form ([K1,N], [K1,K2], [K2,N]).
+ * Needs M > 128, N >= 256, K2 in {64, 128}. */
+int b200rl_gemm_lora(const void* A1, long long lda1, const void* B1, long long ldb1, int K1, const void* Bext,
+                     long long ld_ext, float ext_alpha, void* U, long long ldu, const void* B2, long long ldb2, int K2,
+                     void* C, long long ldc, const void* bias, const void* residual, long long ldr, int M, int N,
+                     int mn_major, int force_bn, void* stream);
 /* G1 + G5 fused (CTA-pair kernel; needs M > 128 and I % 128 == 0, else B200RL_ERR_*):
  * mode 1: gu[M,2I] = A1.B1^T + A2.B2^T (gate rows then up rows of the weight, Qwen2MLP gate_proj|up_proj) and
  *         aux = act[M,I] = silu(gate)*up written by the same epilogue;

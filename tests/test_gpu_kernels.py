@@ -184,6 +184,34 @@ def test_gemm_wide_tile_is_bit_identical_to_256(cuda, b_mn):
     assert torch.equal(o256.view(torch.int16), o512.view(torch.int16))
 
 
+@pytest.mark.parametrize("bn", [256, 512], ids=["tile256", "wide512"])
+@pytest.mark.parametrize("M,N,K1,K2,b_mn", [(4446, 3584, 3584, 64, False), (8892, 4608, 3584, 64, False), (300, 512, 256, 64, False),
+                                            (4446, 3584, 4608, 64, True), (8892, 3584, 37888, 64, True), (1000, 768, 640, 128, False),
+                                            (1000, 768, 640, 128, True), (33000, 512, 256, 64, False)])
+def test_gemm_lora_in_kernel(cuda, M, N, K1, K2, b_mn, bn):
+    """LoRA intermediate produced inside the launch (ext units + flags, gemm2_tcgen05.cu) vs the two-GEMM formulation:
+    U = bf16(s * a1 @ Bext^T) must equal the separately computed skinny GEMM up to its fp32 summation order, and
+    C = a1 @ B1^T + U @ B2^T is then checked against torch using the U the kernel actually produced."""
+    from distrl_llm_b200 import ops
+    s_ = 0.5
+    a1 = _rand((M, K1), cuda, seed=1)
+    b1 = _rand((K1, N) if b_mn else (N, K1), cuda, seed=2)
+    bext = _rand((K1, K2) if b_mn else (K2, K1), cuda, seed=3, scale=0.1)
+    b2 = _rand((K2, N) if b_mn else (N, K2), cuda, seed=4)
+    res = _rand((M, N), cuda, seed=5)
+    for _ in range(3):      # repeated launches: the flag epoch advances
+        out, u = ops.gemm_lora(a1, b1, bext, b2, scale=s_, residual=res, b_mn=b_mn, force_bn=bn)
+    torch.cuda.synchronize()
+    u_ref = s_ * (a1.float() @ (bext.float() if b_mn else bext.float().T))
+    assert _rel_err(u, u_ref) < 4e-3
+    ref = a1.float() @ (b1.float() if b_mn else b1.float().T) + u.float() @ (b2.float() if b_mn else b2.float().T) + res.float()
+    assert _rel_err(out, ref) < 4e-3
+    assert torch.isfinite(out.float()).all()
+    # same numbers as the separate skinny GEMM + K-extension path (bf16 rounding of U may differ by one ulp at most)
+    u2 = ops.gemm(a1, bext, alpha=s_, b_mn=b_mn)
+    assert (u.float() - u2.float()).abs().max().item() <= 2.0 ** -7 * u_ref.abs().max().item()
+
+
 @pytest.mark.parametrize("tokens,splits", [(4446, 2), (700, 1), (1000, 4)])
 def test_gemm_dw_grouped(cuda, tokens, splits):
     """All dB / dA products of a layer in one persistent launch (gemm_dw_grouped.cu) vs torch fp32."""
