@@ -85,6 +85,9 @@ def create_actor_and_learner(number_of_actors=1, number_of_learners=1, model_nam
 
     learners = [local_rpc.ActorHandle(*learner_factory(i), own_stream=shared_dev) for i in range(number_of_learners)]
     if number_of_learners > 1:   # same-process peers: plain pointers + peer access instead of IPC handles
+        if shared_dev:           # learners sharing a device: every kernel must be loaded before a barrier can spin (warmup())
+            for l in learners:
+                local_rpc.get(l.warmup.remote())
         groups = local_rpc.get([l.p2p_local_group.remote() for l in learners])
         P2PGroup.wire_same_process(groups)
         local_rpc.get([l.p2p_attach_local.remote() for l in learners])

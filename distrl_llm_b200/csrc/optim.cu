@@ -212,6 +212,26 @@ static int p2p_status_init() {
   g_p2p_status_dev = (int*)d;
   return 0;
 }
+// With CUDA's lazy module loading the FIRST launch of a kernel loads its code, which synchronises with the device: if a
+// barrier kernel of this context is spinning at that moment (several learners in one process, or one stream per "rank" in
+// the single-device tests) the load waits for the barrier and the barrier waits for the kernel behind the load.  Force the
+// kernels of the exchange to be resident before the first barrier is ever launched.
+static int p2p_preload_kernels() {
+  static bool done[64] = {false};
+  int dev = 0;
+  B200RL_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && done[dev]) return 0;
+  cudaFuncAttributes fa;
+  B200RL_CUDA_OK(cudaFuncGetAttributes(&fa, p2p_barrier_kernel));
+  B200RL_CUDA_OK(cudaFuncGetAttributes(&fa, reduce_adam_kernel<0>));
+  B200RL_CUDA_OK(cudaFuncGetAttributes(&fa, reduce_adam_kernel<1>));
+  B200RL_CUDA_OK(cudaFuncGetAttributes(&fa, reduce_adam_kernel<2>));
+  B200RL_CUDA_OK(cudaFuncGetAttributes(&fa, reduce_adam_kernel<4>));
+  B200RL_CUDA_OK(cudaFuncGetAttributes(&fa, reduce_adam_kernel<8>));
+  B200RL_CUDA_OK(cudaFuncGetAttributes(&fa, lora_pack_kernel));
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return 0;
+}
 static double p2p_timeout_s() {
   static double t = -1.0;
   if (t < 0) {
@@ -286,6 +306,7 @@ extern "C" int b200rl_p2p_barrier_timeout(unsigned int* const* flags_peer, int w
   B200RL_REQUIRE(flags_peer && world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world,
                  "p2p_barrier: bad args");
   int rc = p2p_status_init();
+  if (!rc) rc = p2p_preload_kernels();
   if (rc) return rc;
   BarrierArgs a;
   for (int r = 0; r < MAX_PEERS; ++r) a.flags_peer[r] = r < world ? flags_peer[r] : nullptr;
@@ -314,6 +335,11 @@ extern "C" int b200rl_p2p_status(int reset) {
 // ---- CUDA IPC plumbing for the peer-mapped buffers (library-owned allocations) -------------------
 extern "C" int b200rl_p2p_alloc(long long bytes, void** ptr, void* handle64) {
   B200RL_REQUIRE(bytes > 0 && ptr && handle64, "p2p_alloc: bad args");
+  {
+    int rc = p2p_status_init();
+    if (!rc) rc = p2p_preload_kernels();
+    if (rc) return rc;
+  }
   B200RL_CUDA_OK(cudaMalloc(ptr, (size_t)bytes));
   B200RL_CUDA_OK(cudaMemset(*ptr, 0, (size_t)bytes));
   cudaIpcMemHandle_t h;

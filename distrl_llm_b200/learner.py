@@ -293,6 +293,23 @@ class BaseLearner:
     def vocab_size(self):
         return self.policy.cfg.vocab
 
+    def warmup(self):
+        """Run one throw-away micro-batch (forward, backward, optimizer kernels) and restore the state.  CUDA loads a
+        kernel's code at its first launch and that load synchronises with the device, so learners that SHARE a device (one
+        process, one stream each — tests) must have launched every kernel once before the first P2P barrier spins on it."""
+        pol = self.policy
+        flat, m, v, step = pol.lora_flat.clone(), pol.adam_m.clone(), pol.adam_v.clone(), pol.opt_step
+        B = min(self.update_batch_size, pol.max_batch)
+        msgs = [[1, 2, 3]] * B
+        answ = [[4, 5, 6, 7]] * B
+        self.compute_loss(msgs, answ, [1.0] * B)
+        pol.optimizer_step(self.lr)
+        pol.lora_flat.copy_(flat); pol.adam_m.copy_(m); pol.adam_v.copy_(v)
+        pol.opt_step = step
+        pol.lora_grad.zero_()
+        pol.sync_lora()
+        torch.cuda.synchronize(pol.device)
+
     def export_flat(self):
         """The flat fp32 adapter on the host (tests / debugging)."""
         torch.cuda.synchronize(self.policy.device)
