@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# a learner that never reaches a P2P barrier must fail a test in a minute, not after the production default of 600 s
+os.environ.setdefault("B200RL_P2P_TIMEOUT_S", "60")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
