@@ -246,6 +246,10 @@ def config_dict(args):
             "passes": f"{getattr(args, 'fuse_microbatches', 1)} reference micro-batches of {args.micro_batch} per model pass (gradient accumulation is linear: identical result)",
             "layout": "classic [B, P+T] rows" if getattr(args, "no_share_prompts", False) else
                       "packed shared-prompt rows (each group's prompt processed once; identical gradients)",
+            "weights": {"auto": "NF4 at the boundary; resident bf16 image of the dequantised base (15.2 GB) inside",
+                        "cache": "NF4 at the boundary; resident bf16 image of the dequantised base (15.2 GB) inside",
+                        "scratch": "NF4 dequantised into a scratch before each GEMM",
+                        "inkernel": "NF4 dequantised inside the GEMM mainloop (no bf16 copy of the base)"}[getattr(args, "weights", "auto")],
             "l2": "per-step activations and weights (>30 GB) far exceed the 126 MB L2; no flush needed"}
 
 
@@ -374,6 +378,8 @@ def main():
     ap.add_argument("--fuse_microbatches", type=int, default=2, help="reference micro-batches per model pass (identical gradients; 1 = one pass per micro-batch like the reference)")
     ap.add_argument("--ragged", action="store_true", help="cfg2 only: ragged synthetic lengths (prompt ~ U[P/2,P], completion ~ U[T/4,T]); value counts REAL completion tokens")
     ap.add_argument("--no_share_prompts", action="store_true", help="classic [B, P+T] layout (every prompt recomputed per completion)")
+    ap.add_argument("--weights", default="auto", choices=["auto", "cache", "scratch", "inkernel"],
+                    help="NF4 base: resident bf16 cache (auto/cache), dequant into a scratch before each GEMM, or inside the GEMM mainloop")
     ap.add_argument("--no_verify_exchange", action="store_true", help="N > 1: skip the post-run parameter identity / NCCL cross-check")
     args = ap.parse_args()
     preset = PRESETS[args.config]
@@ -435,6 +441,7 @@ def main():
         print(f"[bench] pass sizing skipped: {e}", file=sys.stderr)
     if world > 1:
         group, kw = P2PGroup.from_torch_distributed(cfg, FK * B, P, T, dev)
+    kw["cache_weights"] = {"auto": "auto", "cache": True, "scratch": False, "inkernel": "inkernel"}[args.weights]
     pol = Policy.random_init(cfg, dev, FK * B, P, T, seed=1234, **kw)   # same base + LoRA on every learner
     if group is not None:
         group.attach(pol)

@@ -53,6 +53,8 @@ SIGNATURES = {
     "b200rl_gemm_set_tail_split": (c_int, [c_int]),
     "b200rl_gemm_set_wide": (c_int, [c_int]),
     "b200rl_gemm_set_ext": (c_int, [c_int]),
+    "b200rl_gemm_nf4": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll,
+                                c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "b200rl_gemm_lora": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_float, c_void_p, c_ll, c_void_p, c_ll,
                                  c_int, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "b200rl_gemm_dw_grouped": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
@@ -105,6 +107,7 @@ SIGNATURES = {
     "b200rl_model_destroy": (c_int, [c_void_p]),
     "b200rl_model_weight_cache_bytes": (c_ll, [C.POINTER(ModelConfig)]),
     "b200rl_model_set_weight_cache": (c_int, [c_void_p, c_void_p, c_ll]),
+    "b200rl_model_set_nf4_inkernel": (c_int, [c_void_p, c_int]),
     "b200rl_model_set_fusion": (c_int, [c_void_p, c_int]),
     "b200rl_model_sync_lora": (c_int, [c_void_p, c_void_p]),
     "b200rl_model_debug_ptr": (c_void_p, [c_void_p, C.c_char_p, c_int]),

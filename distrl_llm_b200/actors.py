@@ -89,7 +89,7 @@ def create_actor_and_learner(number_of_actors=1, number_of_learners=1, model_nam
             for l in learners:
                 local_rpc.get(l.warmup.remote())
         groups = local_rpc.get([l.p2p_local_group.remote() for l in learners])
-        P2PGroup.wire_same_process(groups)
+        P2PGroup.wire_same_process(groups, threaded=True)
         local_rpc.get([l.p2p_attach_local.remote() for l in learners])
     desc = local_rpc.get(learners[0].adapter_publisher.remote())
     vocab = cfg.vocab if cfg is not None else local_rpc.get(learners[0].vocab_size.remote())

@@ -117,6 +117,43 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 // MACs): the 256 x 256 mainloop sits at the L2 -> SM fill limit, so the operand bytes, not the tensor
 // pipe, set its speed.  Price: both accumulators belong to the same tile, so a sub-tile's epilogue only overlaps the
 // next tile's mainloop from the moment ITS accumulator has been drained (tmem_empty per sub-tile).
+// NF4 level table (same values as csrc/nf4.cu; __constant__ symbols do not link across translation units)
+__constant__ float c_nf4_levels[16] = {-1.0f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f,
+                                       -0.28444138169288635f, -0.18477343022823334f, -0.09105003625154495f, 0.0f,
+                                       0.07958029955625534f, 0.16093020141124725f, 0.24611230194568634f,
+                                       0.33791524171829224f, 0.44070982933044434f, 0.5626170039176941f,
+                                       0.7229568362236023f, 1.0f};
+
+// 64 NF4 codes (32 bytes: q0, q1) of one 128-byte K-/MN-major shared-memory row -> bf16(level * absmax), written as the
+// eight 16-byte chunks of the row in the 128B-swizzle pattern TMA would have produced (chunk c at c ^ (row & 7)).
+// Bit-identical to nf4_dequant_kernel (csrc/nf4.cu): fp32 product, round-to-nearest bf16, even element in the high nibble.
+__device__ __forceinline__ void nf4_row_to_smem(uint32_t row_addr, int rsw, const uint4& q0, const uint4& q1, float am,
+                                                const float2* lut) {
+  const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float2 v = lut[(w[c] >> (8 * b)) & 0xFFu];
+      o[b] = pack_bf16x2(v.x * am, v.y * am);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((c ^ rsw) << 4)), "r"(o[0]), "r"(o[1]),
+                 "r"(o[2]), "r"(o[3])
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {  // release at cluster scope
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+
 template <int BN, bool B_MN, int NT = 1>
 struct PairCfg {
   static_assert(NT == 1 || BN == 256, "wide tiles are 2 x 256 columns");
@@ -133,8 +170,12 @@ struct PairCfg {
 
 // EW = epilogue warps per CTA (4 or 8): the fused SwiGLU epilogues use 8, two per TMEM lane quadrant, each pair
 // splitting the accumulator columns.
-template <int BN, bool B_MN, int FUSE, int EW, int NT>
-__global__ void __launch_bounds__(128 + 32 * EW, 1)
+// NF4 = true: segment 1 of the B operand comes from NF4 storage (p.nf4_q / p.nf4_am).  Four extra producer warps per CTA
+// (warps 4+EW ..) expand the 4-bit codes of every k-block into the stage's swizzled bf16 B tile(s) — the same bytes TMA
+// would have delivered from a dequantised copy — and arrive on the leader's full barrier next to the TMA transaction of
+// the A tile; the MMA issuer, the K-extension (LoRA) segment, the ext units and every epilogue are unchanged.
+template <int BN, bool B_MN, int FUSE, int EW, int NT, bool NF4>
+__global__ void __launch_bounds__(128 + 32 * EW + (NF4 ? 128 : 0), 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmExt, const GemmParams p) {
@@ -144,6 +185,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float2 s_lut[NF4 ? 256 : 1];   // byte -> (level[hi nibble], level[lo nibble])
+  if constexpr (NF4) {
+    if (threadIdx.x < 256) s_lut[threadIdx.x] = make_float2(c_nf4_levels[threadIdx.x >> 4], c_nf4_levels[threadIdx.x & 15]);
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -154,7 +199,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 2);
+      mbar_init(&full_bar[s], NF4 ? 2 + 8 : 2);   // + the four dequant warps of both CTAs
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -244,10 +289,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         const CUtensorMap* ta = seg2 ? &tmA2 : &tmA1;
         const CUtensorMap* tb = seg2 ? &tmB2 : &tmB1;
         const int k0 = (seg2 ? kb - p.kb1 : kb) * BK;
-        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+        const bool b_by_warps = NF4 && !seg2;   // the dequant warps fill the B tile(s) of this stage
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], b_by_warps ? 2 * A_TILE_BYTES : 2 * C::STAGE_BYTES);
         tma_load_2d_pair(sa, ta, &full_bar[stage], k0, row0);
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
+          if (b_by_warps) break;
           const int n_sub = n_blk * NT + t;
           // FUSE 1: CTA 0 stages 128 gate rows of the weight, CTA 1 the 128 up rows with the same index
           const int col0 = FUSE == 1 ? n_sub * C::BH + (int)rank * p.fuse_I : n_sub * BN + (int)rank * C::BH;
@@ -347,7 +394,114 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       for (int t = 0; t < NT; ++t) umma_commit_pair(&tmem_full_bar[acc0 + t]);
       ++local1;
     }
-  } else if (warp >= 4) {
+  } else if (NF4 && warp >= 4 + EW) {
+    // ===================== NF4 dequant producers (both CTAs, 4 warps = 128 threads) =====================
+    // K-major B (forward, W [N, K1]): thread dt owns row dt of each 128-row sub-tile: 64 codes = 32 packed bytes per
+    // k-block, one absmax.  MN-major B (dX form, W [K1, N]): thread dt owns k-row dt/2 and the 64-column half dt%2.
+    const int dt = (int)threadIdx.x - (128 + 32 * EW);
+    const long long kblocks_per_row = B_MN ? (p.N >> 6) : (p.K1 >> 6);   // absmax entries per matrix row
+    int stage = 0;
+    uint32_t phase = 0;
+    auto arrive_full = [&](int st) {
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&full_bar[st]);
+        else mbar_arrive_cluster(&full_bar[st], 0);
+      }
+    };
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      if (unit < n_ext) {   // ext units stage TMA operands only: arrive to keep the barrier count uniform
+        for (int kb = 0; kb < p.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          arrive_full(stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        continue;
+      }
+      int tile, kb_begin, kb_end, part, sidx, m_blk, n_blk;
+      unit_decode(p, unit - n_ext, kb_total, tile, kb_begin, kb_end, part, sidx);
+      tile_coords(tile, p.num_m_blocks, p.num_n_blocks, p.gm, m_blk, n_blk);
+      // global coordinates of this thread's codes inside sub-tile t (k-block independent part)
+      long long row_off[NT];      // element offset of the first code of k-block 0
+      long long am_off[NT];       // absmax index of k-block 0
+      bool in_range[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int n_sub = n_blk * NT + t;
+        const int col0 = FUSE == 1 ? n_sub * C::BH + (int)rank * p.fuse_I : n_sub * BN + (int)rank * C::BH;
+        if constexpr (!B_MN) {
+          const int n = col0 + dt;                       // matrix row (output feature)
+          in_range[t] = n < (FUSE == 1 ? 2 * p.fuse_I : p.N) && (FUSE != 1 || n_sub * 128 < p.fuse_I);
+          row_off[t] = (long long)n * p.K1;
+          am_off[t] = (long long)n * kblocks_per_row;
+        } else {
+          const int n = col0 + (dt & 1) * 64;            // first of this thread's 64 columns
+          in_range[t] = n < p.N;
+          row_off[t] = n;                                // + k * N per k-row
+          am_off[t] = n >> 6;
+        }
+      }
+      constexpr int PF = 4;                              // k-blocks of packed codes in flight per thread
+      uint4 q[PF][NT][2];
+      float am[PF][NT];
+      auto issue = [&](int slot, int kb) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const bool ok = in_range[t] && kb < kb_end && kb < p.kb1;
+          long long e, a;
+          if constexpr (!B_MN) {
+            e = row_off[t] + (long long)kb * BK;
+            a = am_off[t] + kb;
+          } else {
+            const long long k = (long long)kb * BK + (dt >> 1);
+            e = k * p.N + row_off[t];
+            a = k * kblocks_per_row + am_off[t];
+          }
+          if (ok) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.nf4_q + (e >> 1));
+            q[slot][t][0] = __ldg(src);
+            q[slot][t][1] = __ldg(src + 1);
+            am[slot][t] = __ldg(p.nf4_am + a);
+          } else {
+            q[slot][t][0] = make_uint4(0x77777777u, 0x77777777u, 0x77777777u, 0x77777777u);   // code 7 = level 0.0
+            q[slot][t][1] = q[slot][t][0];
+            am[slot][t] = 0.f;
+          }
+        }
+      };
+#pragma unroll
+      for (int i = 0; i < PF; ++i) issue(i, kb_begin + i);
+      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += PF) {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+          const int kb = kb0 + i;
+          if (kb < kb_end) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (kb < p.kb1) {
+              const uint32_t sb0 = smem_base + stage * C::STAGE_BYTES + A_TILE_BYTES;
+#pragma unroll
+              for (int t = 0; t < NT; ++t) {
+                uint32_t row_addr;
+                int rsw;
+                if constexpr (!B_MN) {
+                  row_addr = sb0 + t * C::B_TILE_BYTES + dt * 128;
+                  rsw = dt & 7;
+                } else {
+                  row_addr = sb0 + t * C::B_TILE_BYTES + (dt & 1) * 8192 + (dt >> 1) * 128;
+                  rsw = (dt >> 1) & 7;
+                }
+                nf4_row_to_smem(row_addr, rsw, q[i][t][0], q[i][t][1], am[i][t], s_lut);
+              }
+              fence_proxy_async_smem();   // generic-proxy smem writes -> the UMMA's async-proxy reads
+            }
+            arrive_full(stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            issue(i, kb + PF);            // refill this slot: codes of the k-block PF steps ahead
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + EW) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;  // 0, or 1 for the second warp of a quadrant (EW == 8)
@@ -610,7 +764,7 @@ static int tail_workspace(cudaStream_t stream, size_t bytes, TailWs** out) {
   return 0;
 }
 
-template <int BN, bool B_MN, int FUSE = 0, int EW = 4, int NT = 1>
+template <int BN, bool B_MN, int FUSE = 0, int EW = 4, int NT = 1, bool NF4 = false>
 static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   using C = PairCfg<BN, B_MN, NT>;
   GemmParams p;
@@ -640,7 +794,16 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap tA1, tB1, tA2, tB2, tExt;
   int rc;
   if ((rc = make_map(&tA1, a.A1, a.K1, a.M, a.lda1, BK, BM))) return rc;
-  if ((rc = B_MN ? make_map(&tB1, a.B1, a.N, a.K1, a.ldb1, 64, BK) : make_map(&tB1, a.B1, a.K1, a.N, a.ldb1, BK, C::BH))) return rc;
+  if constexpr (NF4) {
+    B200RL_REQUIRE(a.nf4_packed && a.nf4_absmax && a.K1 % 64 == 0 && a.N % 64 == 0,
+                   "gemm(nf4): needs packed codes + absmax, K1 %% 64 == 0 and N %% 64 == 0 (K1=%d N=%d)", a.K1, a.N);
+    p.nf4_q = reinterpret_cast<const uint8_t*>(a.nf4_packed);
+    p.nf4_am = a.nf4_absmax;
+    p.K1 = a.K1;
+    tB1 = tA1;   // unused: the dequant warps write the B tiles
+  } else {
+    if ((rc = B_MN ? make_map(&tB1, a.B1, a.N, a.K1, a.ldb1, 64, BK) : make_map(&tB1, a.B1, a.K1, a.N, a.ldb1, BK, C::BH))) return rc;
+  }
   if (a.K2 > 0) {
     if ((rc = make_map(&tA2, a.A2, a.K2, a.M, a.lda2, BK, BM))) return rc;
     if ((rc = B_MN ? make_map(&tB2, a.B2, a.N, a.K2, a.ldb2, 64, BK) : make_map(&tB2, a.B2, a.K2, a.N, a.ldb2, BK, C::BH))) return rc;
@@ -663,7 +826,7 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   } else {
     tExt = tB1;
   }
-  auto kern = gemm_pair_kernel<BN, B_MN, FUSE, EW, NT>;
+  auto kern = gemm_pair_kernel<BN, B_MN, FUSE, EW, NT, NF4>;
   static bool attr_set = false;
   if (!attr_set) {
     B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -704,7 +867,7 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(128 + 32 * EW);
+  cfg.blockDim = dim3(128 + 32 * EW + (NF4 ? 128 : 0));
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -744,12 +907,17 @@ bool gemm_ext_supported(int M, int N, int K2) {
   return g_ext != 0 && gemm_pair_enabled() && M > BM && N >= 256 && (K2 == 64 || K2 == 128);
 }
 
-// Wide (256 x 512) tiles: -1 = env B200RL_GEMM_WIDE (default on), 0 / 1 = forced by b200rl_gemm_set_wide (tests, A/B runs).
+// Wide (256 x 512) tiles: -1 = env B200RL_GEMM_WIDE, 0 / 1 = forced by b200rl_gemm_set_wide (tests, A/B runs).
+// DEFAULT OFF — measured on one B200 box (profiles/r2_run02_wide_ext_ab.txt): with the wide tiles the step ran at a
+// higher SM clock under the power cap (1620 vs 1522 MHz: fewer operand bytes per flop = less power) but took 1061 ms
+// instead of 1033 ms, because both TMEM accumulators belong to one tile and the epilogue of a tile no longer overlaps the
+// mainloop of the next (GEMM 873 ms vs 834 ms).  Kept as an option and under test; needs an epilogue that drains faster
+// than it does today before it can pay.
 static int g_wide = -1;
 bool gemm_pair_wide_enabled() {
   if (g_wide < 0) {
     const char* e = getenv("B200RL_GEMM_WIDE");
-    g_wide = (e && e[0] == '0') ? 0 : 1;
+    g_wide = (e && e[0] == '1') ? 1 : 0;
   }
   return g_wide != 0;
 }
@@ -761,8 +929,30 @@ static bool want_wide(const GemmArgs& a, int n_cols) {
   return n_cols >= 512 && wide_tiles >= num_sms() / 2;
 }
 
+// NF4 in the mainloop: same conditions as the CTA-pair kernel itself, 256-column (sub-)tiles only
+bool gemm_nf4_supported(int M, int N, int K1) {
+  return gemm_pair_enabled() && M > BM && N >= 256 && N % 64 == 0 && K1 % 64 == 0;
+}
+
+static int gemm_pair_dispatch_nf4(const GemmArgs& a, int bn, cudaStream_t stream) {
+  const bool b_mn = (a.mn_major & 2) != 0;
+  if (a.fuse == 1) {
+    B200RL_REQUIRE(!b_mn && !a.c_fp32 && !a.bias && !a.residual && a.aux && a.N % 256 == 0 && a.ld_aux % 8 == 0,
+                   "gemm(fused swiglu fwd): needs TN layout, bf16 C, N = 2I with I %% 128 == 0, no bias/residual");
+    return want_wide(a, a.N) ? launch_pair<256, false, 1, 8, 2, true>(a, stream) : launch_pair<256, false, 1, 8, 1, true>(a, stream);
+  }
+  if (a.fuse == 2) {
+    B200RL_REQUIRE(b_mn && !a.c_fp32 && !a.bias && !a.residual && a.aux && a.N % 8 == 0 && a.ld_aux % 8 == 0,
+                   "gemm(fused swiglu bwd): needs dX layout, bf16 C, no bias/residual");
+    return want_wide(a, a.N) ? launch_pair<256, true, 2, 8, 2, true>(a, stream) : launch_pair<256, true, 2, 8, 1, true>(a, stream);
+  }
+  if (bn == 512) return b_mn ? launch_pair<256, true, 0, 4, 2, true>(a, stream) : launch_pair<256, false, 0, 4, 2, true>(a, stream);
+  return b_mn ? launch_pair<256, true, 0, 4, 1, true>(a, stream) : launch_pair<256, false, 0, 4, 1, true>(a, stream);
+}
+
 int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream) {
   const bool b_mn = (a.mn_major & 2) != 0;
+  if (a.nf4_packed) return gemm_pair_dispatch_nf4(a, bn, stream);
   if (a.fuse == 1) {
     B200RL_REQUIRE(!b_mn && !a.c_fp32 && !a.bias && !a.residual && a.aux && a.N % 256 == 0 && a.ld_aux % 8 == 0,
                    "gemm(fused swiglu fwd): needs TN layout, bf16 C, N = 2I with I %% 128 == 0, no bias/residual");

@@ -48,6 +48,11 @@ struct GemmParams {
   float ext_alpha = 1.f;
   int* ext_flags = nullptr;    // [num_m_blocks][2 CTAs][4 warps]
   int ext_epoch = 0;
+  // CTA-pair kernel, NF4 instantiations: the segment-1 B operand is NF4 storage (GemmArgs::nf4_packed), expanded to bf16
+  // by four producer warps per CTA straight into the swizzled shared-memory stage the UMMA reads
+  const uint8_t* nf4_q = nullptr;   // packed codes, 2 per byte, row-major like the dense matrix
+  const float* nf4_am = nullptr;    // one fp32 absmax per 64 consecutive values
+  int K1 = 0;                       // segment-1 depth in elements (row length of a K-major B / row count of an MN-major B)
 };
 
 // ---- descriptors ---------------------------------------------------------------------------
@@ -196,7 +201,13 @@ struct GemmArgs {
   const void* ext_B = nullptr;
   long long ld_ext_b = 0;
   float ext_alpha = 1.f;
+  // NF4 base weight dequantised IN the mainloop (north_star: "4-bit base weights dequantised on the fly in-kernel";
+  // CTA-pair kernel, the caller checks gemm_nf4_supported()): B1 is given as NF4 storage instead of a bf16 matrix —
+  // packed codes [N, K1] (mn_major bit 1 clear) or [K1, N] (set), dense row-major, K1 % 64 == 0, N % 64 == 0.
+  const void* nf4_packed = nullptr;
+  const float* nf4_absmax = nullptr;
 };
+bool gemm_nf4_supported(int M, int N, int K1);
 bool gemm_ext_supported(int M, int N, int K2);
 bool gemm_fuse_supported(int M, int I);
 

@@ -258,7 +258,11 @@ static double g_pair_cost224 = 1.12, g_pair_cost192 = 1.35;
 int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
   B200RL_REQUIRE(a.M > 0 && a.N > 0 && a.K1 > 0 && a.K2 >= 0, "gemm: bad shape M=%d N=%d K1=%d K2=%d",
                  a.M, a.N, a.K1, a.K2);
-  B200RL_REQUIRE(a.A1 && a.B1 && a.C, "gemm: null operand");
+  B200RL_REQUIRE(a.A1 && (a.B1 || a.nf4_packed) && a.C, "gemm: null operand");
+  if (a.nf4_packed)
+    B200RL_REQUIRE(!(a.mn_major & 1) && a.splits <= 1 && gemm_nf4_supported(a.M, a.N, a.K1) &&
+                       (a.force_bn == 0 || a.force_bn == 256 || a.force_bn == 512),
+                   "gemm(nf4): in-kernel dequant needs the CTA-pair kernel (M > 128, N >= 256, N %% 64 == 0, K1 %% 64 == 0)");
   B200RL_REQUIRE(a.K2 == 0 || (a.A2 && a.B2), "gemm: K2 > 0 needs A2/B2");
   B200RL_REQUIRE(a.N % 8 == 0 && a.ldc % 8 == 0, "gemm: N and ldc must be multiples of 8 (N=%d ldc=%lld)",
                  a.N, a.ldc);
@@ -300,7 +304,7 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
     if (pbn == 0 && gemm_pair_wide_enabled() && a.N >= 512 &&
         (long long)((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + 511) / 512) >= num_sms() / 2)
       pbn = 512;
-    if (pbn == 0 && a.ext_B) pbn = 256;   // ext units are instantiated for the 256-column (sub-)tiles only
+    if (pbn == 0 && (a.ext_B || a.nf4_packed)) pbn = 256;   // ext units / NF4 producers: 256-column (sub-)tiles only
     if (pbn == 0) {
       const int clusters = num_sms() / 2;
       const long long mb = (a.M + 2 * BM - 1) / (2 * BM);
@@ -405,6 +409,26 @@ extern "C" int b200rl_gemm_lora(const void* A1, long long lda1, const void* B1, 
   a.mn_major = mn_major; a.splits = 1; a.c_split_stride = 0;
   a.force_bn = force_bn; a.max_ctas = 0;
   a.ext_B = Bext; a.ld_ext_b = ld_ext; a.ext_alpha = ext_alpha;
+  return gemm_dispatch(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// C = A1 . dequant(NF4)^T (+ A2.B2^T) (+bias) (+residual) with the 4-bit base weight expanded inside the GEMM mainloop
+// (reference: load_in_4bit weights, distributed_actor.py:16-17, :58-66).  mn_major 0: codes of W [N, K1]; 2: of W [K1, N].
+extern "C" int b200rl_gemm_nf4(const void* A1, long long lda1, const void* packed, const float* absmax, int K1,
+                               const void* A2, long long lda2, const void* B2, long long ldb2, int K2, void* C,
+                               long long ldc, const void* bias, const void* residual, long long ldr, int M, int N,
+                               int mn_major, int force_bn, void* stream) {
+  B200RL_REQUIRE(mn_major == 0 || mn_major == 2, "gemm_nf4: mn_major must be 0 or 2");
+  GemmArgs a;
+  a.A1 = A1; a.B1 = nullptr; a.A2 = A2; a.B2 = B2;
+  a.lda1 = lda1; a.ldb1 = 0; a.lda2 = lda2; a.ldb2 = ldb2;
+  a.K1 = K1; a.K2 = K2;
+  a.C = C; a.ldc = ldc; a.c_fp32 = 0;
+  a.bias = bias; a.residual = residual; a.ldr = ldr;
+  a.alpha = 1.f; a.M = M; a.N = N;
+  a.mn_major = mn_major; a.splits = 1; a.c_split_stride = 0;
+  a.force_bn = force_bn; a.max_ctas = 0;
+  a.nf4_packed = packed; a.nf4_absmax = absmax;
   return gemm_dispatch(a, reinterpret_cast<cudaStream_t>(stream));
 }
 

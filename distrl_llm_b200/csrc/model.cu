@@ -210,6 +210,11 @@ struct b200rl_model {
   bool fuse_swiglu = !(getenv("B200RL_FUSE_SWIGLU") && getenv("B200RL_FUSE_SWIGLU")[0] == '0');  // b200rl_model_set_fusion
   bf16* wcache = nullptr;
   long long wcache_per_layer = 0;
+  // without a cache: 0 = dequantise each matrix into the scratch right before its GEMM, 1 = hand the NF4 storage to the GEMM,
+  // whose producer warps dequantise it inside the mainloop (b200rl_model_set_nf4_inkernel; env B200RL_NF4_INKERNEL=1)
+  bool nf4_inkernel = getenv("B200RL_NF4_INKERNEL") && getenv("B200RL_NF4_INKERNEL")[0] == '1';
+  const void* next_q = nullptr;      // set by base_weight(), consumed by the next gemm_l()
+  const float* next_am = nullptr;
   std::vector<uint8_t> wcache_valid;  // [n_layers*4]
   // optional per-op CUDA-event profiling (bench.py roofline / DESIGN.md breakdown)
   bool prof_on = false;
@@ -572,6 +577,10 @@ int gemm_l(b200rl_model* m, int cat, int layout, cudaStream_t st, const bf16* A1
   a.force_bn = 0; a.max_ctas = 0;
   a.fuse = fuse; a.aux = aux; a.ld_aux = ld_aux;
   a.ext_B = extB; a.ld_ext_b = ld_ext; a.ext_alpha = ext_alpha;   // LoRA intermediate A2 produced inside this launch
+  if (m->next_q) {   // base_weight() chose the in-kernel dequant for this GEMM: B1 is NF4 storage
+    a.nf4_packed = m->next_q; a.nf4_absmax = m->next_am;
+    m->next_q = nullptr; m->next_am = nullptr;
+  }
   PM(cat, 2.0 * M * N * K1 + (K2 ? 2.0 * M * N * m->cfg.lora_r : 0.0) + (extB ? 2.0 * M * K2 * (double)K1 : 0.0));
   if (cat == CAT_GEMM_SKINNY) {
     // rank-r LoRA intermediates (N = K2 <= 192): only ceil(M/128) output tiles, so split K across CTAs
@@ -731,7 +740,7 @@ struct Layout {
 
 // Dequantised base weight of projection `which` (0 qkv, 1 o, 2 gate|up, 3 down) of layer l: from the resident cache
 // when one is attached (filled on first use), else NF4 -> bf16 into the shared scratch right before the GEMM.
-static int base_weight(b200rl_model* m, cudaStream_t st, int l, int which, const bf16** out) {
+static int base_weight(b200rl_model* m, cudaStream_t st, int l, int which, const bf16** out, int M = 0, int N = 0, int K1 = 0) {
   const b200rl_model_config& c = m->cfg;
   const b200rl_layer_weights& w = m->layers[l];
   const int H = c.hidden, I = c.inter, QKV = m->QKV, QD = m->QD;
@@ -739,6 +748,13 @@ static int base_weight(b200rl_model* m, cudaStream_t st, int l, int which, const
   const float* absmax[4] = {(const float*)w.qkv_absmax, (const float*)w.o_absmax, (const float*)w.gu_absmax, (const float*)w.down_absmax};
   const int rows[4] = {QKV, H, 2 * I, H}, cols[4] = {H, QD, H, I};
   bf16* dst = m->wbuf;
+  if (!m->wcache && m->nf4_inkernel && gemm_nf4_supported(M, N, K1)) {
+    // in-kernel dequant: the GEMM that follows (M x N output, reduction depth K1) reads the packed codes itself
+    m->next_q = packed[which];
+    m->next_am = absmax[which];
+    *out = nullptr;
+    return 0;
+  }
   if (m->wcache) {
     long long off = 0;
     for (int i = 0; i < which; ++i) off += (long long)rows[i] * cols[i];
@@ -801,7 +817,7 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     const bool xq = lora && gemm_ext_supported(M, QKV, gq.K2), xo = lora && gemm_ext_supported(M, H, go.K2);
     const bool xg = lora && gemm_ext_supported(M, 2 * I, gg.K2), xd = lora && gemm_ext_supported(M, H, gd.K2);
     if (lora && !xq) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h1, H, ar + gq.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_qkv, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
-    RC(base_weight(m, st, l, 0, &Wd));
+    RC(base_weight(m, st, l, 0, &Wd, M, QKV, H));
     RC(gemm_l(m, CAT_GEMM, 0, st, a.h1, H, Wd, H, H, a.u_qkv, gq.K2, ar + gq.bcat, gq.K2, lora ? gq.K2 : 0, a.qkv, QKV,
                (const bf16*)w.qkv_bias, nullptr, 0, 1.f, M, QKV, 0, nullptr, 0, xq ? ar + gq.acat : nullptr, H, s));
     PM(CAT_ROW, 2.0 * M * (c.n_q_heads + c.n_kv_heads) * c.head_dim * 2);
@@ -811,13 +827,13 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     if (pb) RC(b200rl_attn_seg_fwd(a.qkv, attn_mask, a.attn_o, a.lse, M, c.n_q_heads, c.n_kv_heads, attn_scale, pb->qblocks, pb->n_qblocks, stream));
     else RC(b200rl_attn_fwd(a.qkv, attn_mask, a.attn_o, a.lse, B, L, c.n_q_heads, c.n_kv_heads, c.head_dim, attn_scale, stream));
     if (lora && !xo) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.attn_o, QD, ar + go.acat, QD, QD, nullptr, 0, nullptr, 0, 0, a.u_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
-    RC(base_weight(m, st, l, 1, &Wd));
+    RC(base_weight(m, st, l, 1, &Wd, M, H, QD));
     RC(gemm_l(m, CAT_GEMM, 0, st, a.attn_o, QD, Wd, QD, QD, a.u_o, go.K2, ar + go.bcat, go.K2, lora ? go.K2 : 0, a.x_mid, H,
                nullptr, x, H, 1.f, M, H, 0, nullptr, 0, xo ? ar + go.acat : nullptr, QD, s));
     PM(CAT_ROW, 2.0 * M * H * 2);
     RC(b200rl_rmsnorm_fwd(a.x_mid, w.ln2_w, a.h2, a.rstd2, M, H, c.rms_eps, stream));
     if (lora && !xg) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.h2, H, ar + gg.acat, H, H, nullptr, 0, nullptr, 0, 0, a.u_gu, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
-    RC(base_weight(m, st, l, 2, &Wd));
+    RC(base_weight(m, st, l, 2, &Wd, M, 2 * I, H));
     if (fuse_swiglu) {  // gate|up GEMM whose epilogue also writes act = silu(gate)*up
       RC(gemm_l(m, CAT_GEMM, 0, st, a.h2, H, Wd, H, H, a.u_gu, gg.K2, ar + gg.bcat, gg.K2, lora ? gg.K2 : 0, a.gu, 2 * I,
                  nullptr, nullptr, 0, 1.f, M, 2 * I, 1, a.act, I, xg ? ar + gg.acat : nullptr, H, s));
@@ -828,7 +844,7 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
       RC(b200rl_swiglu_fwd(a.gu, a.act, M, I, stream));
     }
     if (lora && !xd) RC(gemm_l(m, CAT_GEMM_SKINNY, 0, st, a.act, I, ar + gd.acat, I, I, nullptr, 0, nullptr, 0, 0, a.u_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
-    RC(base_weight(m, st, l, 3, &Wd));
+    RC(base_weight(m, st, l, 3, &Wd, M, H, I));
     RC(gemm_l(m, CAT_GEMM, 0, st, a.act, I, Wd, I, I, a.u_d, gd.K2, ar + gd.bcat, gd.K2, lora ? gd.K2 : 0, xn, H, nullptr,
                a.x_mid, H, 1.f, M, H, 0, nullptr, 0, xd ? ar + gd.acat : nullptr, I, s));
   }
@@ -893,7 +909,7 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     const bool yo = grouped && gemm_ext_supported(M, QD, go.K2), yq = grouped && l > 0 && gemm_ext_supported(M, H, gq.K2);
     if (!yd) RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx, H, ar + gd.bcat, gd.K2, H, nullptr, 0, nullptr, 0, 0, du_d, gd.K2, nullptr, nullptr, 0, s, M, gd.K2));
     if (!grouped) RC(lora_dw(m, st, gd, m->dx, H, a.u_d, a.act, I, du_d, M));
-    RC(base_weight(m, st, l, 3, &Wd));
+    RC(base_weight(m, st, l, 3, &Wd, M, I, H));
     if (fuse_swiglu) {  // dact never reaches HBM: the epilogue turns it into dgate|dup
       RC(gemm_l(m, CAT_GEMM, 2, st, m->dx, H, Wd, I, H, du_d, gd.K2, ar + gd.acat, I, gd.K2, m->dgu, 2 * I, nullptr, nullptr, 0, 1.f, M, I,
                  2, a.gu, 2 * I, yd ? ar + gd.bcat : nullptr, gd.K2, s));
@@ -906,7 +922,7 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     // ---- gate|up:  gu = h2.Wgu^T + u_gu.Bgu^T
     if (!yg) RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dgu, 2 * I, ar + gg.bcat, gg.K2, 2 * I, nullptr, 0, nullptr, 0, 0, du_g, gg.K2, nullptr, nullptr, 0, s, M, gg.K2));
     if (!grouped) RC(lora_dw(m, st, gg, m->dgu, 2 * I, a.u_gu, a.h2, H, du_g, M));
-    RC(base_weight(m, st, l, 2, &Wd));
+    RC(base_weight(m, st, l, 2, &Wd, M, H, 2 * I));
     RC(gemm_l(m, CAT_GEMM, 2, st, m->dgu, 2 * I, Wd, H, 2 * I, du_g, gg.K2, ar + gg.acat, H, gg.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H,
                0, nullptr, 0, yg ? ar + gg.bcat : nullptr, gg.K2, s));
     PM(CAT_ROW, 4.0 * M * H * 2);
@@ -914,7 +930,7 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     // ---- o projection:  x_mid = x + attn_o.Wo^T + u_o.Bo^T
     if (!yo) RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dx2, H, ar + go.bcat, go.K2, H, nullptr, 0, nullptr, 0, 0, du_o, go.K2, nullptr, nullptr, 0, s, M, go.K2));
     if (!grouped) RC(lora_dw(m, st, go, m->dx2, H, a.u_o, a.attn_o, QD, du_o, M));
-    RC(base_weight(m, st, l, 1, &Wd));
+    RC(base_weight(m, st, l, 1, &Wd, M, QD, H));
     RC(gemm_l(m, CAT_GEMM, 2, st, m->dx2, H, Wd, QD, H, du_o, go.K2, ar + go.acat, QD, go.K2, m->dattn, QD, nullptr, nullptr, 0, 1.f, M, QD,
                0, nullptr, 0, yo ? ar + go.bcat : nullptr, go.K2, s));
     // ---- attention + rope
@@ -929,7 +945,7 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     if (!yq) RC(gemm_l(m, CAT_GEMM_SKINNY, 2, st, m->dqkv, QKV, ar + gq.bcat, gq.K2, QKV, nullptr, 0, nullptr, 0, 0, du_q, gq.K2, nullptr, nullptr, 0, s, M, gq.K2));
     if (!grouped) RC(lora_dw(m, st, gq, m->dqkv, QKV, a.u_qkv, a.h1, H, du_q, M));
     if (yq) {   // the qkv dX GEMM produces du_q: it has to run before the grouped dW launch that consumes it
-      RC(base_weight(m, st, l, 0, &Wd));
+      RC(base_weight(m, st, l, 0, &Wd, M, H, QKV));
       RC(gemm_l(m, CAT_GEMM, 2, st, m->dqkv, QKV, Wd, H, QKV, du_q, gq.K2, ar + gq.acat, H, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H,
                  0, nullptr, 0, ar + gq.bcat, gq.K2, s));
     }
@@ -946,7 +962,7 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
     }
     if (l > 0) {  // embeddings are frozen: layer 0 needs no input gradient
       if (!yq) {
-        RC(base_weight(m, st, l, 0, &Wd));
+        RC(base_weight(m, st, l, 0, &Wd, M, H, QKV));
         RC(gemm_l(m, CAT_GEMM, 2, st, m->dqkv, QKV, Wd, H, QKV, du_q, gq.K2, ar + gq.acat, H, gq.K2, m->dh, H, nullptr, nullptr, 0, 1.f, M, H));
       }
       PM(CAT_ROW, 4.0 * M * H * 2);
@@ -973,6 +989,14 @@ extern "C" int b200rl_model_set_weight_cache(b200rl_model* m, void* buf, long lo
   m->wcache = (bf16*)buf;
   m->wcache_per_layer = need / 2 / m->cfg.n_layers;
   m->wcache_valid.assign((size_t)m->cfg.n_layers * 4, 0);
+  return 0;
+}
+
+// Without a weight cache: 1 = the GEMMs dequantise the NF4 base inside their mainloop (north_star), 0 = each matrix is
+// dequantised into the shared scratch right before its GEMM.  Same bits either way (tests/test_gpu_learner.py).
+extern "C" int b200rl_model_set_nf4_inkernel(b200rl_model* m, int enable) {
+  B200RL_REQUIRE(m != nullptr, "model_set_nf4_inkernel: null model");
+  m->nf4_inkernel = enable != 0;
   return 0;
 }
 

@@ -52,6 +52,20 @@ def gemm_lora(a1, b1, bext, b2, *, scale=1.0, bias=None, residual=None, b_mn=Fal
     return out, u
 
 
+def gemm_nf4(a1, packed, absmax, N, a2=None, b2=None, *, bias=None, residual=None, b_mn=False, force_bn=0):
+    """C = a1 @ dequant(W).T (+ a2 @ b2.T): W given as NF4 storage (nf4_quantize of W [N, K1], or of W [K1, N] with
+    b_mn=True), expanded inside the GEMM mainloop."""
+    M, K1 = a1.shape
+    K2 = a2.shape[1] if a2 is not None else 0
+    out = torch.empty(M, N, device=a1.device, dtype=BF16)
+    check(lib().b200rl_gemm_nf4(ptr(a1), a1.stride(0), ptr(packed), ptr(absmax), K1, ptr(a2),
+                                a2.stride(0) if a2 is not None else 0, ptr(b2), b2.stride(0) if b2 is not None else 0, K2,
+                                ptr(out), out.stride(0), ptr(bias), ptr(residual),
+                                residual.stride(0) if residual is not None else 0, M, N, 2 if b_mn else 0, force_bn,
+                                stream()), "gemm_nf4")
+    return out
+
+
 def gemm_dw(y, u, *, splits=1, force_bn=0):
     """dW form: returns fp32 slabs [splits, Ny, Nu] whose sum over dim 0 is y.T @ u.
     y: [tokens, Ny], u: [tokens, Nu] (bf16, row-major)."""

@@ -44,6 +44,7 @@ class P2PGroup:
         self._opened = []
         self.numel = 0
         self.last_timing = None   # CUDA events of the last reduce_adam_step(timing=True)
+        self.step_rendezvous = None   # host-side rendezvous before each exchange (same-process learners, see wire_same_process)
 
     # ---- phase 1 ---------------------------------------------------------------------------------
     def alloc_local(self, numel):
@@ -79,9 +80,18 @@ class P2PGroup:
             self.peers[name] = ptrs
 
     @staticmethod
-    def wire_same_process(groups):
-        """Several 'learners' living in ONE process on one device (tests: fake multi-GPU on a single GPU, one stream per
-        rank): peer pointers are the other groups' local pointers, no IPC handle involved."""
+    def wire_same_process(groups, threaded=False):
+        """Several 'learners' living in ONE process (the thread-per-actor harness of actors.py; tests: fake multi-GPU on a
+        single GPU, one stream per rank): peer pointers are the other groups' local pointers, no IPC handle involved.
+        threaded=True (one host thread per learner): every exchange starts with a host-side rendezvous of the learner
+        threads.  Learners of one process share a CUDA context, and CUDA loads a kernel's code at its first launch, which
+        synchronises with the device: a learner still launching new kernels while a peer's flag barrier is already
+        spinning would dead-lock the two.  After the rendezvous every learner has ENQUEUED its whole step."""
+        if threaded:
+            import threading
+            bar = threading.Barrier(len(groups))
+            for g in groups:
+                g.step_rendezvous = bar.wait
         for g in groups:
             assert g.world == len(groups)
             for name in _NAMES:
@@ -130,6 +140,11 @@ class P2PGroup:
         check(lib().b200rl_p2p_barrier_timeout(C.cast(self._ptr_array("flags"), C.c_void_p), self.world, self.rank,
                                                self.epoch, float(timeout_s), stream()), "p2p_barrier")
 
+    @staticmethod
+    def reset_status():
+        """Clear the process-wide 'a barrier gave up' word without raising (tests)."""
+        lib().b200rl_p2p_status(1)
+
     def check(self, reset=False):
         """Raise if a barrier of this process timed out (call after a synchronisation; the loss .item() of a step is one)."""
         check(lib().b200rl_p2p_status(1 if reset else 0), "p2p_status")
@@ -138,6 +153,8 @@ class P2PGroup:
         """barrier -> fused P2P reduce + Adam(W) + write-back -> barrier -> zero_grad + bf16 operand refresh.
         timing=True records CUDA events around the three phases on this stream (read them with exchange_ms())."""
         policy.opt_step += 1
+        if self.step_rendezvous is not None:
+            self.step_rendezvous()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timing else None
         if ev:
             ev[0].record()

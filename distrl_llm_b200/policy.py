@@ -157,7 +157,7 @@ class Policy:
         self.embed = self.final_norm = self.lm_head = None
         self.handle = None
         self.workspace = None
-        self.cache_weights = cache_weights   # True / False / "auto": resident bf16 copy of the dequantised base
+        self.cache_weights = cache_weights   # True / False / "auto": resident bf16 copy of the dequantised base; "inkernel": no copy at all
         self.weight_cache = None
         self.loss_accum = torch.zeros(1, device=self.device, dtype=torch.float64)
         # offsets of every LoRA tensor in the flat buffer
@@ -197,6 +197,9 @@ class Policy:
         """Keep the dequantised base resident in HBM when it fits comfortably ("auto": cache <= 1/3 of the free
         memory).  The NF4 tensors stay the source of truth; the cache only removes the per-micro-batch dequant passes."""
         want = self.cache_weights
+        if want == "inkernel":   # no cache: the GEMMs expand the NF4 codes inside their mainloop (north_star)
+            check(lib().b200rl_model_set_nf4_inkernel(self.handle, 1), "model_set_nf4_inkernel")
+            return
         need = int(lib().b200rl_model_weight_cache_bytes(C.byref(self.ccfg)))
         if want == "auto":
             free, _ = torch.cuda.mem_get_info(self.device)

@@ -44,7 +44,14 @@ int b200rl_gemm(const void* A1, long long lda1, const void* B1, long long ldb1, 
 int b200rl_gemm_set_cta_pair(int enable);
 /* 1 (default) = the CTA-pair GEMM splits the tiles of its last, partially filled wave along K (gemm2_tcgen05.cu) */
 int b200rl_gemm_set_tail_split(int enable);
-int b200rl_gemm_set_wide(int enable); /* 1 (default): 256 x 512 CTA-pair tiles where every pair gets one; 0: 256 x 256 only */
+int b200rl_gemm_set_wide(int enable); /* 1: 256 x 512 CTA-pair tiles where every pair gets one; 0 (default, see gemm2_tcgen05.cu): 256 x 256 only */
+/* GEMM with the NF4 base weight dequantised INSIDE the mainloop (north_star; reference: load_in_4bit weights,
+ * distributed_actor.py:16-17, :58-66): four producer warps per CTA expand the packed codes of every k-block into the
+ * 128B-swizzled shared-memory tile the UMMA reads.  packed / absmax describe W [N, K1] (mn_major 0) or W [K1, N]
+ * (mn_major 2) in the layout of b200rl_nf4_quantize.  Bit-identical to b200rl_nf4_dequant + b200rl_gemm. */
+int b200rl_gemm_nf4(const void* A1, long long lda1, const void* packed, const float* absmax, int K1, const void* A2,
+                    long long lda2, const void* B2, long long ldb2, int K2, void* C, long long ldc, const void* bias,
+                    const void* residual, long long ldr, int M, int N, int mn_major, int force_bn, void* stream);
 int b200rl_gemm_set_ext(int enable);  /* 1 (default): the model driver computes the LoRA intermediates inside the big GEMMs */
 /* Base + LoRA projection in ONE launch (north_star: "LoRA A/B resident in SMEM"): U[M,K2] = ext_alpha * A1.Bext^T is
  * produced by the first work units of the launch ("ext units", one per 256-row block, its own TMEM accumulator) and
@@ -231,6 +238,9 @@ int b200rl_model_destroy(b200rl_model* m);
 long long b200rl_model_weight_cache_bytes(const b200rl_model_config* cfg);
 int b200rl_model_set_weight_cache(b200rl_model* m, void* buf, long long bytes);
 /* bit 0: fuse SwiGLU into the gate|up and down-dX GEMM epilogues (default 1; bit-identical results) */
+/* no weight cache attached: 1 = NF4 base weights are dequantised inside the GEMM mainloop (b200rl_gemm_nf4), 0 (default)
+ * = into a scratch right before each GEMM.  Measured trade-off: DESIGN.md section 5. */
+int b200rl_model_set_nf4_inkernel(b200rl_model* m, int enable);
 int b200rl_model_set_fusion(b200rl_model* m, int flags);
 /* refresh the bf16 operand copies of the LoRA tensors after an optimizer step */
 int b200rl_model_sync_lora(b200rl_model* m, void* stream);

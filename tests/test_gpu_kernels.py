@@ -164,7 +164,7 @@ def test_gemm_swiglu_fused_is_bit_identical(cuda, M, I, H, wide):
         assert torch.equal(dgu.view(torch.int16), dgu_ref.view(torch.int16))
     finally:
         lib.b200rl_gemm_set_tail_split(1)
-        lib.b200rl_gemm_set_wide(1)
+        lib.b200rl_gemm_set_wide(0)    # library default (gemm2_tcgen05.cu: measured slower in-step)
 
 
 @pytest.mark.parametrize("b_mn", [False, True], ids=["tn", "dx"])
@@ -213,6 +213,35 @@ def test_gemm_lora_in_kernel(cuda, M, N, K1, K2, b_mn, bn):
     # same numbers as the separate skinny GEMM + K-extension path (bf16 rounding of U may differ by one ulp at most)
     u2 = ops.gemm(a1, bext, alpha=s_, b_mn=b_mn)
     assert (u.float() - u2.float()).abs().max().item() <= 2.0 ** -7 * u_ref.abs().max().item()
+
+
+@pytest.mark.parametrize("bn", [256, 512], ids=["tile256", "wide512"])
+@pytest.mark.parametrize("M,N,K1,K2,b_mn", [(4446, 3584, 3584, 64, False), (8892, 4608, 3584, 0, False), (300, 512, 256, 64, False),
+                                            (4446, 3584, 4608, 64, True), (2100, 3584, 18944, 64, True), (700, 832, 320, 0, False),
+                                            (700, 832, 320, 64, True)])
+def test_gemm_nf4_in_mainloop_is_bit_identical(cuda, M, N, K1, K2, b_mn, bn):
+    """NF4 base weight expanded by the GEMM's own producer warps (b200rl_gemm_nf4) vs nf4_dequant + the bf16 GEMM: the
+    shared-memory tiles hold the same bf16 values and the K order is the same, so the outputs agree bit for bit
+    (tail split off: it re-orders K)."""
+    from distrl_llm_b200 import _capi, ops
+    w = _rand((K1, N) if b_mn else (N, K1), cuda, seed=2, scale=0.05)
+    packed, absmax = ops.nf4_quantize(w)
+    a1 = _rand((M, K1), cuda, seed=1)
+    a2 = _rand((M, K2), cuda, seed=3) if K2 else None
+    b2 = (_rand((K2, N) if b_mn else (N, K2), cuda, seed=4)) if K2 else None
+    res = _rand((M, N), cuda, seed=5)
+    dense = ops.nf4_dequant(packed, absmax, *w.shape)
+    try:
+        _capi.lib().b200rl_gemm_set_tail_split(0)
+        ref = ops.gemm(a1, dense, a2, b2, residual=res, force_bn=bn, b_mn=b_mn)
+        for _ in range(2):
+            out = ops.gemm_nf4(a1, packed, absmax, N, a2, b2, residual=res, b_mn=b_mn, force_bn=bn)
+        torch.cuda.synchronize()
+    finally:
+        _capi.lib().b200rl_gemm_set_tail_split(1)
+    assert _rel_err(ref, a1.float() @ (dense.float() if b_mn else dense.float().T)
+                    + (a2.float() @ (b2.float() if b_mn else b2.float().T) if K2 else 0) + res.float()) < 4e-3
+    assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
 
 
 @pytest.mark.parametrize("tokens,splits", [(4446, 2), (700, 1), (1000, 4)])

@@ -262,6 +262,32 @@ def test_weight_cache_is_bit_identical(cuda):
     assert torch.equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
 
 
+def test_nf4_in_mainloop_is_bit_identical(cuda):
+    """No weight cache: NF4 dequantised inside the GEMM mainloop (Policy(cache_weights="inkernel"), north_star) vs
+    dequantised into a scratch before each GEMM — same bf16 operand values, same K order -> identical gradients."""
+    from distrl_llm_b200 import _capi
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer
+    from distrl_llm_b200.policy import Policy
+    ocfg = lo.OracleConfig(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=64,
+                           lora_r=16, lora_alpha=16)
+    params, nf4 = lo.make_params(ocfg, seed=2)
+    P, T, B = 12, 36, 4          # 192 rows per micro-batch > 128: the CTA-pair kernels are used
+    prompts, answers, rewards = lo.make_batch(ocfg, 8, P, T, seed=4, ragged=True, group_size=4, learner="grpo")
+    out = []
+    try:
+        _capi.lib().b200rl_gemm_set_tail_split(0)      # the two paths may pick different tile widths; keep the K order equal
+        for mode in (False, "inkernel"):
+            pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, cuda, max_batch=B, P=P, T=T, cache_weights=mode)
+            assert pol.weight_cache is None
+            ln = GRPOLearner(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5})
+            ln._compute_gradients(prompts, answers, list(rewards), export=False)
+            out.append((pol.lora_grad.clone(), float(pol.loss_accum.item())))
+    finally:
+        _capi.lib().b200rl_gemm_set_tail_split(1)
+    assert out[0][0].abs().max() > 0
+    assert torch.equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+
+
 def test_swiglu_fusion_is_bit_identical(cuda):
     """b200rl_model_set_fusion: SwiGLU inside the GEMM epilogues vs separate row kernels -> identical gradients."""
     from distrl_llm_b200 import _capi
@@ -286,6 +312,7 @@ def test_swiglu_fusion_is_bit_identical(cuda):
 def test_grouped_dw_matches_per_group_path(cuda, monkeypatch):
     """One grouped dW launch per layer (default) vs eight separate dW GEMMs: same K-ranges are NOT guaranteed, so the
     comparison is numerical (fp32 slabs summed in a different split): rel-L2 < 1e-5 on the flat gradient."""
+    from distrl_llm_b200 import _capi
     from distrl_llm_b200.learner import GRPOLearner, IdTokenizer
     from distrl_llm_b200.policy import Policy
     ocfg = lo.OracleConfig(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=64,
@@ -294,15 +321,47 @@ def test_grouped_dw_matches_per_group_path(cuda, monkeypatch):
     P, T, B = 12, 36, 4
     prompts, answers, rewards = lo.make_batch(ocfg, 8, P, T, seed=4, ragged=True, group_size=4, learner="grpo")
     out = []
-    for env in ("1", "0"):
-        monkeypatch.setenv("B200RL_GROUPED_DW", env)   # read at model creation
-        pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, cuda, max_batch=B, P=P, T=T)
-        ln = GRPOLearner(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5})
-        ln._compute_gradients(prompts, answers, list(rewards), export=False)
-        out.append(pol.lora_grad.clone())
+    try:
+        _capi.lib().b200rl_gemm_set_ext(0)   # isolate the dW path: the in-kernel LoRA intermediates exist only next to it
+        for env in ("1", "0"):
+            monkeypatch.setenv("B200RL_GROUPED_DW", env)   # read at model creation
+            pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, cuda, max_batch=B, P=P, T=T)
+            ln = GRPOLearner(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5})
+            ln._compute_gradients(prompts, answers, list(rewards), export=False)
+            out.append(pol.lora_grad.clone())
+    finally:
+        _capi.lib().b200rl_gemm_set_ext(1)
     assert out[1].abs().max() > 0
     rel = ((out[0] - out[1]).norm() / out[1].norm()).item()
     assert rel < 1e-5, rel
+
+
+def test_inkernel_lora_intermediates_match_separate_gemms(cuda):
+    """LoRA intermediates u = s x A^T / du = s dY B produced by the ext units of the big GEMMs (default) vs the separate
+    split-K skinny GEMMs: the same products summed in a different fp32 order and rounded to bf16 once, so the gradients
+    agree to bf16 reassociation (measured 2.3e-4 rel-L2 on B200; bound 2e-3)."""
+    from distrl_llm_b200 import _capi
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer
+    from distrl_llm_b200.policy import Policy
+    ocfg = lo.OracleConfig(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=64,
+                           lora_r=16, lora_alpha=16)
+    params, nf4 = lo.make_params(ocfg, seed=2)
+    P, T, B = 12, 36, 4          # 192 rows per micro-batch > 128: the CTA-pair kernels (and with them the ext units) run
+    prompts, answers, rewards = lo.make_batch(ocfg, 8, P, T, seed=4, ragged=True, group_size=4, learner="grpo")
+    out = []
+    try:
+        for ext in (1, 0):
+            _capi.lib().b200rl_gemm_set_ext(ext)
+            pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, cuda, max_batch=B, P=P, T=T)
+            ln = GRPOLearner(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5})
+            ln._compute_gradients(prompts, answers, list(rewards), export=False)
+            out.append((pol.lora_grad.clone(), float(pol.loss_accum.item())))
+    finally:
+        _capi.lib().b200rl_gemm_set_ext(1)
+    assert out[0][0].abs().max() > 0 and not torch.equal(out[0][0], out[1][0])   # the two paths really differ
+    rel = ((out[0][0] - out[1][0]).norm() / out[1][0].norm()).item()
+    assert rel < 2e-3, rel
+    assert abs(out[0][1] - out[1][1]) < 1e-9
 
 
 def test_hf_state_dict_loader_vs_transformers(cuda):

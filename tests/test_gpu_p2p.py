@@ -53,7 +53,7 @@ def test_fake_world_reduce_adam_matches_mean_plus_adam(cuda, world):
     streams = [torch.cuda.Stream(device=cuda) for _ in range(world)]
     for pol in pols:            # first use of torch's fill kernel happens here, not while a barrier kernel is spinning
         pol.lora_grad.zero_()   # (CUDA loads a kernel's code at its first launch, which synchronises with the device)
-    groups[0].check(reset=True)
+    groups[0].reset_status()    # the status word is process-wide and sticky: start clean whatever ran before
     torch.cuda.synchronize()
     covered = torch.zeros(n, dtype=torch.int32)
     for r in range(world):
