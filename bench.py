@@ -380,6 +380,7 @@ def main():
     ap.add_argument("--no_share_prompts", action="store_true", help="classic [B, P+T] layout (every prompt recomputed per completion)")
     ap.add_argument("--weights", default="auto", choices=["auto", "cache", "scratch", "inkernel"],
                     help="NF4 base: resident bf16 cache (auto/cache), dequant into a scratch before each GEMM, or inside the GEMM mainloop")
+    ap.add_argument("--lean", action="store_true", help="long configs (cfg4): one e2e warm-up, no repeat of the device timing, one exchange-timing step")
     ap.add_argument("--no_verify_exchange", action="store_true", help="N > 1: skip the post-run parameter identity / NCCL cross-check")
     args = ap.parse_args()
     preset = PRESETS[args.config]
@@ -582,10 +583,12 @@ def main():
         torch.cuda.profiler.stop()
         return
     ms_dev, clocks, launches = timed(device_step, args.steps, sample_clocks=True)
-    for _ in range(2):
+    for _ in range(1 if args.lean else 2):
         e2e_step()
     ms_e2e, _, _ = timed(e2e_step, args.steps)
-    ms_dev2, _, _ = timed(device_step, args.steps)   # diagnostic: same region without the nvidia-smi sampler
+    ms_dev2 = None
+    if not args.lean:
+        ms_dev2, _, _ = timed(device_step, args.steps)   # diagnostic: same region without the nvidia-smi sampler
 
     # ---- N > 1: where the exchange time goes, and is the result right? ---------------------------------------------
     exchange = None
@@ -593,7 +596,7 @@ def main():
         barrier()
         timing_on[0] = True
         comp, waits, reds, refr = [], [], [], []
-        for _ in range(3):
+        for _ in range(1 if args.lean else 3):
             device_step()
             wait_ms, red_ms, refresh_ms = group.exchange_ms()
             comp.append(ev_pre[0].elapsed_time(ev_pre[1])); waits.append(wait_ms); reds.append(red_ms); refr.append(refresh_ms)

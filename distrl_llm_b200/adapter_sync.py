@@ -92,8 +92,7 @@ class AdapterSubscriber:
         """Copy the publisher's current adapter into self.flat; returns its version (0 = nothing published yet)."""
         for _ in range(max_tries):
             v1 = int(self._ver.item())
-            if v1 % 2 == 1:          # a publish is in flight
-                torch.cuda.synchronize(self.device)
+            if v1 % 2 == 1:          # a publish is in flight (the .item() above already waited on this stream): look again
                 continue
             if v1 == self.version:
                 return v1            # already have it

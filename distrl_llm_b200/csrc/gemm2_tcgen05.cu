@@ -913,21 +913,27 @@ bool gemm_ext_supported(int M, int N, int K2) {
 // instead of 1033 ms, because both TMEM accumulators belong to one tile and the epilogue of a tile no longer overlaps the
 // mainloop of the next (GEMM 873 ms vs 834 ms).  Kept as an option and under test; needs an epilogue that drains faster
 // than it does today before it can pay.
+// Modes: 0 = never, 1 = wherever every pair gets a wide tile, 2 = additionally only for K-long GEMMs (>= 256 k-blocks:
+// down forward, gate|up dX, lm_head dX), where the un-overlapped epilogue is < 3 % of a tile and the DRAM re-reads of the
+// 256 x 256 schedule are largest.
 static int g_wide = -1;
-bool gemm_pair_wide_enabled() {
+static int wide_mode() {
   if (g_wide < 0) {
     const char* e = getenv("B200RL_GEMM_WIDE");
-    g_wide = (e && e[0] == '1') ? 1 : 0;
+    g_wide = e ? atoi(e) : 0;
+    if (g_wide < 0 || g_wide > 2) g_wide = 0;
   }
-  return g_wide != 0;
+  return g_wide;
 }
-// Wide tiles pay when there is enough work to keep every CTA pair busy with them: at least one wide tile per pair.
-static bool want_wide(const GemmArgs& a, int n_cols) {
-  if (!gemm_pair_wide_enabled()) return false;
-  const long long mb = (a.M + 2 * BM - 1) / (2 * BM);
-  const long long wide_tiles = mb * ((n_cols + 511) / 512);
-  return n_cols >= 512 && wide_tiles >= num_sms() / 2;
+bool gemm_pair_wide_enabled() { return wide_mode() != 0; }
+bool gemm_pair_wide_for(int M, int n_cols, int k_total) {
+  const int mode = wide_mode();
+  if (mode == 0 || n_cols < 512) return false;
+  if (mode == 2 && (k_total + BK - 1) / BK < 256) return false;
+  const long long mb = (M + 2 * BM - 1) / (2 * BM);
+  return mb * ((n_cols + 511) / 512) >= num_sms() / 2;
 }
+static bool want_wide(const GemmArgs& a, int n_cols) { return gemm_pair_wide_for(a.M, n_cols, a.K1 + a.K2); }
 
 // NF4 in the mainloop: same conditions as the CTA-pair kernel itself, 256-column (sub-)tiles only
 bool gemm_nf4_supported(int M, int N, int K1) {
@@ -986,8 +992,8 @@ extern "C" int b200rl_gemm_set_ext(int enable) {
   return 0;
 }
 // test / A-B switch for the wide (256 x 512) pair tiles: 1 = use them where applicable (default), 0 = 256 x 256 only
-extern "C" int b200rl_gemm_set_wide(int enable) {
-  b200rl::g_wide = enable ? 1 : 0;
+extern "C" int b200rl_gemm_set_wide(int mode) {
+  b200rl::g_wide = (mode < 0 || mode > 2) ? 0 : mode;
   return 0;
 }
 // test / bisection switch for the K-split of the last partial wave (default on; env B200RL_GEMM_TAIL_SPLIT=0 disables)

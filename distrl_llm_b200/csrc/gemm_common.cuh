@@ -251,5 +251,6 @@ int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream);  // gemm
 void gemm_pair_set_tail_split(int enable);
 bool gemm_pair_enabled();
 bool gemm_pair_wide_enabled();   // 256 x 512 "wide" pair tiles (gemm2_tcgen05.cu, PairCfg NT = 2)
+bool gemm_pair_wide_for(int M, int n_cols, int k_total);
 
 }  // namespace b200rl

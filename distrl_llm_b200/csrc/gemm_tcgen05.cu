@@ -301,9 +301,7 @@ int gemm_dispatch(const GemmArgs& a, cudaStream_t stream) {
     // 74 CTA pairs: pick the width in {256, 224, 192} with the lowest waves x per-tile cost.
     int pbn = a.force_bn;
     // wide 256 x 512 tiles (25 % fewer operand bytes per flop) when every CTA pair gets at least one of them
-    if (pbn == 0 && gemm_pair_wide_enabled() && a.N >= 512 &&
-        (long long)((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + 511) / 512) >= num_sms() / 2)
-      pbn = 512;
+    if (pbn == 0 && gemm_pair_wide_for(a.M, a.N, a.K1 + a.K2)) pbn = 512;
     if (pbn == 0 && (a.ext_B || a.nf4_packed)) pbn = 256;   // ext units / NF4 producers: 256-column (sub-)tiles only
     if (pbn == 0) {
       const int clusters = num_sms() / 2;

@@ -308,11 +308,11 @@ class BaseLearner:
         pol.opt_step = step
         pol.lora_grad.zero_()
         pol.sync_lora()
-        torch.cuda.synchronize(pol.device)
+        torch.cuda.current_stream(pol.device).synchronize()
 
     def export_flat(self):
         """The flat fp32 adapter on the host (tests / debugging)."""
-        torch.cuda.synchronize(self.policy.device)
+        torch.cuda.current_stream(self.policy.device).synchronize()
         if self.p2p is not None:
             self.p2p.check()
         return self.policy.lora_flat.detach().cpu().clone()

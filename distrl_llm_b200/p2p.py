@@ -126,7 +126,9 @@ class P2PGroup:
             except Exception:  # pragma: no cover
                 host_rendezvous = None
         if host_rendezvous is not None:
-            torch.cuda.synchronize(self.device)
+            # this learner's stream only: a DEVICE-wide synchronize would also wait for a peer learner of the same process
+            # and device whose flag barrier is already spinning — and that barrier waits for the one launched below
+            torch.cuda.current_stream(self.device).synchronize()
             host_rendezvous()
         self.barrier()  # every learner finished initialising its parameters
 
