@@ -880,12 +880,11 @@ constexpr int SMEM_DQ = 2 * TILE_BYTES + 8 * HALF_TILE + 1024;
 constexpr int SMEM_DKV = 2 * TILE_BYTES + 10 * HALF_TILE + 1024;
 
 int set_attrs() {
-  static bool done = false;
-  if (done) return 0;
+  static DeviceOnce once;   // kernel attributes are per device
+  if (!once.first()) return 0;
   B200RL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
   B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
   B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
-  done = true;
   return 0;
 }
 

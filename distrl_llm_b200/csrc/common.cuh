@@ -47,6 +47,19 @@ int set_error(int code, const char* fmt, ...);
   } while (0)
 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+// Kernel attributes (max dynamic shared memory ...) belong to a (function, DEVICE) pair: a process that drives several
+// devices (one learner thread per GPU) has to set them once per device, not once per process.  Usage:
+//   static DeviceOnce once;  if (once.first()) cudaFuncSetAttribute(...);
+struct DeviceOnce {
+  bool done[64] = {false};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 extern long long g_launch_count;  // kernels launched by this library (bench.py's gpu_launches)
 extern int g_pdl_enabled;         // programmatic dependent launch on the hot-path kernels (b200rl_set_pdl / B200RL_PDL)
 

@@ -827,11 +827,9 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
     tExt = tB1;
   }
   auto kern = gemm_pair_kernel<BN, B_MN, FUSE, EW, NT, NF4>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;   // per template instantiation, per device
+  if (attr_once.first())
     B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int slots = tiles + p.n_ext;   // work units before any tail split
   int clusters = num_sms() / 2;

@@ -224,11 +224,9 @@ int dw_grouped_dispatch(int nprob, const void* const* Y, const long long* ldy, c
     maps.u[i] = maps.u[0];
   }
   for (int i = nprob; i <= DW_MAX; ++i) p.unit0[i] = unit;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;   // kernel attributes are per device
+  if (attr_once.first())
     B200RL_CUDA_OK(cudaFuncSetAttribute(dw_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
-    attr_set = true;
-  }
   int ctas = num_sms();
   if (unit < ctas) ctas = unit;
   B200RL_CUDA_OK(launch_pdl(dw_grouped_kernel, dim3(ctas), dim3(256), DW_SMEM_BYTES, stream, maps, p));

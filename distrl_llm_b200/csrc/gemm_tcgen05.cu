@@ -237,12 +237,9 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     tB2 = tB1;
   }
   auto kern = gemm_kernel<BN, A_MN, B_MN>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        C::SMEM_BYTES));
-    attr_set = true;
-  }
+  static DeviceOnce attr_once;  // per template instantiation, per device
+  if (attr_once.first())
+    B200RL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
   int ctas = num_sms();
   if (a.max_ctas > 0 && a.max_ctas < ctas) ctas = a.max_ctas;

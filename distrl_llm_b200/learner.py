@@ -349,10 +349,25 @@ class BaseLearner:
         sd = self.policy.lora_state_dict()
         torch.save(sd, os.path.join(path, "adapter_model.pt"))
         write_peft_adapter(path, sd, self.policy.cfg, base_model=self.model_name)
+        self.save_optimizer_state(path)
+
+    def save_optimizer_state(self, path):
+        """Adam moments + step counter.  Single learner: the whole state in optimizer_state.pt.  With the fused P2P exchange
+        every learner holds the moments of ITS 1/N slice only (csrc/optim.cu), so each learner writes its slice
+        (optimizer_state.rank{r}of{n}.pt; the Trainer calls this on every learner) and load_checkpoint merges what it finds."""
+        import os
+        os.makedirs(path, exist_ok=True)
         pol = self.policy
-        torch.save({"adam_m": pol.adam_m.detach().cpu(), "adam_v": pol.adam_v.detach().cpu(), "opt_step": int(pol.opt_step),
-                    "lr": self.lr, "weight_decay": self.weight_decay, "betas": (0.9, 0.999), "eps": 1e-8,
-                    "lora_numel": int(pol.lora_numel)}, os.path.join(path, "optimizer_state.pt"))
+        meta = {"opt_step": int(pol.opt_step), "lr": self.lr, "weight_decay": self.weight_decay, "betas": (0.9, 0.999),
+                "eps": 1e-8, "lora_numel": int(pol.lora_numel)}
+        if self.p2p is None:
+            torch.save(dict(meta, adam_m=pol.adam_m.detach().cpu(), adam_v=pol.adam_v.detach().cpu()),
+                       os.path.join(path, "optimizer_state.pt"))
+            return
+        from .p2p import owned_slice
+        lo, hi = owned_slice(self.p2p.numel, self.p2p.world, self.p2p.rank)
+        torch.save(dict(meta, lo=lo, hi=hi, adam_m=pol.adam_m[lo:hi].detach().cpu(), adam_v=pol.adam_v[lo:hi].detach().cpu()),
+                   os.path.join(path, f"optimizer_state.rank{self.p2p.rank}of{self.p2p.world}.pt"))
 
     def load_checkpoint(self, path):
         """Resume from a directory written by save_checkpoint (adapter + optimizer state) or by PEFT / the reference itself
@@ -370,18 +385,20 @@ class BaseLearner:
             raise ValueError(f"adapter target_modules {sorted(conf['target_modules'])} != {sorted(want)} (helper.py:29-37)")
         self.policy.load_lora_state(sd)
         pol = self.policy
+        import glob
+        pol.adam_m.zero_()
+        pol.adam_v.zero_()
+        pol.opt_step = 0
         opt = os.path.join(path, "optimizer_state.pt")
-        if os.path.exists(opt):
-            st = torch.load(opt, map_location="cpu")
+        slices = sorted(glob.glob(os.path.join(path, "optimizer_state.rank*of*.pt")))
+        for f in ([opt] if os.path.exists(opt) else slices):   # whole state, or the per-learner slices of a P2P run
+            st = torch.load(f, map_location="cpu")
             if int(st["lora_numel"]) != int(pol.lora_numel):
                 raise ValueError("optimizer state belongs to a different adapter layout")
-            pol.adam_m.copy_(st["adam_m"].to(pol.device))
-            pol.adam_v.copy_(st["adam_v"].to(pol.device))
+            lo, hi = int(st.get("lo", 0)), int(st.get("hi", pol.lora_numel))
+            pol.adam_m[lo:hi].copy_(st["adam_m"].to(pol.device))
+            pol.adam_v[lo:hi].copy_(st["adam_v"].to(pol.device))
             pol.opt_step = int(st["opt_step"])
-        else:
-            pol.adam_m.zero_()
-            pol.adam_v.zero_()
-            pol.opt_step = 0
         pol.lora_grad.zero_()
 
     def save_adapter(self):

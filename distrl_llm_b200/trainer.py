@@ -174,6 +174,13 @@ class Trainer:
     def save_adapter(self):
         _get(self.learners[0].save_adapter.remote())
 
+    def _save_checkpoint(self, path):
+        """reference :373-380 (learner 0 writes the adapter); with several learners the others add their slice of the Adam
+        moments (the fused exchange keeps them sharded)."""
+        _get(self.learners[0].save_checkpoint.remote(path))
+        if self.num_learners > 1:
+            _get([l.save_optimizer_state.remote(path) for l in self.learners[1:]])
+
     # ---- the loop (reference :232-382) ----------------------------------------------------------------------------------
     def train(self):
         step = samples = 0
@@ -205,14 +212,14 @@ class Trainer:
                 if self.eval_every > 0 and step % self.eval_every == 0:
                     self.evaluate(step)
                 if step % self.save_every == 0:
-                    _get(self.learners[0].save_checkpoint.remote(os.path.join(self.run_directory, f"model_{step}")))
+                    self._save_checkpoint(os.path.join(self.run_directory, f"model_{step}"))
                 if self.max_steps and step >= self.max_steps:
                     return step, time.time() - t_run
                 if not self.overlap and nxt is not None:
                     started = self._start_round(nxt)
                 batch = nxt
             if not self.max_steps:
-                _get(self.learners[0].save_checkpoint.remote(os.path.join(self.run_directory, f"model_{step}")))
+                self._save_checkpoint(os.path.join(self.run_directory, f"model_{step}"))
         return step, time.time() - t_run
 
     @staticmethod

@@ -101,6 +101,9 @@ class _FakeLearner:
     def save_checkpoint(self, path):
         self.log.append((self.name, "save_checkpoint", path))
 
+    def save_optimizer_state(self, path):
+        self.log.append((self.name, "save_optimizer_state", path))
+
 
 def _oracle_prep(candidates, learner_type, topk, device):
     """trainer_prep.apply_advantages_and_topk restated with the oracle (the product runs this block in the G9 CUDA kernel)."""
