@@ -552,10 +552,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       const int row = m_blk * BM2 + (int)rank * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       if (part == 0) {
-        // K-range 0 of a tail tile: wait for the same warp (rank, quad) of every other K-range of this tile
+        // K-range 0 of a tail tile: wait for the same warp (rank, quad[, half]) of every other K-range of this tile
         if (lane == 0) {
           for (int s = 1; s < p.tail_split; ++s) {
-            const int* f = p.tail_flags + (sidx * p.tail_split + s) * 8 + rank * 4 + quad;
+            const int* f = NT == 2 ? p.tail_flags + ((sidx * p.tail_split + s) * 8 + rank * 4 + quad) * 2 + half
+                                   : p.tail_flags + (sidx * p.tail_split + s) * 8 + rank * 4 + quad;
             long long t0 = clock64();
             while (ld_acquire_gpu(f) != p.tail_epoch) {
               if (clock64() - t0 > 40000000000LL) {
@@ -575,6 +576,117 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+      if constexpr (NT == 2) {
+        // ---- wide tiles: registers are the second accumulator buffer ----
+        // Both TMEM accumulators belong to this tile, so the next tile's MMAs can only start once they are drained.  Each
+        // of the 8 epilogue warps therefore pulls ITS 128 accumulator columns of this sub-tile into registers first
+        // (4 x tcgen05.ld 32x32b.x32), releases the accumulator (tmem_empty arrive: ~300 cycles after the commit instead of
+        // the ~2-3 k cycles of the conversion + global stores) and only then converts / stores from registers.
+        static_assert(EW == 8, "wide tiles use 8 epilogue warps: two per TMEM lane quadrant, 128 columns each");
+        uint32_t r[4][32];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // FUSE 1: gate columns [64 half, 64 half + 64) and the up columns with the same index (accumulator cols + 128)
+          const int col = FUSE == 1 ? (j < 2 ? half * 64 + j * 32 : 128 + half * 64 + (j - 2) * 32) : half * 128 + j * 32;
+          tmem_ld_32x32(taddr0 + col, r[j]);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+          else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+        }
+        if constexpr (FUSE == 1) {
+          if (n_sub * 128 < p.fuse_I && row_ok) {
+            bf16* gu_row = reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc;
+            bf16* act_row = p.aux_out + (long long)row * p.ld_aux;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = n_sub * 128 + half * 64 + j * 32 + g * 8;
+                float a[8], b[8], o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  a[i] = __uint_as_float(r[j][g * 8 + i]) * p.alpha;
+                  b[i] = __uint_as_float(r[j + 2][g * 8 + i]) * p.alpha;
+                }
+                const bf16x8 ga = pack8(a), ub = pack8(b);
+                *reinterpret_cast<bf16x8*>(gu_row + col) = ga;
+                *reinterpret_cast<bf16x8*>(gu_row + p.fuse_I + col) = ub;
+                unpack8(ga, a);  // the activation is computed from the bf16-rounded gate / up, like the row kernel
+                unpack8(ub, b);
+                swiglu_fwd8(a, b, o);
+                *reinterpret_cast<bf16x8*>(act_row + col) = pack8(o);
+              }
+            }
+          }
+        } else if constexpr (FUSE == 2) {
+          if (row_ok) {
+            const bf16* gu_row = p.aux_in + (long long)row * p.ld_aux;
+            bf16* dgu_row = reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = n_sub * BN + half * 128 + j * 32 + g * 8;
+                if (col < p.N) {
+                  float a[8], b[8], d[8], og[8], ou[8];
+                  unpack8(*reinterpret_cast<const bf16x8*>(gu_row + col), a);
+                  unpack8(*reinterpret_cast<const bf16x8*>(gu_row + p.fuse_I + col), b);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(r[j][g * 8 + i]) * p.alpha;
+                  unpack8(pack8(d), d);  // dact is a bf16 tensor in the unfused path
+                  swiglu_bwd8(a, b, d, og, ou);
+                  *reinterpret_cast<bf16x8*>(dgu_row + col) = pack8(og);
+                  *reinterpret_cast<bf16x8*>(dgu_row + p.fuse_I + col) = pack8(ou);
+                }
+              }
+            }
+          }
+        } else if (part > 0) {
+          // K-range 1..S-1 of a tail tile: raw fp32 accumulators -> workspace; flag after the last sub-tile
+          float* ws = p.tail_ws + (((long long)(sidx * (p.tail_split - 1) + (part - 1)) * 2 + rank) * NT + t) * (BM * BN);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = half * 4 + j;
+            float4* dst = reinterpret_cast<float4*>(ws + ((c * 4 + quad) * 32 + lane) * 32);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              dst[g] = make_float4(__uint_as_float(r[j][4 * g]), __uint_as_float(r[j][4 * g + 1]),
+                                   __uint_as_float(r[j][4 * g + 2]), __uint_as_float(r[j][4 * g + 3]));
+          }
+          if (t == NT - 1) {
+            __threadfence();
+            __syncwarp();
+            // 8 warps: the two warps of a quadrant share one flag slot pair -> one flag per (rank, quad, half)
+            if (lane == 0) st_release_gpu(p.tail_flags + ((sidx * p.tail_split + part) * 8 + rank * 4 + quad) * 2 + half, p.tail_epoch);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = half * 4 + j;
+            if (part == 0) {
+              for (int s2 = 1; s2 < p.tail_split; ++s2) {
+                const float4* src = reinterpret_cast<const float4*>(
+                    p.tail_ws + (((long long)(sidx * (p.tail_split - 1) + (s2 - 1)) * 2 + rank) * NT + t) * (BM * BN) +
+                    ((c * 4 + quad) * 32 + lane) * 32);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float4 v = __ldcg(src + g);
+                  r[j][4 * g] = __float_as_uint(__uint_as_float(r[j][4 * g]) + v.x);
+                  r[j][4 * g + 1] = __float_as_uint(__uint_as_float(r[j][4 * g + 1]) + v.y);
+                  r[j][4 * g + 2] = __float_as_uint(__uint_as_float(r[j][4 * g + 2]) + v.z);
+                  r[j][4 * g + 3] = __float_as_uint(__uint_as_float(r[j][4 * g + 3]) + v.w);
+                }
+              }
+            }
+            if (row_ok) epilogue_store32(p, r[j], row, n_sub * BN + c * 32, 0);
+          }
+        }
+        continue;
+      }
       if constexpr (FUSE == 1) {
         if (n_sub * 128 >= p.fuse_I) {   // second sub-tile of the last wide tile when I / 128 is odd: nothing to store
           tc_fence_before();
@@ -736,7 +848,7 @@ static constexpr int EXT_MAX_MBLOCKS = 4096;   // 1M rows per launch
 static std::mutex g_tail_mu;
 static std::map<std::pair<int, cudaStream_t>, TailWs> g_tail_ws;
 static int g_tail_enabled = -1;
-static constexpr int TAIL_MAX_FLAGS = 128 * 4 * 8;  // <= 128 tail tiles x 4 parts x 8 warps
+static constexpr int TAIL_MAX_FLAGS = 128 * 4 * 16;  // <= 128 tail tiles x 4 parts x 16 warps (8 per CTA with wide tiles)
 
 void gemm_pair_set_tail_split(int enable) { g_tail_enabled = enable ? 1 : 0; }
 
@@ -950,7 +1062,7 @@ static int gemm_pair_dispatch_nf4(const GemmArgs& a, int bn, cudaStream_t stream
                    "gemm(fused swiglu bwd): needs dX layout, bf16 C, no bias/residual");
     return want_wide(a, a.N) ? launch_pair<256, true, 2, 8, 2, true>(a, stream) : launch_pair<256, true, 2, 8, 1, true>(a, stream);
   }
-  if (bn == 512) return b_mn ? launch_pair<256, true, 0, 4, 2, true>(a, stream) : launch_pair<256, false, 0, 4, 2, true>(a, stream);
+  if (bn == 512) return b_mn ? launch_pair<256, true, 0, 8, 2, true>(a, stream) : launch_pair<256, false, 0, 8, 2, true>(a, stream);
   return b_mn ? launch_pair<256, true, 0, 4, 1, true>(a, stream) : launch_pair<256, false, 0, 4, 1, true>(a, stream);
 }
 
@@ -969,7 +1081,7 @@ int gemm_pair_dispatch(const GemmArgs& a, int bn, cudaStream_t stream) {
     if (want_wide(a, a.N)) return launch_pair<256, true, 2, 8, 2>(a, stream);
     return fuse_epilogue_warps() == 8 ? launch_pair<256, true, 2, 8>(a, stream) : launch_pair<256, true, 2, 4>(a, stream);
   }
-  if (bn == 512) return b_mn ? launch_pair<256, true, 0, 4, 2>(a, stream) : launch_pair<256, false, 0, 4, 2>(a, stream);
+  if (bn == 512) return b_mn ? launch_pair<256, true, 0, 8, 2>(a, stream) : launch_pair<256, false, 0, 8, 2>(a, stream);
   if (bn == 256) return b_mn ? launch_pair<256, true>(a, stream) : launch_pair<256, false>(a, stream);
   if (bn == 224) return b_mn ? launch_pair<224, true>(a, stream) : launch_pair<224, false>(a, stream);
   if (bn == 192) return b_mn ? launch_pair<192, true>(a, stream) : launch_pair<192, false>(a, stream);
