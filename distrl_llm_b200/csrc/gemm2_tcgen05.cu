@@ -1017,12 +1017,12 @@ bool gemm_ext_supported(int M, int N, int K2) {
   return g_ext != 0 && gemm_pair_enabled() && M > BM && N >= 256 && (K2 == 64 || K2 == 128);
 }
 
-// Wide (256 x 512) tiles: -1 = env B200RL_GEMM_WIDE, 0 / 1 = forced by b200rl_gemm_set_wide (tests, A/B runs).
-// DEFAULT OFF — measured on one B200 box (profiles/r2_run02_wide_ext_ab.txt): with the wide tiles the step ran at a
-// higher SM clock under the power cap (1620 vs 1522 MHz: fewer operand bytes per flop = less power) but took 1061 ms
-// instead of 1033 ms, because both TMEM accumulators belong to one tile and the epilogue of a tile no longer overlaps the
-// mainloop of the next (GEMM 873 ms vs 834 ms).  Kept as an option and under test; needs an epilogue that drains faster
-// than it does today before it can pay.
+// Wide (256 x 512) tiles: -1 = env B200RL_GEMM_WIDE (default 2), else forced by b200rl_gemm_set_wide (tests, A/B runs).
+// Measured on B200 (profiles/r2_run02_wide_ext_ab.txt, r2_run05_wide_modes_ab.txt), config 2, ms per learner step:
+//   first version (epilogue drains TMEM while the tensor pipe waits): mode 1 1061 vs mode 0 1033 — slower although the SM
+//   clock under the power cap rose from 1522 to 1620 MHz (fewer operand bytes per flop);
+//   with the early-release epilogue (accumulator -> registers, free TMEM, then convert / store):
+//   mode 0 1031 / 1039, mode 1 1029, mode 2 1016  -> default 2: wide tiles for the K-long GEMMs only.
 // Modes: 0 = never, 1 = wherever every pair gets a wide tile, 2 = additionally only for K-long GEMMs (>= 256 k-blocks:
 // down forward, gate|up dX, lm_head dX), where the un-overlapped epilogue is < 3 % of a tile and the DRAM re-reads of the
 // 256 x 256 schedule are largest.
@@ -1030,8 +1030,8 @@ static int g_wide = -1;
 static int wide_mode() {
   if (g_wide < 0) {
     const char* e = getenv("B200RL_GEMM_WIDE");
-    g_wide = e ? atoi(e) : 0;
-    if (g_wide < 0 || g_wide > 2) g_wide = 0;
+    g_wide = e ? atoi(e) : 2;
+    if (g_wide < 0 || g_wide > 2) g_wide = 2;
   }
   return g_wide;
 }

@@ -44,7 +44,7 @@ int b200rl_gemm(const void* A1, long long lda1, const void* B1, long long ldb1, 
 int b200rl_gemm_set_cta_pair(int enable);
 /* 1 (default) = the CTA-pair GEMM splits the tiles of its last, partially filled wave along K (gemm2_tcgen05.cu) */
 int b200rl_gemm_set_tail_split(int enable);
-int b200rl_gemm_set_wide(int mode); /* 256 x 512 CTA-pair tiles: 0 (default) never, 1 wherever every pair gets one, 2 only for K-long GEMMs (gemm2_tcgen05.cu) */
+int b200rl_gemm_set_wide(int mode); /* 256 x 512 CTA-pair tiles: 0 never, 1 wherever every pair gets one, 2 (default) only for K-long GEMMs (gemm2_tcgen05.cu) */
 /* GEMM with the NF4 base weight dequantised INSIDE the mainloop (north_star; reference: load_in_4bit weights,
  * distributed_actor.py:16-17, :58-66): four producer warps per CTA expand the packed codes of every k-block into the
  * 128B-swizzled shared-memory tile the UMMA reads.  packed / absmax describe W [N, K1] (mn_major 0) or W [K1, N]

@@ -164,7 +164,7 @@ def test_gemm_swiglu_fused_is_bit_identical(cuda, M, I, H, wide):
         assert torch.equal(dgu.view(torch.int16), dgu_ref.view(torch.int16))
     finally:
         lib.b200rl_gemm_set_tail_split(1)
-        lib.b200rl_gemm_set_wide(0)    # library default (gemm2_tcgen05.cu: measured slower in-step)
+        lib.b200rl_gemm_set_wide(2)    # library default (gemm2_tcgen05.cu: wide tiles for K-long GEMMs only)
 
 
 @pytest.mark.parametrize("b_mn", [False, True], ids=["tn", "dx"])
