@@ -84,7 +84,13 @@ struct AttnParams {
   int stat_h;            // lse/delta head stride
   int nq, nkv;
   float scale, scale_log2;
+  unsigned long long* prof;  // debug (b200rl_attn_set_prof): per-phase clock64 sums of the forward kernel, see PROF_*
 };
+// slots of AttnParams::prof (cycles summed over CTAs; [16] = key blocks, [17] = CTAs)
+enum { PROF_S_WAIT = 0, PROF_S_LD, PROF_MAX_XCHG, PROF_ABSORB_WAIT, PROF_ABSORB, PROF_EXP_STORE, PROF_FENCE_ARRIVE, PROF_LOOP,
+       PROF_PROLOGUE, PROF_EPILOGUE, PROF_M_KFULL, PROF_M_SEMPTY, PROF_M_PFULL, PROF_M_VFULL, PROF_M_OEMPTY, PROF_M_TOTAL,
+       PROF_BLOCKS, PROF_CTAS, PROF_N };
+#define PROF_T(var) const long long var = prof_on ? clock64() : 0
 
 // classic layout descriptors from the launch grid: grid = (ceil(L/128), heads, B), heavy blocks first
 __device__ __forceinline__ QBlock classic_qblock(const AttnParams& p) {
@@ -125,6 +131,9 @@ struct KeyIter {
   }
 };
 
+// PROF = true: debug instantiation with per-phase clock64 counters (scripts/prof_attn_phases.py); the production
+// instantiation carries none of it
+template <bool PROF>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -136,6 +145,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   __shared__ float s_l[2][BQ];           // [warpgroup][row] partial row sums (final combine)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr bool prof_on = PROF;
+  const long long t_start = prof_on ? clock64() : 0;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   // [Q 32K][K0 32K][V0 32K][K1 32K][V1 32K][P 32K]
@@ -207,11 +218,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     constexpr uint32_t idesc_qk = idesc_128x128(false);
     constexpr uint32_t idesc_pv = idesc_128x128(true);
     mbar_wait(&q_full, 0);
+    long long m_k = 0, m_s = 0, m_p = 0, m_v = 0, m_o = 0;
+    const long long m_t0 = prof_on ? clock64() : 0;
     auto issue_pv = [&](int j) {
       const int st = j & 1;
+      PROF_T(a0);
       mbar_wait(&p_full, j & 1);
+      PROF_T(a1);
       mbar_wait(&v_full[st], (j >> 1) & 1);
+      PROF_T(a2);
       mbar_wait(&o_empty[st], ((j >> 1) & 1) ^ 1u);
+      PROF_T(a3);
+      m_p += a1 - a0; m_v += a2 - a1; m_o += a3 - a2;
       tc_fence_after();
       const uint32_t v = sKV + TILE_BYTES * (2 * st + 1);
       const uint32_t tmem_o = tmem_base + 256 + st * 128;
@@ -228,8 +246,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     };
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
+      PROF_T(b0);
       mbar_wait(&k_full[st], (j >> 1) & 1);
+      PROF_T(b1);
       mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1u);
+      PROF_T(b2);
+      m_k += b1 - b0; m_s += b2 - b1;
       tc_fence_after();
       const uint32_t k = sKV + TILE_BYTES * (2 * st);
       const uint32_t tmem_s = tmem_base + st * 128;
@@ -244,6 +266,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       if (j > 0) issue_pv(j - 1);
     }
     issue_pv(n_kb - 1);
+    if (prof_on) {
+      atomicAdd(p.prof + PROF_M_KFULL, (unsigned long long)m_k);
+      atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
+      atomicAdd(p.prof + PROF_M_PFULL, (unsigned long long)m_p);
+      atomicAdd(p.prof + PROF_M_VFULL, (unsigned long long)m_v);
+      atomicAdd(p.prof + PROF_M_OEMPTY, (unsigned long long)m_o);
+      atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
+    }
   } else if (warp >= 4) {
     // ===================== softmax / output =====================
     // two warpgroups share every query row: warpgroup wg owns keys [64 wg, 64 wg + 64) of each block (one
@@ -257,10 +287,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 #pragma unroll
     for (int i = 0; i < 64; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+    long long c_sw = 0, c_ld = 0, c_mx = 0, c_aw = 0, c_ab = 0, c_ex = 0, c_fa = 0;
+    const long long t_loop0 = prof_on ? clock64() : 0;
 
     auto absorb = [&](int j, float corr) {  // O_reg = O_reg * corr + O_j   (own 64 columns)
       const int st = j & 1;
+      PROF_T(w0);
       mbar_wait(&o_full[st], (j >> 1) & 1);
+      PROF_T(w1);
+      c_aw += w1 - w0;
       tc_fence_after();
       uint32_t a0[32], a1[32];
       const uint32_t to = tmem_base + 256 + st * 128 + lane_addr + wg * 64;
@@ -274,12 +309,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       }
       tc_fence_before();
       mbar_arrive(&o_empty[st]);
+      if (prof_on) c_ab += clock64() - w1;
     };
 
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
       int row0, valid, local0;
       kit.get(d, j, row0, valid, local0);
+      PROF_T(e0);
       if (wg == 0) {  // validity bitmask of this block's 128 keys: inside the segment AND a real token
         const int mk = (r < valid) ? p.key_mask[row0 + r] : 0;
         const uint32_t bal = __ballot_sync(0xffffffffu, mk != 0);
@@ -290,7 +327,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       // causal clipping is needed only when an own key of the block can lie after the tile's first query
       const bool diag = local0 >= 0 && (local0 + BKV - 1 > d.q_local0);
       const bool plain = !diag && (w0 & w1) == 0xFFFFFFFFu;          // no masking at all (the common case)
+      PROF_T(e1);
       mbar_wait(&s_full[st], (j >> 1) & 1);
+      PROF_T(e2);
       tc_fence_after();
       const uint32_t ts = tmem_base + st * 128 + lane_addr + wg * 64;
       uint32_t v0[32], v1[32];
@@ -299,6 +338,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_empty[st]);  // scores are in registers: S[st] may be overwritten by QK_{j+2}
+      PROF_T(e3);
+      c_mx += e1 - e0; c_sw += e2 - e1; c_ld += e3 - e2;
       const int kbase = local0 + wg * 64;  // local index of this warpgroup's first key (own blocks)
       // ---- row max over the own 64 keys, then exchange with the other warpgroup ----
       float mx = -INFINITY;
@@ -326,7 +367,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       const float corr = ex2_approx(m_run - mu);
       // fold the previous block's P.V into the register accumulator (also guarantees the previous P.V has
       // finished reading the P tile before it is overwritten below)
+      PROF_T(e4);
+      c_mx += e4 - e3;
       if (j > 0) absorb(j - 1, corr_prev);
+      PROF_T(e5);
       // ---- p = exp2(s - m) -> bf16 into this warpgroup's 64-key atom of the P tile ----
       float rs = 0.f;
       const uint32_t prow = sP + wg * (TILE_BYTES / 2) + r * 128;
@@ -352,9 +396,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       l_run = l_run * corr + rs;
       m_run = m_new;
       corr_prev = corr;
+      PROF_T(e6);
       fence_proxy_async_smem();  // P tile visible to the tensor core (async proxy)
       mbar_arrive(&p_full);
+      if (prof_on) { c_ex += e6 - e5; c_fa += clock64() - e6; }
     }
+    const long long t_loop1 = prof_on ? clock64() : 0;
     // corr bookkeeping: O_reg before absorbing block j is relative to m_{j-1}; corr_j = exp2(m_{j-1} - m_j) was
     // computed when block j's scores were processed and O_j (from P_j) is relative to m_j.
     absorb(n_kb - 1, corr_prev);
@@ -372,6 +419,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) f[u] = o[i + u] * inv;
         *reinterpret_cast<bf16x8*>(dst + i) = pack8(f);
+      }
+    }
+    if (prof_on && (threadIdx.x == 128 || threadIdx.x == 256)) {   // one thread of each softmax warpgroup
+      atomicAdd(p.prof + PROF_S_WAIT, (unsigned long long)c_sw);
+      atomicAdd(p.prof + PROF_S_LD, (unsigned long long)c_ld);
+      atomicAdd(p.prof + PROF_MAX_XCHG, (unsigned long long)c_mx);
+      atomicAdd(p.prof + PROF_ABSORB_WAIT, (unsigned long long)c_aw);
+      atomicAdd(p.prof + PROF_ABSORB, (unsigned long long)c_ab);
+      atomicAdd(p.prof + PROF_EXP_STORE, (unsigned long long)c_ex);
+      atomicAdd(p.prof + PROF_FENCE_ARRIVE, (unsigned long long)c_fa);
+      atomicAdd(p.prof + PROF_LOOP, (unsigned long long)(t_loop1 - t_loop0));
+      atomicAdd(p.prof + PROF_PROLOGUE, (unsigned long long)(t_loop0 - t_start));
+      atomicAdd(p.prof + PROF_EPILOGUE, (unsigned long long)(clock64() - t_loop1));
+      if (threadIdx.x == 128) {
+        atomicAdd(p.prof + PROF_BLOCKS, (unsigned long long)n_kb);
+        atomicAdd(p.prof + PROF_CTAS, 1ull);
       }
     }
   }
@@ -882,11 +945,14 @@ constexpr int SMEM_DKV = 2 * TILE_BYTES + 10 * HALF_TILE + 1024;
 int set_attrs() {
   static DeviceOnce once;   // kernel attributes are per device
   if (!once.first()) return 0;
-  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
   B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
   B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
   return 0;
 }
+
+unsigned long long* g_attn_prof = nullptr;   // device buffer of PROF_N counters (debug; scripts/prof_attn_phases.py)
 
 AttnParams base_params(const int* key_mask, int nq, int nkv, float scale) {
   AttnParams p;
@@ -896,6 +962,7 @@ AttnParams base_params(const int* key_mask, int nq, int nkv, float scale) {
   p.nkv = nkv;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.prof = g_attn_prof;
   return p;
 }
 
@@ -927,7 +994,7 @@ int attn_fwd_tc_launch(const void* qkv, const int* key_mask, void* out, float* l
   p.L = L;
   p.stat_h = L;
   dim3 grid((L + BQ - 1) / BQ, nq, B);
-  B200RL_CUDA_OK(launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(384), SMEM_FWD, stream, tm, p));
+  B200RL_CUDA_OK(launch_pdl(p.prof ? attn_fwd_tc_kernel<true> : attn_fwd_tc_kernel<false>, dim3(grid), dim3(384), SMEM_FWD, stream, tm, p));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -969,7 +1036,7 @@ int attn_fwd_seg_launch(const void* qkv, const int* key_mask, void* out, float* 
   p.qblocks = qblocks_dev;
   p.stat_h = (int)rows;
   dim3 grid(n_qblocks, nq, 1);
-  B200RL_CUDA_OK(launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(384), SMEM_FWD, stream, tm, p));
+  B200RL_CUDA_OK(launch_pdl(p.prof ? attn_fwd_tc_kernel<true> : attn_fwd_tc_kernel<false>, dim3(grid), dim3(384), SMEM_FWD, stream, tm, p));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -1004,4 +1071,12 @@ int attn_bwd_seg_launch(const void* qkv, const int* key_mask, const void* dout, 
   return 0;
 }
 
+void g_attn_prof_set(unsigned long long* b) { g_attn_prof = b; }
+
 }  // namespace b200rl
+
+// debug: per-phase cycle counters of the tcgen05 attention forward kernel (18 x uint64 device buffer, or NULL = off)
+extern "C" int b200rl_attn_set_prof(void* buf_dev) {
+  b200rl::g_attn_prof_set(reinterpret_cast<unsigned long long*>(buf_dev));
+  return 0;
+}
