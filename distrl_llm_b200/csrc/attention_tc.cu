@@ -140,7 +140,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], o_full[2],
       o_empty[2], p_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t s_maskw[2][4];     // key-padding bitmask of the 128 keys of a block
   __shared__ float s_mx[2][2][BQ];       // [stage][warpgroup][row] partial row max
   __shared__ float s_l[2][BQ];           // [warpgroup][row] partial row sums (final combine)
 
@@ -312,18 +311,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       if (prof_on) c_ab += clock64() - w1;
     };
 
+    // validity of this warpgroup's 64 keys of a block (inside the segment AND a real token): every warp builds the two
+    // 32-bit words itself with two coalesced loads + ballots, and the loads for block j+1 are issued during block j — no
+    // shared-memory exchange, no named barrier, no global-load latency on the per-block critical path (the phase counters
+    // showed 2073 cycles per key block in "mask + max + exchange" before this, profiles/r2_run08_attn_fwd_phases_before.txt)
+    int mk0 = 0, mk1 = 0;
+    auto fetch_mask = [&](int j) {
+      int row0, valid, local0;
+      kit.get(d, j, row0, valid, local0);
+      const int k0 = wg * 64 + lane;
+      mk0 = (k0 < valid) ? p.key_mask[row0 + k0] : 0;
+      mk1 = (k0 + 32 < valid) ? p.key_mask[row0 + k0 + 32] : 0;
+    };
+    if (n_kb > 0) fetch_mask(0);
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
       int row0, valid, local0;
       kit.get(d, j, row0, valid, local0);
       PROF_T(e0);
-      if (wg == 0) {  // validity bitmask of this block's 128 keys: inside the segment AND a real token
-        const int mk = (r < valid) ? p.key_mask[row0 + r] : 0;
-        const uint32_t bal = __ballot_sync(0xffffffffu, mk != 0);
-        if (lane == 0) s_maskw[st][quad] = bal;
-      }
-      named_bar_sync(1, 256);
-      const uint32_t w0 = s_maskw[st][2 * wg], w1 = s_maskw[st][2 * wg + 1];
+      const uint32_t w0 = __ballot_sync(0xffffffffu, mk0 != 0), w1 = __ballot_sync(0xffffffffu, mk1 != 0);
+      if (j + 1 < n_kb) fetch_mask(j + 1);
       // causal clipping is needed only when an own key of the block can lie after the tile's first query
       const bool diag = local0 >= 0 && (local0 + BKV - 1 > d.q_local0);
       const bool plain = !diag && (w0 & w1) == 0xFFFFFFFFu;          // no masking at all (the common case)
@@ -467,7 +474,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t qdo_full, kv_full[3], kv_empty[3], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], dq_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t s_maskw[2][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -583,18 +589,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     const long long sidx = (long long)d.stat0 + (long long)h * p.stat_h + r;
     const float lse = q_ok ? p.lse2[sidx] : INFINITY;
     const float del = q_ok ? p.delta[sidx] : 0.f;
+    // validity word of this warpgroup's 32-key chunk: built by every warp itself (one coalesced load + ballot), the load
+    // for block j+1 issued during block j — no shared-memory exchange, no named barrier, no load latency per block
+    const int c = wg;
+    int mk = 0;
+    auto fetch_mask = [&](int j) {
+      int row0, valid, local0;
+      kit.get(d, j, row0, valid, local0);
+      const int k0 = c * 32 + lane;
+      mk = (k0 < valid) ? p.key_mask[row0 + k0] : 0;
+    };
+    if (n_kb > 0) fetch_mask(0);
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
       int row0, valid, local0;
       kit.get(d, j, row0, valid, local0);
-      if (t < 64) {  // warps 4 and 5: validity bitmask of the block's two 32-key chunks
-        const int mk = (t < valid) ? p.key_mask[row0 + t] : 0;
-        const uint32_t bal = __ballot_sync(0xffffffffu, mk != 0);
-        if (lane == 0) s_maskw[st][t >> 5] = bal;
-      }
-      named_bar_sync(1, 256);
-      const int c = wg;
-      const uint32_t mw = s_maskw[st][c];
+      const uint32_t mw = __ballot_sync(0xffffffffu, mk != 0);
+      if (j + 1 < n_kb) fetch_mask(j + 1);
       const int kc0 = local0 + c * 32;  // local index of the chunk's first key (own blocks)
       // causal clipping only when an own key of the chunk can lie after the tile's first query
       const bool diag = local0 >= 0 && (kc0 + 31 > d.q_local0);
@@ -801,16 +812,27 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     const bool row_ok = r < d.k_rows;
     const bool key_ok = row_ok && p.key_mask[d.k_row0 + (row_ok ? r : 0)] != 0;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    // softmax statistics of the 64 queries of an inner block: warps 4-5 load them one iteration AHEAD into registers and
+    // only publish them to shared memory here, so the global-load latency is off the per-iteration critical path
+    float lse_n = INFINITY, del_n = 0.f;
+    auto fetch_stats = [&](int it) {
+      if (t < 64) {
+        const int h = g * group + it / nqb;
+        const int qi = (qb0 + it % nqb) * 64 + t;
+        const long long sidx = (long long)d.stat0 + (long long)h * p.stat_h + qi;
+        lse_n = qi < d.q_len ? p.lse2[sidx] : INFINITY;   // +inf -> probability 0 for queries past the end
+        del_n = qi < d.q_len ? p.delta[sidx] : 0.f;
+      }
+    };
+    if (n_it > 0) fetch_stats(0);
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
-      const int h = g * group + it / nqb;
       const int qs = (qb0 + it % nqb) * 64;  // local index of the block's first query
       if (t < 64) {
-        const int qi = qs + t;
-        const long long sidx = (long long)d.stat0 + (long long)h * p.stat_h + qi;
-        s_lse[st][t] = qi < d.q_len ? p.lse2[sidx] : INFINITY;   // +inf -> probability 0 for queries past the end
-        s_del[st][t] = qi < d.q_len ? p.delta[sidx] : 0.f;
+        s_lse[st][t] = lse_n;
+        s_del[st][t] = del_n;
       }
+      if (it + 1 < n_it) fetch_stats(it + 1);
       named_bar_sync(1, 256);
       const int c = wg;
       const int qc0 = qs + c * 32;
