@@ -349,22 +349,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       c_mx += e1 - e0; c_sw += e2 - e1; c_ld += e3 - e2;
       const int kbase = local0 + wg * 64;  // local index of this warpgroup's first key (own blocks)
       // ---- row max over the own 64 keys, then exchange with the other warpgroup ----
+      // masked scores become -inf in place (UNSCALED: scale > 0 keeps -inf), so that the exp loop below is the same
+      // straight-line code for plain and masked blocks (a `plain ? a : b` inside it made the compiler issue both MUFUs
+      // under opposite predicates: 130 MUFU issue slots per warp and block instead of 64)
+      const float sl2 = p.scale_log2;
       float mx = -INFINITY;
-      if (plain) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-        mx *= p.scale_log2;  // scale > 0
-      } else {
+      if (!plain) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const bool ok0 = ((w0 >> i) & 1u) && (!diag || kbase + i <= ql);
           const bool ok1 = ((w1 >> i) & 1u) && (!diag || kbase + 32 + i <= ql);
-          const float a = ok0 ? __uint_as_float(v0[i]) * p.scale_log2 : -INFINITY;
-          const float c = ok1 ? __uint_as_float(v1[i]) * p.scale_log2 : -INFINITY;
-          v0[i] = __float_as_uint(a);  // keep the masked, scaled score
-          v1[i] = __float_as_uint(c);
-          mx = fmaxf(mx, fmaxf(a, c));
+          if (!ok0) v0[i] = 0xFF800000u;   // -inf
+          if (!ok1) v1[i] = 0xFF800000u;
         }
+      }
+      {
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+        mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;   // scale > 0; -inf stays -inf
       }
       s_mx[st][wg][r] = mx;
       named_bar_sync(2, 256);
@@ -379,7 +382,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       if (j > 0) absorb(j - 1, corr_prev);
       PROF_T(e5);
       // ---- p = exp2(s - m) -> bf16 into this warpgroup's 64-key atom of the P tile ----
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       const uint32_t prow = sP + wg * (TILE_BYTES / 2) + r * 128;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -387,9 +390,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float sv = __uint_as_float(half == 0 ? v0[i] : v1[i]);
-          const float pv = plain ? ex2_approx(sv * p.scale_log2 - mu) : ex2_approx(sv - mu);  // masked -> 2^-inf = 0
+          const float pv = ex2_approx(fmaf(sv, sl2, -mu));   // masked: -inf * scale - mu = -inf -> 2^-inf = 0
           pf[i] = pv;
-          rs += pv;
+          rs4[i & 3] += pv;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -400,7 +403,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
                        : "memory");
         }
       }
-      l_run = l_run * corr + rs;
+      l_run = l_run * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       m_run = m_new;
       corr_prev = corr;
       PROF_T(e6);
