@@ -71,7 +71,7 @@ SIGNATURES = {
     "b200rl_gather_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200rl_scatter_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200rl_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
-    "b200rl_attn_set_prof": (c_int, [c_void_p]),
+    "b200rl_attn_set_prof": (c_int, [c_void_p, c_int]),
     "b200rl_attn_set_tc": (c_int, [c_int]),
     "b200rl_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),

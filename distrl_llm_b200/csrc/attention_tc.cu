@@ -471,9 +471,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 // ---------------------------------------------------------------------------------------------------
 // dQ
 // ---------------------------------------------------------------------------------------------------
+template <bool PROF>
 __global__ void __launch_bounds__(384, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_do128,
                       const __grid_constant__ CUtensorMap tm_kv64, const AttnParams p) {
+  constexpr bool prof_on = PROF;
+  const long long t_start = prof_on ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t qdo_full, kv_full[3], kv_empty[3], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], dq_full;
   __shared__ uint32_t tmem_base_smem;
@@ -540,9 +543,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     constexpr uint32_t id_s = idesc_n(64, false);    // [128 q] x [64 keys], both K-major over d
     constexpr uint32_t id_dq = idesc_n(128, true);   // [128 q] x [128 d], B = K_j MN-major (k = keys)
     mbar_wait(&qdo_full, 0);
+    long long m_k = 0, m_s = 0, m_d = 0;
+    const long long m_t0 = prof_on ? clock64() : 0;
     auto issue_dq = [&](int j) {
       const int st = j & 1, k3 = j % 3;
+      PROF_T(a0);
       mbar_wait(&ds_full[st], (j >> 1) & 1);
+      if (prof_on) m_d += clock64() - a0;
       tc_fence_after();
       const uint32_t kt = sKV + k3 * 2 * HALF_TILE;
       const uint32_t ds = sDS + st * HALF_TILE;
@@ -557,8 +564,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     };
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1, k3 = j % 3;
+      PROF_T(b0);
       mbar_wait(&kv_full[k3], (j / 3) & 1);
+      PROF_T(b1);
       mbar_wait(&sp_empty[st], ((j >> 1) & 1) ^ 1u);
+      if (prof_on) { m_k += b1 - b0; m_s += clock64() - b1; }
       tc_fence_after();
       const uint32_t kt = sKV + k3 * 2 * HALF_TILE, vt = kt + HALF_TILE;
 #pragma unroll
@@ -580,6 +590,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     }
     issue_dq(n_kb - 1);
     umma_commit(&dq_full);
+    if (prof_on) {
+      atomicAdd(p.prof + PROF_M_KFULL, (unsigned long long)m_k);
+      atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
+      atomicAdd(p.prof + PROF_M_PFULL, (unsigned long long)m_d);
+      atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
+    }
   } else if (warp >= 4) {
     // ===================== dS producer: two warpgroups, each 32 of the 64 keys of a block =====================
     const int wg = (warp - 4) >> 2;
@@ -603,18 +619,24 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
       mk = (k0 < valid) ? p.key_mask[row0 + k0] : 0;
     };
     if (n_kb > 0) fetch_mask(0);
+    long long c_sw = 0, c_dw = 0, c_ld = 0, c_ma = 0, c_fa = 0, c_mk = 0;
+    const long long t_loop0 = prof_on ? clock64() : 0;
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
       int row0, valid, local0;
       kit.get(d, j, row0, valid, local0);
+      PROF_T(e0);
       const uint32_t mw = __ballot_sync(0xffffffffu, mk != 0);
       if (j + 1 < n_kb) fetch_mask(j + 1);
       const int kc0 = local0 + c * 32;  // local index of the chunk's first key (own blocks)
       // causal clipping only when an own key of the chunk can lie after the tile's first query
       const bool diag = local0 >= 0 && (kc0 + 31 > d.q_local0);
       const bool plain = !diag && mw == 0xFFFFFFFFu;
+      PROF_T(e1);
       mbar_wait(&sp_full[st], (j >> 1) & 1);
+      PROF_T(e2);
       mbar_wait(&ds_empty[st], ((j >> 1) & 1) ^ 1u);  // dQ MMA of block j-2 finished reading dS[st]
+      PROF_T(e3);
       tc_fence_after();
       {
         uint32_t sv[32], dv[32];
@@ -623,6 +645,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&sp_empty[st]);
+        PROF_T(e4);
+        c_mk += e1 - e0; c_sw += e2 - e1; c_dw += e3 - e2; c_ld += e4 - e3;
         float f[32];
         if (plain) {
 #pragma unroll
@@ -639,10 +663,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
           }
         }
         store_row32_sw128(sDS + st * HALF_TILE, r, c * 32, f);
+        if (prof_on) c_ma += clock64() - e4;
       }
+      PROF_T(e5);
       fence_proxy_async_smem();
       mbar_arrive(&ds_full[st]);
+      if (prof_on) c_fa += clock64() - e5;
     }
+    const long long t_loop1 = prof_on ? clock64() : 0;
     // ---- write dQ ----
     mbar_wait(&dq_full, 0);
     tc_fence_after();
@@ -665,6 +693,21 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
         }
       }
     }
+    if (prof_on && (threadIdx.x == 128 || threadIdx.x == 256)) {
+      atomicAdd(p.prof + PROF_S_WAIT, (unsigned long long)c_sw);
+      atomicAdd(p.prof + PROF_S_LD, (unsigned long long)c_ld);
+      atomicAdd(p.prof + PROF_MAX_XCHG, (unsigned long long)c_mk);
+      atomicAdd(p.prof + PROF_ABSORB_WAIT, (unsigned long long)c_dw);
+      atomicAdd(p.prof + PROF_EXP_STORE, (unsigned long long)c_ma);
+      atomicAdd(p.prof + PROF_FENCE_ARRIVE, (unsigned long long)c_fa);
+      atomicAdd(p.prof + PROF_LOOP, (unsigned long long)(t_loop1 - t_loop0));
+      atomicAdd(p.prof + PROF_PROLOGUE, (unsigned long long)(t_loop0 - t_start));
+      atomicAdd(p.prof + PROF_EPILOGUE, (unsigned long long)(clock64() - t_loop1));
+      if (threadIdx.x == 128) {
+        atomicAdd(p.prof + PROF_BLOCKS, (unsigned long long)n_kb);
+        atomicAdd(p.prof + PROF_CTAS, 1ull);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -677,9 +720,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
 // ---------------------------------------------------------------------------------------------------
 // dK, dV
 // ---------------------------------------------------------------------------------------------------
+template <bool PROF>
 __global__ void __launch_bounds__(384, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_constant__ CUtensorMap tm_q64,
                        const __grid_constant__ CUtensorMap tm_do64, const AttnParams p) {
+  constexpr bool prof_on = PROF;
+  const long long t_start = prof_on ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t kv_full, qd_full[3], qd_empty[3], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], out_full;
   __shared__ uint32_t tmem_base_smem;
@@ -761,9 +807,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     constexpr uint32_t id_s = idesc_n(64, false);    // [128 keys] x [64 queries], K-major over d
     constexpr uint32_t id_g = idesc_n(128, true);    // [128 keys] x [128 d], B = dO / Q MN-major (k = queries)
     mbar_wait(&kv_full, 0);
+    long long m_k = 0, m_s = 0, m_d = 0;
+    const long long m_t0 = prof_on ? clock64() : 0;
     auto issue_grad = [&](int it) {
       const int st = it & 1, q3 = it % 3;
+      PROF_T(a0);
       mbar_wait(&ds_full[st], (it >> 1) & 1);
+      if (prof_on) m_d += clock64() - a0;
       tc_fence_after();
       const uint32_t qt = sQD + q3 * 2 * HALF_TILE, dt = qt + HALF_TILE;
       const uint32_t pt = sPD + st * 2 * HALF_TILE, dst = pt + HALF_TILE;
@@ -782,8 +832,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     };
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1, q3 = it % 3;
+      PROF_T(b0);
       mbar_wait(&qd_full[q3], (it / 3) & 1);
+      PROF_T(b1);
       mbar_wait(&sp_empty[st], ((it >> 1) & 1) ^ 1u);
+      if (prof_on) { m_k += b1 - b0; m_s += clock64() - b1; }
       tc_fence_after();
       const uint32_t qt = sQD + q3 * 2 * HALF_TILE, dt = qt + HALF_TILE;
 #pragma unroll
@@ -805,6 +858,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     }
     if (n_it > 0) issue_grad(n_it - 1);
     umma_commit(&out_full);
+    if (prof_on) {
+      atomicAdd(p.prof + PROF_M_KFULL, (unsigned long long)m_k);
+      atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
+      atomicAdd(p.prof + PROF_M_PFULL, (unsigned long long)m_d);
+      atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
+    }
   } else if (warp >= 4) {
     // ===================== P^T / dS^T producer: one KEY row per thread, two warpgroups x 32 queries =====================
     const int wg = (warp - 4) >> 2;
@@ -828,9 +887,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       }
     };
     if (n_it > 0) fetch_stats(0);
+    long long c_sw = 0, c_dw = 0, c_ld = 0, c_ma = 0, c_fa = 0, c_mk = 0;
+    const long long t_loop0 = prof_on ? clock64() : 0;
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
       const int qs = (qb0 + it % nqb) * 64;  // local index of the block's first query
+      PROF_T(e0);
       if (t < 64) {
         s_lse[st][t] = lse_n;
         s_del[st][t] = del_n;
@@ -840,8 +902,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       const int c = wg;
       const int qc0 = qs + c * 32;
       const bool need_cmp = d.causal && (qc0 < d.k_local0 + BQ - 1);  // some (key, query) pair may violate key <= query
+      PROF_T(e1);
       mbar_wait(&sp_full[st], (it >> 1) & 1);
+      PROF_T(e2);
       mbar_wait(&ds_empty[st], ((it >> 1) & 1) ^ 1u);
+      PROF_T(e3);
       tc_fence_after();
       const uint32_t pt = sPD + st * 2 * HALF_TILE, dst = pt + HALF_TILE;
       {
@@ -851,6 +916,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&sp_empty[st]);
+        PROF_T(e4);
+        c_mk += e1 - e0; c_sw += e2 - e1; c_dw += e3 - e2; c_ld += e4 - e3;
         float fp[32], fs[32];
         const float4* l4 = reinterpret_cast<const float4*>(&s_lse[st][c * 32]);
         const float4* d4 = reinterpret_cast<const float4*>(&s_del[st][c * 32]);
@@ -869,10 +936,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
         }
         store_row32_sw128(pt, r, c * 32, fp);
         store_row32_sw128(dst, r, c * 32, fs);
+        if (prof_on) c_ma += clock64() - e4;
       }
+      PROF_T(e5);
       fence_proxy_async_smem();
       mbar_arrive(&ds_full[st]);
+      if (prof_on) c_fa += clock64() - e5;
     }
+    const long long t_loop1 = prof_on ? clock64() : 0;
     // ---- write dK (warpgroup 0) / dV (warpgroup 1): bf16 into dqkv (classic) or an fp32 partial slab (packed) ----
     mbar_wait(&out_full, 0);
     tc_fence_after();
@@ -900,6 +971,21 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
             *reinterpret_cast<bf16x8*>(dst16 + c * 32 + u * 8) = pack8(f);
           }
         }
+      }
+    }
+    if (prof_on && (threadIdx.x == 128 || threadIdx.x == 256)) {
+      atomicAdd(p.prof + PROF_S_WAIT, (unsigned long long)c_sw);
+      atomicAdd(p.prof + PROF_S_LD, (unsigned long long)c_ld);
+      atomicAdd(p.prof + PROF_MAX_XCHG, (unsigned long long)c_mk);
+      atomicAdd(p.prof + PROF_ABSORB_WAIT, (unsigned long long)c_dw);
+      atomicAdd(p.prof + PROF_EXP_STORE, (unsigned long long)c_ma);
+      atomicAdd(p.prof + PROF_FENCE_ARRIVE, (unsigned long long)c_fa);
+      atomicAdd(p.prof + PROF_LOOP, (unsigned long long)(t_loop1 - t_loop0));
+      atomicAdd(p.prof + PROF_PROLOGUE, (unsigned long long)(t_loop0 - t_start));
+      atomicAdd(p.prof + PROF_EPILOGUE, (unsigned long long)(clock64() - t_loop1));
+      if (threadIdx.x == 128) {
+        atomicAdd(p.prof + PROF_BLOCKS, (unsigned long long)n_it);
+        atomicAdd(p.prof + PROF_CTAS, 1ull);
       }
     }
   }
@@ -972,12 +1058,15 @@ int set_attrs() {
   if (!once.first()) return 0;
   B200RL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
   B200RL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
-  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
-  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
+  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
+  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
+  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
+  B200RL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
   return 0;
 }
 
 unsigned long long* g_attn_prof = nullptr;   // device buffer of PROF_N counters (debug; scripts/prof_attn_phases.py)
+int g_attn_prof_which = 0;                   // which kernel writes them: 0 forward, 1 dQ, 2 dK/dV
 
 AttnParams base_params(const int* key_mask, int nq, int nkv, float scale) {
   AttnParams p;
@@ -1019,7 +1108,7 @@ int attn_fwd_tc_launch(const void* qkv, const int* key_mask, void* out, float* l
   p.L = L;
   p.stat_h = L;
   dim3 grid((L + BQ - 1) / BQ, nq, B);
-  B200RL_CUDA_OK(launch_pdl(p.prof ? attn_fwd_tc_kernel<true> : attn_fwd_tc_kernel<false>, dim3(grid), dim3(384), SMEM_FWD, stream, tm, p));
+  B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 0 ? attn_fwd_tc_kernel<true> : attn_fwd_tc_kernel<false>, dim3(grid), dim3(384), SMEM_FWD, stream, tm, p));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -1037,12 +1126,12 @@ int attn_bwd_tc_launch(const void* qkv, const int* key_mask, const void* dout, c
   p.stat_h = L;
   {
     dim3 grid((L + BQ - 1) / BQ, nq, B);
-    B200RL_CUDA_OK(launch_pdl(attn_bwd_dq_tc_kernel, dim3(grid), dim3(384), SMEM_DQ, stream, m.q128, m.d128, m.q64, p));
+    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 1 ? attn_bwd_dq_tc_kernel<true> : attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DQ, stream, m.q128, m.d128, m.q64, p));
     B200RL_LAUNCH_OK();
   }
   {
     dim3 grid((L + BQ - 1) / BQ, nkv, B);
-    B200RL_CUDA_OK(launch_pdl(attn_bwd_dkv_tc_kernel, dim3(grid), dim3(384), SMEM_DKV, stream, m.q128, m.q64, m.d64, p));
+    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 2 ? attn_bwd_dkv_tc_kernel<true> : attn_bwd_dkv_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DKV, stream, m.q128, m.q64, m.d64, p));
     B200RL_LAUNCH_OK();
   }
   return 0;
@@ -1061,7 +1150,7 @@ int attn_fwd_seg_launch(const void* qkv, const int* key_mask, void* out, float* 
   p.qblocks = qblocks_dev;
   p.stat_h = (int)rows;
   dim3 grid(n_qblocks, nq, 1);
-  B200RL_CUDA_OK(launch_pdl(p.prof ? attn_fwd_tc_kernel<true> : attn_fwd_tc_kernel<false>, dim3(grid), dim3(384), SMEM_FWD, stream, tm, p));
+  B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 0 ? attn_fwd_tc_kernel<true> : attn_fwd_tc_kernel<false>, dim3(grid), dim3(384), SMEM_FWD, stream, tm, p));
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -1083,12 +1172,12 @@ int attn_bwd_seg_launch(const void* qkv, const int* key_mask, const void* dout, 
   p.stat_h = (int)rows;
   {
     dim3 grid(n_qblocks, nq, 1);
-    B200RL_CUDA_OK(launch_pdl(attn_bwd_dq_tc_kernel, dim3(grid), dim3(384), SMEM_DQ, stream, m.q128, m.d128, m.q64, p));
+    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 1 ? attn_bwd_dq_tc_kernel<true> : attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DQ, stream, m.q128, m.d128, m.q64, p));
     B200RL_LAUNCH_OK();
   }
   {
     dim3 grid(n_kblocks, nkv, 1);
-    B200RL_CUDA_OK(launch_pdl(attn_bwd_dkv_tc_kernel, dim3(grid), dim3(384), SMEM_DKV, stream, m.q128, m.q64, m.d64, p));
+    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 2 ? attn_bwd_dkv_tc_kernel<true> : attn_bwd_dkv_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DKV, stream, m.q128, m.q64, m.d64, p));
     B200RL_LAUNCH_OK();
   }
   B200RL_CUDA_OK(launch_pdl(kv_reduce_kernel, dim3((unsigned)rows), dim3(128), 0, stream, kv_part, red_start_dev, red_list_dev, (bf16*)dqkv, nq, nkv));
@@ -1096,12 +1185,12 @@ int attn_bwd_seg_launch(const void* qkv, const int* key_mask, const void* dout, 
   return 0;
 }
 
-void g_attn_prof_set(unsigned long long* b) { g_attn_prof = b; }
+void g_attn_prof_set(unsigned long long* b, int which) { g_attn_prof = b; g_attn_prof_which = which; }
 
 }  // namespace b200rl
 
 // debug: per-phase cycle counters of the tcgen05 attention forward kernel (18 x uint64 device buffer, or NULL = off)
-extern "C" int b200rl_attn_set_prof(void* buf_dev) {
-  b200rl::g_attn_prof_set(reinterpret_cast<unsigned long long*>(buf_dev));
+extern "C" int b200rl_attn_set_prof(void* buf_dev, int which) {
+  b200rl::g_attn_prof_set(reinterpret_cast<unsigned long long*>(buf_dev), which);
   return 0;
 }

@@ -103,7 +103,7 @@ int b200rl_scatter_add_rows(const void* d, const int* start, const int* list, vo
 int b200rl_attn_fwd(const void* qkv, const int* key_mask, void* out, float* lse, int B, int L,
                     int n_q_heads, int n_kv_heads, int head_dim, float scale, void* stream);
 /* bisection switch: 1 (default) = tcgen05/TMEM attention where available (head_dim 128), 0 = mma.sync kernels */
-int b200rl_attn_set_prof(void* buf_dev); /* debug: 18 x uint64 per-phase cycle sums of the tcgen05 attention forward (NULL = off) */
+int b200rl_attn_set_prof(void* buf_dev, int which); /* debug: 18 x uint64 per-phase cycle sums of a tcgen05 attention kernel (which: 0 fwd, 1 dQ, 2 dK/dV; NULL = off) */
 int b200rl_attn_set_tc(int enable);
 int b200rl_attn_bwd(const void* qkv, const int* key_mask, const void* out, const void* dout,
                     const float* lse, float* delta, void* dqkv, int B, int L, int n_q_heads,

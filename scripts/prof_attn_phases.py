@@ -50,17 +50,48 @@ for _ in range(10):
 e1.record()
 torch.cuda.synchronize()
 print(f"rows {rows}, q-blocks {c.n_qblocks}, fwd {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch (counters off)")
-prof = torch.zeros(18, device=dev, dtype=torch.int64)
-lib.b200rl_attn_set_prof(prof.data_ptr())
-fwd()
+dout = (torch.randn(rows, nq * hd, device=dev) * 0.5).to(torch.bfloat16)
+delta = torch.empty_like(lse)
+dqkv = torch.zeros_like(qkv)
+kvpart = torch.empty(host.part_rows, 2 * nkv * hd, device=dev, dtype=torch.float32)
+
+
+def bwd():
+    _capi.check(lib.b200rl_attn_seg_bwd(qkv.data_ptr(), c.key_mask, out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                        delta.data_ptr(), dqkv.data_ptr(), kvpart.data_ptr(), rows, nq, nkv, hd ** -0.5,
+                                        c.qblocks, c.n_qblocks, c.kblocks, c.n_kblocks, c.red_start, c.red_list,
+                                        _capi.stream()), "attn_seg_bwd")
+
+
+for _ in range(3):
+    bwd()
 torch.cuda.synchronize()
-lib.b200rl_attn_set_prof(None)
-v = prof.cpu().numpy().astype(np.float64)
-blocks, ctas = v[16], v[17]
-print(f"CTAs {int(ctas)}, key blocks {int(blocks)} ({blocks / ctas:.2f} per CTA)")
-for i in range(10):
-    per = v[i] / (2 * ctas) if i >= 7 else v[i] / (2 * blocks)      # two reporting threads (one per softmax warpgroup)
-    print(f"  softmax  {NAMES[i]:24s} {per:9.0f} cycles per {'CTA' if i >= 7 else 'key block'}")
-for i in range(10, 16):
-    per = v[i] / ctas if i == 15 else v[i] / blocks
-    print(f"  issuer   {NAMES[i]:24s} {per:9.0f} cycles per {'CTA' if i == 15 else 'key block'}")
+e0.record()
+for _ in range(10):
+    bwd()
+e1.record()
+torch.cuda.synchronize()
+print(f"k-blocks {c.n_kblocks}, bwd (delta + dQ + dK/dV + reduce) {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch (counters off)")
+
+BWD_NAMES = ["S/dP full wait", "S,dP tmem ld", "mask ballot / stats stage", "dS buffer free wait", "-", "exp + dS math + store", "fence+arrive",
+             "loop total", "prologue", "epilogue", "MMA: operand full wait", "MMA: S/dP tmem free wait", "MMA: dS full wait", "-", "-", "MMA total",
+             "blocks", "CTAs"]
+for which, title, names, run in ((0, "forward", NAMES, fwd), (1, "dQ kernel", BWD_NAMES, bwd), (2, "dK/dV kernel", BWD_NAMES, bwd)):
+    prof = torch.zeros(18, device=dev, dtype=torch.int64)
+    lib.b200rl_attn_set_prof(prof.data_ptr(), which)
+    run()
+    torch.cuda.synchronize()
+    lib.b200rl_attn_set_prof(None, 0)
+    v = prof.cpu().numpy().astype(np.float64)
+    blocks, ctas = v[16], v[17]
+    print(f"== {title}: CTAs {int(ctas)}, inner blocks {int(blocks)} ({blocks / ctas:.2f} per CTA)")
+    for i in range(10):
+        if names[i] == "-":
+            continue
+        per = v[i] / (2 * ctas) if i >= 7 else v[i] / (2 * blocks)      # two reporting threads (one per softmax warpgroup)
+        print(f"  softmax  {names[i]:26s} {per:9.0f} cycles per {'CTA' if i >= 7 else 'block'}")
+    for i in range(10, 16):
+        if names[i] == "-":
+            continue
+        per = v[i] / ctas if i == 15 else v[i] / blocks
+        print(f"  issuer   {names[i]:26s} {per:9.0f} cycles per {'CTA' if i == 15 else 'block'}")
