@@ -52,6 +52,8 @@ SIGNATURES = {
     "b200rl_gemm_set_cta_pair": (c_int, [c_int]),
     "b200rl_gemm_set_tail_split": (c_int, [c_int]),
     "b200rl_gemm_set_wide": (c_int, [c_int]),
+    "b200rl_gemm_set_raster": (c_int, [c_int]),
+    "b200rl_logprob_slots": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_double, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200rl_gemm_set_ext": (c_int, [c_int]),
     "b200rl_gemm_nf4": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll,
                                 c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),

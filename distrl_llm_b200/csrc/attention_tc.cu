@@ -539,29 +539,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
       tma_load_rows(vd + HALF_TILE / 2, &tm_kv64, &kv_full[st], vcol + 64, row0);
     }
   } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer 1: S_j = Q.K_j^T and dP_j = dO.V_j^T =====================
+    // Two issuing threads on two SM sub-partitions (profiles/r2_run11: one thread needs ~90 cycles per tcgen05.mma
+    // while N = 64 MMAs execute in 48, so a single issuer, not the tensor pipe, paced the kernel).  The tensor pipe
+    // runs the MMAs in arrival order; the order that matters is carried by the mbarriers as before.
     constexpr uint32_t id_s = idesc_n(64, false);    // [128 q] x [64 keys], both K-major over d
-    constexpr uint32_t id_dq = idesc_n(128, true);   // [128 q] x [128 d], B = K_j MN-major (k = keys)
     mbar_wait(&qdo_full, 0);
-    long long m_k = 0, m_s = 0, m_d = 0;
+    long long m_k = 0, m_s = 0;
     const long long m_t0 = prof_on ? clock64() : 0;
-    auto issue_dq = [&](int j) {
-      const int st = j & 1, k3 = j % 3;
-      PROF_T(a0);
-      mbar_wait(&ds_full[st], (j >> 1) & 1);
-      if (prof_on) m_d += clock64() - a0;
-      tc_fence_after();
-      const uint32_t kt = sKV + k3 * 2 * HALF_TILE;
-      const uint32_t ds = sDS + st * HALF_TILE;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {  // 64 keys = 4 x K16
-        const uint64_t da = smem_desc_sw128(ds + kk * 32, 16, 1024);
-        const uint64_t db = smem_desc_sw128(kt + kk * 2048, HALF_TILE / 2, 1024);
-        umma_bf16(tmem_base + 256, da, db, id_dq, (j > 0 || kk > 0) ? 1u : 0u);
-      }
-      umma_commit(&kv_empty[k3]);
-      umma_commit(&ds_empty[st]);
-    };
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1, k3 = j % 3;
       PROF_T(b0);
@@ -586,15 +571,40 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
                   smem_desc_sw128(vt + boff, 16, 1024), id_s, kk > 0 ? 1u : 0u);
       }
       umma_commit(&sp_full[st]);
-      if (j > 0) issue_dq(j - 1);
     }
-    issue_dq(n_kb - 1);
-    umma_commit(&dq_full);
     if (prof_on) {
       atomicAdd(p.prof + PROF_M_KFULL, (unsigned long long)m_k);
       atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
-      atomicAdd(p.prof + PROF_M_PFULL, (unsigned long long)m_d);
       atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===================== MMA issuer 2: dQ += dS_j.K_j =====================
+    constexpr uint32_t id_dq = idesc_n(128, true);   // [128 q] x [128 d], B = K_j MN-major (k = keys)
+    long long m_d = 0;
+    const long long m_t0 = prof_on ? clock64() : 0;
+    for (int j = 0; j < n_kb; ++j) {
+      const int st = j & 1, k3 = j % 3;
+      PROF_T(a0);
+      mbar_wait(&kv_full[k3], (j / 3) & 1);  // K_j landed (long ago: dS_j was computed from it); orders this thread's reads
+      mbar_wait(&ds_full[st], (j >> 1) & 1);
+      if (prof_on) m_d += clock64() - a0;
+      tc_fence_after();
+      const uint32_t kt = sKV + k3 * 2 * HALF_TILE;
+      const uint32_t ds = sDS + st * HALF_TILE;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {  // 64 keys = 4 x K16
+        const uint64_t da = smem_desc_sw128(ds + kk * 32, 16, 1024);
+        const uint64_t db = smem_desc_sw128(kt + kk * 2048, HALF_TILE / 2, 1024);
+        umma_bf16(tmem_base + 256, da, db, id_dq, (j > 0 || kk > 0) ? 1u : 0u);
+      }
+      // S_j / dP_j (issuer 1) completed before dS_j existed, so K_j / V_j have no reader left once dQ_j is done
+      umma_commit(&kv_empty[k3]);
+      umma_commit(&ds_empty[st]);
+    }
+    umma_commit(&dq_full);
+    if (prof_on) {
+      atomicAdd(p.prof + PROF_M_PFULL, (unsigned long long)m_d);
+      atomicAdd(p.prof + PROF_M_VFULL, (unsigned long long)(clock64() - m_t0));
     }
   } else if (warp >= 4) {
     // ===================== dS producer: two warpgroups, each 32 of the 64 keys of a block =====================
@@ -803,33 +813,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       tma_load_rows(dd + HALF_TILE / 2, &tm_do64, &qd_full[st], h * HD + 64, qrow);
     }
   } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer 1: S^T = K.Q^T and dP^T = V.dO^T (see the dQ kernel: two issuing threads) ==========
     constexpr uint32_t id_s = idesc_n(64, false);    // [128 keys] x [64 queries], K-major over d
-    constexpr uint32_t id_g = idesc_n(128, true);    // [128 keys] x [128 d], B = dO / Q MN-major (k = queries)
     mbar_wait(&kv_full, 0);
-    long long m_k = 0, m_s = 0, m_d = 0;
+    long long m_k = 0, m_s = 0;
     const long long m_t0 = prof_on ? clock64() : 0;
-    auto issue_grad = [&](int it) {
-      const int st = it & 1, q3 = it % 3;
-      PROF_T(a0);
-      mbar_wait(&ds_full[st], (it >> 1) & 1);
-      if (prof_on) m_d += clock64() - a0;
-      tc_fence_after();
-      const uint32_t qt = sQD + q3 * 2 * HALF_TILE, dt = qt + HALF_TILE;
-      const uint32_t pt = sPD + st * 2 * HALF_TILE, dst = pt + HALF_TILE;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {  // 64 queries = 4 x K16
-        umma_bf16(tmem_base + 384, smem_desc_sw128(pt + kk * 32, 16, 1024),
-                  smem_desc_sw128(dt + kk * 2048, HALF_TILE / 2, 1024), id_g, (it > 0 || kk > 0) ? 1u : 0u);
-      }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        umma_bf16(tmem_base + 256, smem_desc_sw128(dst + kk * 32, 16, 1024),
-                  smem_desc_sw128(qt + kk * 2048, HALF_TILE / 2, 1024), id_g, (it > 0 || kk > 0) ? 1u : 0u);
-      }
-      umma_commit(&qd_empty[q3]);
-      umma_commit(&ds_empty[st]);
-    };
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1, q3 = it % 3;
       PROF_T(b0);
@@ -854,15 +842,43 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
                   smem_desc_sw128(dt + boff, 16, 1024), id_s, kk > 0 ? 1u : 0u);
       }
       umma_commit(&sp_full[st]);
-      if (it > 0) issue_grad(it - 1);
     }
-    if (n_it > 0) issue_grad(n_it - 1);
-    umma_commit(&out_full);
     if (prof_on) {
       atomicAdd(p.prof + PROF_M_KFULL, (unsigned long long)m_k);
       atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
-      atomicAdd(p.prof + PROF_M_PFULL, (unsigned long long)m_d);
       atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===================== MMA issuer 2: dV += P^T.dO and dK += dS^T.Q =====================
+    constexpr uint32_t id_g = idesc_n(128, true);    // [128 keys] x [128 d], B = dO / Q MN-major (k = queries)
+    long long m_d = 0;
+    const long long m_t0 = prof_on ? clock64() : 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1, q3 = it % 3;
+      PROF_T(a0);
+      mbar_wait(&qd_full[q3], (it / 3) & 1);  // landed long ago (P^T was computed from it); orders this thread's reads
+      mbar_wait(&ds_full[st], (it >> 1) & 1);
+      if (prof_on) m_d += clock64() - a0;
+      tc_fence_after();
+      const uint32_t qt = sQD + q3 * 2 * HALF_TILE, dt = qt + HALF_TILE;
+      const uint32_t pt = sPD + st * 2 * HALF_TILE, dst = pt + HALF_TILE;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {  // 64 queries = 4 x K16
+        umma_bf16(tmem_base + 384, smem_desc_sw128(pt + kk * 32, 16, 1024),
+                  smem_desc_sw128(dt + kk * 2048, HALF_TILE / 2, 1024), id_g, (it > 0 || kk > 0) ? 1u : 0u);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        umma_bf16(tmem_base + 256, smem_desc_sw128(dst + kk * 32, 16, 1024),
+                  smem_desc_sw128(qt + kk * 2048, HALF_TILE / 2, 1024), id_g, (it > 0 || kk > 0) ? 1u : 0u);
+      }
+      umma_commit(&qd_empty[q3]);
+      umma_commit(&ds_empty[st]);
+    }
+    umma_commit(&out_full);
+    if (prof_on) {
+      atomicAdd(p.prof + PROF_M_PFULL, (unsigned long long)m_d);
+      atomicAdd(p.prof + PROF_M_VFULL, (unsigned long long)(clock64() - m_t0));
     }
   } else if (warp >= 4) {
     // ===================== P^T / dS^T producer: one KEY row per thread, two warpgroups x 32 queries =====================

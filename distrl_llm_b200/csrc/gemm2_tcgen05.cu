@@ -1102,6 +1102,12 @@ extern "C" int b200rl_gemm_set_ext(int enable) {
   return 0;
 }
 // test / A-B switch for the wide (256 x 512) pair tiles: 1 = use them where applicable (default), 0 = 256 x 256 only
+namespace b200rl { int g_gemm_raster_forced = 0; }
+extern "C" int b200rl_gemm_set_raster(int gm) {
+  b200rl::g_gemm_raster_forced = gm > 0 ? gm : 0;
+  return 0;
+}
+
 extern "C" int b200rl_gemm_set_wide(int mode) {
   b200rl::g_wide = (mode < 0 || mode > 2) ? 0 : mode;
   return 0;

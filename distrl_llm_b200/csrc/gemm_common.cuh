@@ -220,7 +220,9 @@ bool gemm_fuse_supported(int M, int I);
 // cut the B traffic as long as a group's A panels stay L2-resident (ncu, packed config 2: with gm = 8 the gate|up GEMM
 // read B 3x from DRAM at 18 m-blocks and 4.4x at 35).  K-long operands (panels > 5 MB) keep the square-ish 8 x ~9 patch
 // that minimises (gm + gn) panels per wave.
+extern int g_gemm_raster_forced;   // b200rl_gemm_set_raster (debug / sweeps): > 0 overrides the choice below
 inline int raster_group(long long a_bytes, int num_m_blocks) {
+  if (g_gemm_raster_forced > 0) return g_gemm_raster_forced;
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("B200RL_GEMM_GM");

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(1024)
 logprob_kernel(bf16* __restrict__ logits, long long ld, const int* __restrict__ targets,
                const float* __restrict__ coef, const float* __restrict__ klw,
                const float* __restrict__ ref_lp, const float* __restrict__ old_lp, float clip_eps,
-               float* __restrict__ lp_out, int V, int write_grad) {
+               float* __restrict__ lp_out, int V, int write_grad, const int* __restrict__ slot) {
   __shared__ float red_m[32], red_s[32];
   __shared__ float s_lse2, s_max2;
   const size_t row = blockIdx.x;
@@ -81,23 +81,26 @@ logprob_kernel(bf16* __restrict__ logits, long long ld, const int* __restrict__ 
   }
   __syncthreads();
   const float lse2 = s_lse2;
+  // compacted scoring (packed layout, live rows only): logits / targets are per compacted row, the per-token arrays
+  // (coef, klw, ref_lp, old_lp, lp_out) stay [B*T] and are addressed through the row's slot
+  const size_t sl = slot ? (size_t)slot[row] : row;
   const int y = targets[row];
   const float zy = (y >= 0 && y < V) ? __bfloat162float(z[y]) : 0.f;
   const float lp = (y >= 0 && y < V) ? (zy * LOG2E - lse2) * LN2 : 0.f;
-  float c = coef ? coef[row] : 0.f;
+  float c = coef ? coef[sl] : 0.f;
   // optional clipped-ratio surrogate (not in the reference, whose ratio exp(lp - lp.detach()) is identically 1,
   // distributed_actor.py:467): loss_t = -min(rho A, clip(rho, 1-eps, 1+eps) A) with rho = exp(lp - old_lp), so
   // d loss_t / d lp = -A rho while the unclipped branch is the active minimum and 0 once rho has left the trust region in
   // the direction the advantage pushes.  coef carries -A mask / (len Bm nb): its sign is that of -A.
   if (old_lp && clip_eps > 0.f && c != 0.f) {
-    const float rho = __expf(lp - old_lp[row]);
+    const float rho = __expf(lp - old_lp[sl]);
     const bool active = c < 0.f ? rho <= 1.f + clip_eps : rho >= 1.f - clip_eps;
     c = active ? c * rho : 0.f;
   }
   // optional KL(pi || pi_ref) term, k3 estimator exp(q-p) - (q-p) - 1 per token:
   // d k3 / d lp = 1 - exp(q - p); klw carries beta * mask / (len * Bm * nb)   (not in the reference: beta = 0)
-  if (klw && ref_lp && klw[row] != 0.f) c += klw[row] * (1.f - __expf(ref_lp[row] - lp));
-  if (threadIdx.x == 0 && lp_out) lp_out[row] = lp;
+  if (klw && ref_lp && klw[sl] != 0.f) c += klw[sl] * (1.f - __expf(ref_lp[sl] - lp));
+  if (threadIdx.x == 0 && lp_out) lp_out[sl] = lp;
   if (!write_grad) return;
   __syncthreads();  // z[y] read above must precede the in-place overwrite
   // ---- pass 2: dz = coef * (onehot - softmax), in place ----
@@ -228,7 +231,7 @@ extern "C" int b200rl_logprob_kl(void* logits, long long ld, const int* targets,
   B200RL_REQUIRE(!write_grad || coef, "logprob: write_grad needs coef");
   const int threads = V >= 8192 ? 1024 : 256;
   logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, klw, ref_lp, nullptr, 0.f, lp_out, V,
-                                               write_grad);
+                                               write_grad, nullptr);
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -240,7 +243,7 @@ extern "C" int b200rl_logprob(void* logits, long long ld, const int* targets, co
   B200RL_REQUIRE(!write_grad || coef, "logprob: write_grad needs coef");
   const int threads = V >= 8192 ? 1024 : 256;
   logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, nullptr, nullptr, nullptr, 0.f, lp_out,
-                                               V, write_grad);
+                                               V, write_grad, nullptr);
   B200RL_LAUNCH_OK();
   return 0;
 }
@@ -279,18 +282,25 @@ extern "C" int b200rl_loss_value(const float* lp, const int* mask, const double*
 
 // Clipped-ratio variants (not in the reference): old_lp [rows] = log-probs of the policy that
 // generated the batch, clip_eps = trust-region half width.  old_lp == NULL or clip_eps == 0 is the plain form above.
-extern "C" int b200rl_logprob_clip(void* logits, long long ld, const int* targets, const float* coef, const float* klw,
-                                   const float* ref_lp, const float* old_lp, double clip_eps, float* lp_out, int rows,
-                                   int V, int write_grad, void* stream) {
+extern "C" int b200rl_logprob_slots(void* logits, long long ld, const int* targets, const float* coef, const float* klw,
+                                    const float* ref_lp, const float* old_lp, double clip_eps, float* lp_out, int rows,
+                                    int V, int write_grad, const int* slot, void* stream) {
   B200RL_REQUIRE(logits && targets && rows > 0 && V > 0 && V % 8 == 0 && ld % 8 == 0,
                  "logprob: bad args (rows=%d V=%d ld=%lld)", rows, V, ld);
   B200RL_REQUIRE(!write_grad || coef, "logprob: write_grad needs coef");
   B200RL_REQUIRE(clip_eps >= 0.0, "logprob: clip_eps must be >= 0");
   const int threads = V >= 8192 ? 1024 : 256;
   logprob_kernel<<<rows, threads, 0, STREAM>>>((bf16*)logits, ld, targets, coef, klw, ref_lp, old_lp, (float)clip_eps,
-                                               lp_out, V, write_grad);
+                                               lp_out, V, write_grad, slot);
   B200RL_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int b200rl_logprob_clip(void* logits, long long ld, const int* targets, const float* coef, const float* klw,
+                                   const float* ref_lp, const float* old_lp, double clip_eps, float* lp_out, int rows,
+                                   int V, int write_grad, void* stream) {
+  return b200rl_logprob_slots(logits, ld, targets, coef, klw, ref_lp, old_lp, clip_eps, lp_out, rows, V, write_grad,
+                              nullptr, stream);
 }
 
 extern "C" int b200rl_loss_value_clip(const float* lp, const int* mask, const double* adv, const float* ref_lp,

@@ -774,7 +774,9 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
                           const float* old_lp, double clip_eps, void* stream) {
   const b200rl_model_config& c = m->cfg;
   const b200rl_packed_batch* pb = lay.pb;
-  const int M = lay.M, B = lay.B, T = lay.T, L = lay.L, P = lay.P, R = B * T;
+  const int M = lay.M, B = lay.B, T = lay.T, L = lay.L, P = lay.P;
+  const int* score_slot = (lay.pb && lay.pb->n_score > 0) ? lay.pb->score_slot : nullptr;
+  const int R = score_slot ? lay.pb->n_score : B * T;   // scored rows: all B*T positions, or the live ones only
   const int* ids = lay.ids;
   const int* attn_mask = lay.key_mask;
   const int* answer_mask = lay.answer_mask;
@@ -865,10 +867,11 @@ static int run_microbatch(b200rl_model* m, const Layout& lay, const double* adv,
   PM(CAT_MISC, 0);
   if (backward) RC(b200rl_loss_coef_kl(answer_mask, adv, m->coef, use_kl ? m->klw : nullptr, kl_beta, m->lens, B, T, nb, stream));
   float* lp = lp_out ? lp_out : m->lp;
+  if (score_slot) B200RL_CUDA_OK(cudaMemsetAsync(lp, 0, sizeof(float) * (size_t)B * T, st));  // positions left out report 0
   PM(CAT_LOGPROB, (backward ? 2.0 : 1.0) * R * V * 2);
-  RC(b200rl_logprob_clip(m->logits, V, targets, backward ? m->coef : nullptr, use_kl ? m->klw : nullptr,
-                         use_kl ? ref_lp : nullptr, use_clip ? old_lp : nullptr, use_clip ? clip_eps : 0.0, lp, R, V,
-                         backward ? 1 : 0, stream));
+  RC(b200rl_logprob_slots(m->logits, V, targets, backward ? m->coef : nullptr, use_kl ? m->klw : nullptr,
+                          use_kl ? ref_lp : nullptr, use_clip ? old_lp : nullptr, use_clip ? clip_eps : 0.0, lp, R, V,
+                          backward ? 1 : 0, score_slot, stream));
   PM(CAT_MISC, 0);
   if (loss_accum && adv)
     RC(b200rl_loss_value_clip(lp, answer_mask, adv, use_kl ? ref_lp : nullptr, use_kl ? kl_beta : 0.0,
@@ -1083,6 +1086,8 @@ static int packed_pass(b200rl_model* m, const b200rl_packed_batch* pb, const dou
   B200RL_REQUIRE(pb->rows > 0 && pb->rows <= c.max_tokens && pb->B > 0 && pb->B <= c.max_batch && pb->T >= 1 &&
                      pb->B * pb->T <= c.max_score_rows && pb->max_pos >= 1 && pb->max_pos <= c.max_seq,
                  "model_microbatch_packed: batch exceeds the workspace (rows=%d B=%d T=%d)", pb->rows, pb->B, pb->T);
+  B200RL_REQUIRE(pb->n_score >= 0 && pb->n_score <= pb->B * pb->T && (pb->n_score == 0 || pb->score_slot),
+                 "model_microbatch_packed: n_score=%d outside [0, B*T=%d] or score_slot missing", pb->n_score, pb->B * pb->T);
   B200RL_REQUIRE(pb->part_rows <= m->kvpart_rows, "model_microbatch_packed: %d dK/dV partial rows > capacity %lld",
                  pb->part_rows, m->kvpart_rows);
   Layout lay;

@@ -83,6 +83,9 @@ class BaseLearner:
         self.share_prompts = bool(config.get("share_prompts", policy.cfg.head_dim == 128))
         # packed layout only: do not store pad tokens at all (packing.py).  Same surviving rows, same positions.
         self.ragged_rows = bool(config.get("ragged_rows", True))
+        # head (final norm, lm_head, log-softmax, lm_head dX) on the completion tokens that carry loss only; False =
+        # all max_new_tokens positions of every sequence like the reference (:245-260), masked afterwards
+        self.compact_scored_rows = bool(config.get("compact_scored_rows", True))
         # Pass fusion: the reference accumulates gradients over micro-batches of train_batch_size sequences
         # (:354-389) because a pass has to fit a 24-80 GB GPU.  The accumulated gradient is linear in the per-sequence
         # coefficients, so k full micro-batches can go through the model as ONE pass with every advantage (and the KL
@@ -133,7 +136,7 @@ class BaseLearner:
 
     def _pack(self, ids, am):
         host = packing.pack_microbatch(ids.numpy(), am.numpy(), self.max_prompt_tokens, self.max_new_tokens,
-                                       ragged=self.ragged_rows)
+                                       ragged=self.ragged_rows, compact_scored=self.compact_scored_rows)
         return packing.PackedDevice(host, self.policy.device, stager=self._stager)
 
     # ---- loss + backward (:349-395 PG, :440-493 GRPO) ---------------------------------------------

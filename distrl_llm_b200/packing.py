@@ -39,7 +39,8 @@ class PackedBatchC(C.Structure):
                 ("n_qblocks", C.c_int), ("n_kblocks", C.c_int), ("part_rows", C.c_int),
                 ("ids", C.c_void_p), ("pos", C.c_void_p), ("key_mask", C.c_void_p), ("score_src", C.c_void_p),
                 ("targets", C.c_void_p), ("answer_mask", C.c_void_p), ("sc_start", C.c_void_p), ("sc_list", C.c_void_p),
-                ("qblocks", C.c_void_p), ("kblocks", C.c_void_p), ("red_start", C.c_void_p), ("red_list", C.c_void_p)]
+                ("qblocks", C.c_void_p), ("kblocks", C.c_void_p), ("red_start", C.c_void_p), ("red_list", C.c_void_p),
+                ("n_score", C.c_int), ("score_slot", C.c_void_p)]
 
 
 @dataclass
@@ -73,8 +74,11 @@ class PackedHost:
         return np.concatenate(parts), offs
 
 
-def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int, ragged: bool = True) -> PackedHost:
-    """ids / attn_mask: [B, P+T] (prompt left-padded to P, completion right-padded to T, reference layout)."""
+def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int, ragged: bool = True,
+                    compact_scored: bool = True) -> PackedHost:
+    """ids / attn_mask: [B, P+T] (prompt left-padded to P, completion right-padded to T, reference layout).
+    compact_scored: the head (final norm, lm_head, log-softmax, lm_head dX) runs on the scored positions with
+    answer_mask 1 only; False keeps all B*T positions like the reference (distributed_actor.py:245-260)."""
     ids = np.asarray(ids, dtype=np.int32)
     am = np.asarray(attn_mask, dtype=np.int32)
     B, L = ids.shape
@@ -143,7 +147,22 @@ def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int, ragg
     # positions without a source row must not be trained on (they are pad positions: answer_mask is already 0 there,
     # except when a sequence has an empty prompt, which the reference cannot produce)
     answer_mask = np.where(live, answer_mask, 0).astype(np.int32)
-    live_idx = np.flatnonzero(live)
+    if compact_scored:
+        # scored rows = the positions that carry loss, in slot order (keeps at least one row: an all-masked micro-batch
+        # still runs the head once, with coefficient 0)
+        score_slot = np.flatnonzero(answer_mask != 0).astype(np.int32)
+        if score_slot.size == 0:
+            score_slot = np.zeros(1, np.int32)
+        if score_slot.size == B * T:
+            score_slot = np.zeros(0, np.int32)      # nothing to drop: identity, no indirection
+        else:
+            live_c = live[score_slot]
+            score_src = score_src[score_slot]
+            targets = targets[score_slot]
+            live = live_c
+    else:
+        score_slot = np.zeros(0, np.int32)
+    live_idx = np.flatnonzero(live)                  # indices of scored ROWS (compacted or not) that have a source row
     order = live_idx[np.argsort(score_src[live_idx], kind="stable")]
     counts = np.bincount(score_src[live_idx], minlength=rows)
     sc_start = np.zeros(rows + 1, np.int32)
@@ -193,7 +212,7 @@ def pack_microbatch(ids: np.ndarray, attn_mask: np.ndarray, P: int, T: int, ragg
     kblocks = np.array([t[1] for t in kb], np.int32).reshape(-1, KB_FIELDS)
     arrays = {"ids": p_ids, "pos": p_pos, "key_mask": p_km, "score_src": score_src, "targets": targets,
               "answer_mask": answer_mask, "sc_start": sc_start, "sc_list": sc_list, "qblocks": qblocks.reshape(-1),
-              "kblocks": kblocks.reshape(-1), "red_start": red_start, "red_list": red_list}
+              "kblocks": kblocks.reshape(-1), "red_start": red_start, "red_list": red_list, "score_slot": score_slot}
     host = PackedHost(rows=rows, B=B, P=P, T=T, n_groups=G, part_rows=max(part_rows, 1), arrays=arrays, seq_group=seq_group)
     host.prompt_row0, host.prompt_ext = p_row0, p_ext       # (first kept padded index, rows) per group
     host.comp_row0, host.comp_len = c_row0, [e[1] for e in c_ext]
@@ -260,4 +279,6 @@ class PackedDevice:
         self.c = PackedBatchC(host.rows, host.B, host.T, host.P + host.T, offs["qblocks"][1] // QB_FIELDS,
                               offs["kblocks"][1] // KB_FIELDS, host.part_rows, p("ids"), p("pos"), p("key_mask"),
                               p("score_src"), p("targets"), p("answer_mask"), p("sc_start"), p("sc_list"),
-                              p("qblocks"), p("kblocks"), p("red_start"), p("red_list"))
+                              p("qblocks"), p("kblocks"), p("red_start"), p("red_list"),
+                              offs["score_slot"][1], p("score_slot") if offs["score_slot"][1] else None)
+        self.n_score = offs["score_slot"][1] or host.B * host.T

@@ -44,6 +44,7 @@ int b200rl_gemm(const void* A1, long long lda1, const void* B1, long long ldb1, 
 int b200rl_gemm_set_cta_pair(int enable);
 /* 1 (default) = the CTA-pair GEMM splits the tiles of its last, partially filled wave along K (gemm2_tcgen05.cu) */
 int b200rl_gemm_set_tail_split(int enable);
+int b200rl_gemm_set_raster(int gm); /* debug / sweeps: m-blocks per rasterisation group of the CTA-pair GEMM (0 = automatic, gemm_common.cuh raster_group) */
 int b200rl_gemm_set_wide(int mode); /* 256 x 512 CTA-pair tiles: 0 never, 1 wherever every pair gets one, 2 (default) only for K-long GEMMs (gemm2_tcgen05.cu) */
 /* GEMM with the NF4 base weight dequantised INSIDE the mainloop (north_star; reference: load_in_4bit weights,
  * distributed_actor.py:16-17, :58-66): four producer warps per CTA expand the packed codes of every k-block into the
@@ -159,6 +160,11 @@ int b200rl_loss_value_kl(const float* lp, const int* mask, const double* adv, co
 int b200rl_logprob_clip(void* logits, long long ld, const int* targets, const float* coef, const float* klw,
                         const float* ref_lp, const float* old_lp, double clip_eps, float* lp_out, int rows, int V,
                         int write_grad, void* stream);
+/* same with compacted rows: logits / targets hold `rows` live scored rows, slot[rows] maps each to its (i*T + t) entry of
+ * the per-token arrays coef / klw / ref_lp / old_lp / lp_out (slot NULL = identity, the call above) */
+int b200rl_logprob_slots(void* logits, long long ld, const int* targets, const float* coef, const float* klw,
+                         const float* ref_lp, const float* old_lp, double clip_eps, float* lp_out, int rows, int V,
+                         int write_grad, const int* slot, void* stream);
 int b200rl_loss_value_clip(const float* lp, const int* mask, const double* adv, const float* ref_lp, double beta,
                            const float* old_lp, double clip_eps, double* accum, int Bm, int T, int grpo, void* stream);
 
@@ -273,8 +279,8 @@ typedef struct b200rl_packed_batch {
   const int* ids;          /* [rows] */
   const int* pos;          /* [rows] position of the token in its original sequence */
   const int* key_mask;     /* [rows] 1 = real token */
-  const int* score_src;    /* [B*T] packed row whose hidden state predicts completion token (i, t) */
-  const int* targets;      /* [B*T] completion token ids */
+  const int* score_src;    /* [n_score] packed row whose hidden state predicts completion token (i, t) */
+  const int* targets;      /* [n_score] completion token ids */
   const int* answer_mask;  /* [B*T] */
   const int* sc_start;     /* [rows+1] CSR: scored rows fed by each packed row */
   const int* sc_list;
@@ -282,6 +288,12 @@ typedef struct b200rl_packed_batch {
   const b200rl_attn_kblock* kblocks;
   const int* red_start;    /* [rows+1] CSR: dK/dV partial rows of each packed row */
   const int* red_list;
+  /* live scored rows only (distributed_actor.py:245-260 scores all T positions and masks afterwards; positions with
+   * answer_mask 0 carry no loss and no gradient, so the final norm / lm_head / log-softmax / lm_head dX run on the
+   * n_score <= B*T live ones): score_slot[n_score] = i*T + t of each scored row.  n_score 0 / score_slot NULL = all
+   * B*T positions in slot order.  Log-probs of the positions left out are reported as 0. */
+  int n_score;
+  const int* score_slot;
 } b200rl_packed_batch;
 /* same contract as b200rl_model_microbatch_ex on the packed layout (head_dim 128 only) */
 int b200rl_model_microbatch_packed(b200rl_model* m, const b200rl_packed_batch* pb, const double* adv, float* lp_out,

@@ -74,7 +74,7 @@ torch.cuda.synchronize()
 print(f"k-blocks {c.n_kblocks}, bwd (delta + dQ + dK/dV + reduce) {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch (counters off)")
 
 BWD_NAMES = ["S/dP full wait", "S,dP tmem ld", "mask ballot / stats stage", "dS buffer free wait", "-", "exp + dS math + store", "fence+arrive",
-             "loop total", "prologue", "epilogue", "MMA: operand full wait", "MMA: S/dP tmem free wait", "MMA: dS full wait", "-", "-", "MMA total",
+             "loop total", "prologue", "epilogue", "MMA1: operand full wait", "MMA1: S/dP tmem free wait", "MMA2: dS full wait", "MMA2 total", "-", "MMA1 total",
              "blocks", "CTAs"]
 for which, title, names, run in ((0, "forward", NAMES, fwd), (1, "dQ kernel", BWD_NAMES, bwd), (2, "dK/dV kernel", BWD_NAMES, bwd)):
     prof = torch.zeros(18, device=dev, dtype=torch.int64)
@@ -93,5 +93,6 @@ for which, title, names, run in ((0, "forward", NAMES, fwd), (1, "dQ kernel", BW
     for i in range(10, 16):
         if names[i] == "-":
             continue
-        per = v[i] / ctas if i == 15 else v[i] / blocks
-        print(f"  issuer   {names[i]:26s} {per:9.0f} cycles per {'CTA' if i == 15 else 'block'}")
+        per_cta = i == 15 or (which > 0 and i == 13)
+        per = v[i] / ctas if per_cta else v[i] / blocks
+        print(f"  issuer   {names[i]:26s} {per:9.0f} cycles per {'CTA' if per_cta else 'block'}")

@@ -288,6 +288,41 @@ def test_nf4_in_mainloop_is_bit_identical(cuda):
     assert torch.equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
 
 
+def test_compact_scored_rows_is_bit_identical(cuda):
+    """Head on the loss-carrying completion tokens only (compact_scored_rows, packed layout) vs on all B*T positions like
+    the reference (distributed_actor.py:245-260 scores everything, masks afterwards): rows are independent in the final
+    norm, lm_head and log-softmax and the dropped rows have coefficient 0 -> identical loss, gradients and log-probs."""
+    from distrl_llm_b200 import _capi
+    from distrl_llm_b200.learner import GRPOLearner, IdTokenizer
+    from distrl_llm_b200.policy import Policy
+    ocfg = lo.OracleConfig(vocab=2048, hidden=256, inter=512, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=128,
+                           lora_r=16, lora_alpha=16)
+    params, nf4 = lo.make_params(ocfg, seed=2)
+    P, T, B = 24, 72, 4
+    prompts, answers, rewards = lo.make_batch(ocfg, 8, P, T, seed=4, ragged=True, group_size=4, learner="grpo")
+    out = []
+    try:
+        _capi.lib().b200rl_gemm_set_tail_split(0)      # the row count changes the tile count; keep the K order equal
+        for compact in (True, False):
+            pol = Policy.from_params(_mk_cfg(ocfg), params, nf4, cuda, max_batch=B, P=P, T=T)
+            ln = GRPOLearner(pol, IdTokenizer(), {"train_batch_size": B, "max_new_tokens": T, "max_prompt_tokens": P, "lr": 1e-5,
+                                                  "compact_scored_rows": compact})
+            assert ln.share_prompts
+            pk = ln._pack(*ln._encode(prompts[:B], answers[:B])[:2])
+            n_live = int(pk.answer_mask.sum().item())
+            assert pk.n_score == (n_live if compact else B * T) and 0 < n_live < B * T
+            lp, mask = ln.compute_current_policy_probs(pol, prompts[:B], answers[:B])
+            ln._compute_gradients(prompts, answers, list(rewards), export=False)
+            out.append((pol.lora_grad.clone(), float(pol.loss_accum.item()), lp.clone(), mask.clone()))
+    finally:
+        _capi.lib().b200rl_gemm_set_tail_split(1)
+    assert out[0][0].abs().max() > 0
+    assert torch.equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+    live = out[0][3] != 0
+    assert torch.equal(out[0][3], out[1][3]) and torch.equal(out[0][2][live], out[1][2][live])
+    assert (out[0][2][~live] == 0).all()               # positions left out report 0
+
+
 def test_swiglu_fusion_is_bit_identical(cuda):
     """b200rl_model_set_fusion: SwiGLU inside the GEMM epilogues vs separate row kernels -> identical gradients."""
     from distrl_llm_b200 import _capi

@@ -114,9 +114,10 @@ def test_two_rank_gradient_mean_and_step_matches_reference_golden():
 # ---------------------------------------------------------------------------------------------------
 # packed shared-prompt / ragged layout bookkeeping (distrl_llm_b200/packing.py) — pure integer logic
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("compact", [True, False])
 @pytest.mark.parametrize("ragged", [True, False])
 @pytest.mark.parametrize("seed", [0, 1, 2])
-def test_packing_descriptors_are_consistent(ragged, seed):
+def test_packing_descriptors_are_consistent(ragged, seed, compact):
     from distrl_llm_b200 import packing
     rng = np.random.default_rng(seed)
     P, T, groups, per = 150, 300, 3, 4
@@ -131,9 +132,16 @@ def test_packing_descriptors_are_consistent(ragged, seed):
             ids[i, P - plen:P], am[i, P - plen:P] = pr, 1
             n = int(rng.integers(0, T + 1)) if (i % 5) else 0          # some empty completions
             ids[i, P:P + n], am[i, P:P + n] = rng.integers(1, 5000, size=n), 1
-    h = packing.pack_microbatch(ids, am, P, T, ragged=ragged)
+    h = packing.pack_microbatch(ids, am, P, T, ragged=ragged, compact_scored=compact)
     a = h.arrays
     assert h.n_groups == groups
+    # scored rows: every (sequence, t) position, or only those that carry loss (score_slot = their i*T+t, ascending)
+    slot = a["score_slot"] if a["score_slot"].size else np.arange(B * T)
+    assert compact or a["score_slot"].size == 0
+    assert a["score_src"].size == slot.size and a["targets"].size == slot.size
+    if compact and a["score_slot"].size:
+        assert np.array_equal(slot, np.flatnonzero(a["answer_mask"])) or (a["answer_mask"].sum() == 0 and slot.tolist() == [0])
+    row_of_slot = {int(sl): k for k, sl in enumerate(slot)}
     real = int(am[:, P:].sum() + sum(am[g * per, :P].sum() for g in range(groups)))
     assert h.rows == (max(real, 1) if ragged else groups * P + B * T)
     assert int(a["key_mask"].sum()) == real
@@ -148,9 +156,10 @@ def test_packing_descriptors_are_consistent(ragged, seed):
         # scored positions: the logit at padded position P-1+t predicts completion token t (reference :245-249)
         for t in range(T):
             if a["answer_mask"][i * T + t]:
-                src = int(a["score_src"][i * T + t])
+                k = row_of_slot[i * T + t]
+                src = int(a["score_src"][k])
                 assert a["pos"][src] == P - 1 + t
-                assert a["targets"][i * T + t] == ids[i, P + t]
+                assert a["targets"][k] == ids[i, P + t]
                 assert (r0 <= src < r0 + n) if t == 0 else (c0 <= src < c0 + cn)
     assert np.array_equal(a["answer_mask"].reshape(B, T) != 0, (am[:, P:] != 0) & (am[:, :P].sum(1, keepdims=True) > 0))
     # scatter CSR = inverse of score_src over the live positions
@@ -159,7 +168,7 @@ def test_packing_descriptors_are_consistent(ragged, seed):
         for k in a["sc_list"][a["sc_start"][r]:a["sc_start"][r + 1]]:
             assert a["score_src"][k] == r
             live.append(int(k))
-    assert len(live) == len(set(live)) and set(np.flatnonzero(a["answer_mask"])) <= set(live)
+    assert len(live) == len(set(live)) and set(np.flatnonzero(a["answer_mask"])) <= set(int(slot[k]) for k in live)
     # query blocks tile every stored row exactly once; key blocks' partial slabs are each reduced into exactly one row
     qb = a["qblocks"].reshape(-1, packing.QB_FIELDS)
     cover = np.zeros(h.rows + 128, np.int32)
