@@ -50,6 +50,16 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo,
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same descriptor split into its halves so that an issuing thread builds it once per tile and only ADDS a byte
+// offset per MMA (the address field holds addr >> 4 in bits 0-13; shared memory is < 256 KB, so no carry leaves it):
+// one thread issues every MMA of a role and each instruction it spends per MMA is serial latency (profiles/r2_run11).
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t addr, uint32_t lbo) {
+  return ((addr & 0x3FFFFu) >> 4) | (((lbo >> 4) & 0x3FFFu) << 16);
+}
+constexpr uint32_t DESC_HI_SBO1024 = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t desc_at(uint32_t lo, uint32_t byte_off) {
+  return ((uint64_t)DESC_HI_SBO1024 << 32) | (uint64_t)(lo + (byte_off >> 4));
+}
 constexpr uint32_t idesc_n(int n, bool b_mn) {  // M = 128, A K-major
   return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(128 >> 4) << 24);
@@ -73,6 +83,8 @@ __device__ __forceinline__ void store_row32_sw128(uint32_t tile, int r, int col0
 
 struct AttnParams {
   const int* key_mask;   // [rows] 1 = real token
+  const bf16* qkv;       // bwd (dQ): [rows, (nq+2nkv)*HD], read directly for the Q rows that go to TMEM
+  const bf16* dout;      // bwd (dQ): [rows, nq*HD]
   bf16* out;             // fwd: [rows, nq*HD]
   float* lse2;           // fwd out / bwd in
   const float* delta;    // bwd in
@@ -471,20 +483,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 // ---------------------------------------------------------------------------------------------------
 // dQ
 // ---------------------------------------------------------------------------------------------------
+// dQ: every MMA takes its A operand from TENSOR MEMORY (tcgen05.mma [d], [a], b-desc).  Q and dO of the query block
+// are written there once (tcgen05.st), and dS_j is written back over the S_j accumulator it was computed from, so
+// shared memory only carries the K / V stream (profiles/r2_run14: with all operands in shared memory the 128 B/clk
+// shared-memory port, not the tensor pipe, was the floor: 176 KB per 64-key block).
+constexpr int DQ_KV_STAGES = 4;
 template <bool PROF>
 __global__ void __launch_bounds__(384, 1)
-attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_do128,
-                      const __grid_constant__ CUtensorMap tm_kv64, const AttnParams p) {
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_kv64, const AttnParams p) {
   constexpr bool prof_on = PROF;
   const long long t_start = prof_on ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t qdo_full, kv_full[3], kv_empty[3], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], dq_full;
+  __shared__ uint64_t qdo_full, kv_full[DQ_KV_STAGES], kv_empty[DQ_KV_STAGES], sp_full[2], ds_full[2], ds_empty[2], dq_full;
   __shared__ uint32_t tmem_base_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // [Q 32K][dO 32K][3 x (K 16K, V 16K)][dS0 16K][dS1 16K]  = 192 KB
-  const uint32_t sQ = smem_base, sdO = sQ + TILE_BYTES, sKV = sdO + TILE_BYTES, sDS = sKV + 6 * HALF_TILE;
+  // [DQ_KV_STAGES x (K 16K, V 16K)]
+  const uint32_t sKV = smem_base;
   const QBlock d = p.qblocks ? p.qblocks[blockIdx.x] : classic_qblock(p);
   const int h = blockIdx.y;
   const int g = h / (p.nq / p.nkv);
@@ -492,15 +508,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
   const int n_kb = kit.n_tot;
 
   if (threadIdx.x == 0) {
-    mbar_init(&qdo_full, 1);
+    mbar_init(&qdo_full, 256);
     mbar_init(&dq_full, 1);
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < DQ_KV_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&sp_full[s], 1);
-      mbar_init(&sp_empty[s], 256);
+      mbar_init(&sp_full[s], 2);
       mbar_init(&ds_full[s], 256);
       mbar_init(&ds_empty[s], 1);
     }
@@ -515,22 +530,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   pdl_enter();
-  // TMEM columns: S0 [0,64) S1 [64,128) dP0 [128,192) dP1 [192,256) dQ [256,384)
+  // TMEM columns: S0 [0,64) S1 [64,128) dP0 [128,192) dP1 [192,256) dQ [256,384) Q [384,448) dO [448,512)
+  // (Q / dO: bf16 pairs, column j = d 2j, 2j+1).  dS_j (bf16 pairs) overwrites S_j: keys 32c..32c+31 -> columns [32c, 32c+16)
+  constexpr uint32_t COL_DP = 128, COL_DQ = 256, COL_Q = 384, COL_DO = 448;
 
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
-    mbar_arrive_expect_tx(&qdo_full, 2 * TILE_BYTES);
-    tma_load_rows(smem_gen, &tm_q128, &qdo_full, h * HD, d.q_row0);
-    tma_load_rows(smem_gen + TILE_BYTES / 2, &tm_q128, &qdo_full, h * HD + 64, d.q_row0);
-    tma_load_rows(smem_gen + TILE_BYTES, &tm_do128, &qdo_full, h * HD, d.q_row0);
-    tma_load_rows(smem_gen + TILE_BYTES + TILE_BYTES / 2, &tm_do128, &qdo_full, h * HD + 64, d.q_row0);
+    // ===================== TMA producer: K_j / V_j =====================
     const int kcol = (p.nq + g) * HD, vcol = (p.nq + p.nkv + g) * HD;
     for (int j = 0; j < n_kb; ++j) {
-      const int st = j % 3;
+      const int st = j % DQ_KV_STAGES;
       int row0, valid, local0;
       kit.get(d, j, row0, valid, local0);
-      mbar_wait(&kv_empty[st], ((j / 3) & 1) ^ 1u);
-      uint8_t* kd = smem_gen + 2 * TILE_BYTES + st * 2 * HALF_TILE;
+      mbar_wait(&kv_empty[st], ((j / DQ_KV_STAGES) & 1) ^ 1u);
+      uint8_t* kd = smem_gen + st * 2 * HALF_TILE;
       uint8_t* vd = kd + HALF_TILE;
       mbar_arrive_expect_tx(&kv_full[st], 2 * HALF_TILE);
       tma_load_rows(kd, &tm_kv64, &kv_full[st], kcol, row0);
@@ -538,68 +550,61 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
       tma_load_rows(vd, &tm_kv64, &kv_full[st], vcol, row0);
       tma_load_rows(vd + HALF_TILE / 2, &tm_kv64, &kv_full[st], vcol + 64, row0);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer 1: S_j = Q.K_j^T and dP_j = dO.V_j^T =====================
-    // Two issuing threads on two SM sub-partitions (profiles/r2_run11: one thread needs ~90 cycles per tcgen05.mma
-    // while N = 64 MMAs execute in 48, so a single issuer, not the tensor pipe, paced the kernel).  The tensor pipe
-    // runs the MMAs in arrival order; the order that matters is carried by the mbarriers as before.
-    constexpr uint32_t id_s = idesc_n(64, false);    // [128 q] x [64 keys], both K-major over d
+  } else if ((warp == 1 || warp == 2) && lane == 0) {
+    // ===================== MMA issuers 1 / 2: S_j = Q.K_j^T (warp 1), dP_j = dO.V_j^T (warp 2) =====================
+    // Three issuing threads on three SM sub-partitions (profiles/r2_run11, r2_run17: one thread needs 80-100 cycles per
+    // tcgen05.mma while an N = 64 MMA executes in < 50, so the issuer, not the tensor pipe, paced the kernel).  The
+    // tensor pipe runs the MMAs in arrival order; the order that matters is carried by the mbarriers.
+    constexpr uint32_t id_s = idesc_n(64, false);    // [128 q] x [64 keys], B K-major over d
+    const bool is_dp = warp == 2;
+    const uint32_t a_col = tmem_base + (is_dp ? COL_DO : COL_Q);
+    const uint32_t d_col = tmem_base + (is_dp ? COL_DP : 0u);
     mbar_wait(&qdo_full, 0);
+    tc_fence_after();
     long long m_k = 0, m_s = 0;
     const long long m_t0 = prof_on ? clock64() : 0;
     for (int j = 0; j < n_kb; ++j) {
-      const int st = j & 1, k3 = j % 3;
+      const int st = j & 1, k3 = j % DQ_KV_STAGES;
       PROF_T(b0);
-      mbar_wait(&kv_full[k3], (j / 3) & 1);
+      mbar_wait(&kv_full[k3], (j / DQ_KV_STAGES) & 1);
       PROF_T(b1);
-      mbar_wait(&sp_empty[st], ((j >> 1) & 1) ^ 1u);
+      mbar_wait(&ds_empty[st], ((j >> 1) & 1) ^ 1u);   // dQ_{j-2} has consumed dS_{j-2}, which lives in S stage st
       if (prof_on) { m_k += b1 - b0; m_s += clock64() - b1; }
       tc_fence_after();
-      const uint32_t kt = sKV + k3 * 2 * HALF_TILE, vt = kt + HALF_TILE;
+      const uint32_t b_lo = desc_lo_sw128(sKV + k3 * 2 * HALF_TILE + (is_dp ? HALF_TILE : 0), 16);
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {  // d = 128 = 8 x K16, two d-halves
-        const uint32_t aoff = (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32;
         const uint32_t boff = (kk >> 2) * (HALF_TILE / 2) + (kk & 3) * 32;
-        umma_bf16(tmem_base + st * 64, smem_desc_sw128(sQ + aoff, 16, 1024), smem_desc_sw128(kt + boff, 16, 1024),
-                  id_s, kk > 0 ? 1u : 0u);
+        umma_bf16_ts(d_col + st * 64, a_col + kk * 8, desc_at(b_lo, boff), id_s, kk > 0 ? 1u : 0u);
       }
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t aoff = (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32;
-        const uint32_t boff = (kk >> 2) * (HALF_TILE / 2) + (kk & 3) * 32;
-        umma_bf16(tmem_base + 128 + st * 64, smem_desc_sw128(sdO + aoff, 16, 1024),
-                  smem_desc_sw128(vt + boff, 16, 1024), id_s, kk > 0 ? 1u : 0u);
-      }
-      umma_commit(&sp_full[st]);
+      umma_commit(&sp_full[st]);   // count 2: S_j and dP_j
     }
-    if (prof_on) {
+    if (prof_on && !is_dp) {
       atomicAdd(p.prof + PROF_M_KFULL, (unsigned long long)m_k);
       atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
       atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
     }
   } else if (warp == 3 && lane == 0) {
-    // ===================== MMA issuer 2: dQ += dS_j.K_j =====================
+    // ===================== MMA issuer 3: dQ += dS_j.K_j =====================
     constexpr uint32_t id_dq = idesc_n(128, true);   // [128 q] x [128 d], B = K_j MN-major (k = keys)
     long long m_d = 0;
     const long long m_t0 = prof_on ? clock64() : 0;
     for (int j = 0; j < n_kb; ++j) {
-      const int st = j & 1, k3 = j % 3;
+      const int st = j & 1, k3 = j % DQ_KV_STAGES;
       PROF_T(a0);
-      mbar_wait(&kv_full[k3], (j / 3) & 1);  // K_j landed (long ago: dS_j was computed from it); orders this thread's reads
+      mbar_wait(&kv_full[k3], (j / DQ_KV_STAGES) & 1);  // K_j landed (long ago: dS_j was computed from it); orders this thread's reads
       mbar_wait(&ds_full[st], (j >> 1) & 1);
       if (prof_on) m_d += clock64() - a0;
       tc_fence_after();
-      const uint32_t kt = sKV + k3 * 2 * HALF_TILE;
-      const uint32_t ds = sDS + st * HALF_TILE;
+      const uint32_t b_lo = desc_lo_sw128(sKV + k3 * 2 * HALF_TILE, HALF_TILE / 2);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {  // 64 keys = 4 x K16
-        const uint64_t da = smem_desc_sw128(ds + kk * 32, 16, 1024);
-        const uint64_t db = smem_desc_sw128(kt + kk * 2048, HALF_TILE / 2, 1024);
-        umma_bf16(tmem_base + 256, da, db, id_dq, (j > 0 || kk > 0) ? 1u : 0u);
+      for (int kk = 0; kk < 4; ++kk) {  // 64 keys = 4 x K16; keys 32c.. sit at columns 32c.. of the S stage
+        const uint32_t a_col = st * 64 + (kk >> 1) * 32 + (kk & 1) * 8;
+        umma_bf16_ts(tmem_base + COL_DQ, tmem_base + a_col, desc_at(b_lo, kk * 2048), id_dq, (j > 0 || kk > 0) ? 1u : 0u);
       }
-      // S_j / dP_j (issuer 1) completed before dS_j existed, so K_j / V_j have no reader left once dQ_j is done
+      // S_j / dP_j completed before dS_j existed, so K_j / V_j have no reader left once dQ_j is done
       umma_commit(&kv_empty[k3]);
-      umma_commit(&ds_empty[st]);
+      umma_commit(&ds_empty[st]);   // count 1; both S / dP issuers wait on it
     }
     umma_commit(&dq_full);
     if (prof_on) {
@@ -611,10 +616,28 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
     const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    const int t = threadIdx.x - 128;
     const int ql = d.q_local0 + r;
     const bool q_ok = r < d.q_rows;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    // ---- this thread's row of Q (warpgroup 0) / dO (warpgroup 1) -> TMEM, once per CTA ----
+    {
+      const bf16* src = wg == 0 ? p.qkv + (long long)(d.q_row0 + (q_ok ? r : 0)) * (long long)(p.nq + 2 * p.nkv) * HD + h * HD
+                                : p.dout + (long long)(d.q_row0 + (q_ok ? r : 0)) * (long long)p.nq * HD + h * HD;
+      const uint32_t col0 = wg == 0 ? COL_Q : COL_DO;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint4 x = q_ok ? __ldg(reinterpret_cast<const uint4*>(src + half * 64) + u) : make_uint4(0u, 0u, 0u, 0u);
+          v[4 * u] = x.x; v[4 * u + 1] = x.y; v[4 * u + 2] = x.z; v[4 * u + 3] = x.w;
+        }
+        tmem_st_32x32(tmem_base + col0 + half * 32 + lane_addr, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&qdo_full);
+    }
     const long long sidx = (long long)d.stat0 + (long long)h * p.stat_h + r;
     const float lse = q_ok ? p.lse2[sidx] : INFINITY;
     const float del = q_ok ? p.delta[sidx] : 0.f;
@@ -629,7 +652,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
       mk = (k0 < valid) ? p.key_mask[row0 + k0] : 0;
     };
     if (n_kb > 0) fetch_mask(0);
-    long long c_sw = 0, c_dw = 0, c_ld = 0, c_ma = 0, c_fa = 0, c_mk = 0;
+    long long c_sw = 0, c_ld = 0, c_ma = 0, c_fa = 0, c_mk = 0;
     const long long t_loop0 = prof_on ? clock64() : 0;
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
@@ -645,18 +668,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
       PROF_T(e1);
       mbar_wait(&sp_full[st], (j >> 1) & 1);
       PROF_T(e2);
-      mbar_wait(&ds_empty[st], ((j >> 1) & 1) ^ 1u);  // dQ MMA of block j-2 finished reading dS[st]
-      PROF_T(e3);
       tc_fence_after();
       {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tmem_base + st * 64 + lane_addr + c * 32, sv);
-        tmem_ld_32x32(tmem_base + 128 + st * 64 + lane_addr + c * 32, dv);
+        tmem_ld_32x32(tmem_base + COL_DP + st * 64 + lane_addr + c * 32, dv);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&sp_empty[st]);
         PROF_T(e4);
-        c_mk += e1 - e0; c_sw += e2 - e1; c_dw += e3 - e2; c_ld += e4 - e3;
+        c_mk += e1 - e0; c_sw += e2 - e1; c_ld += e4 - e2;
         float f[32];
         if (plain) {
 #pragma unroll
@@ -672,11 +691,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
             f[i] = p.scale * pr * (__uint_as_float(dv[i]) - del);
           }
         }
-        store_row32_sw128(sDS + st * HALF_TILE, r, c * 32, f);
+        // dS (bf16 pairs) back into the columns this thread just read S from: A operand of dQ += dS.K
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+        tmem_st_32x16(tmem_base + st * 64 + lane_addr + c * 32, pk);
         if (prof_on) c_ma += clock64() - e4;
       }
       PROF_T(e5);
-      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(&ds_full[st]);
       if (prof_on) c_fa += clock64() - e5;
     }
@@ -690,7 +714,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
 #pragma unroll
       for (int c = 2 * wg; c < 2 * wg + 2; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + 256 + lane_addr + c * 32, v);
+        tmem_ld_32x32(tmem_base + COL_DQ + lane_addr + c * 32, v);
         tmem_ld_wait();
         if (q_ok) {
 #pragma unroll
@@ -707,7 +731,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
       atomicAdd(p.prof + PROF_S_WAIT, (unsigned long long)c_sw);
       atomicAdd(p.prof + PROF_S_LD, (unsigned long long)c_ld);
       atomicAdd(p.prof + PROF_MAX_XCHG, (unsigned long long)c_mk);
-      atomicAdd(p.prof + PROF_ABSORB_WAIT, (unsigned long long)c_dw);
       atomicAdd(p.prof + PROF_EXP_STORE, (unsigned long long)c_ma);
       atomicAdd(p.prof + PROF_FENCE_ARRIVE, (unsigned long long)c_fa);
       atomicAdd(p.prof + PROF_LOOP, (unsigned long long)(t_loop1 - t_loop0));
@@ -730,6 +753,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
 // ---------------------------------------------------------------------------------------------------
 // dK, dV
 // ---------------------------------------------------------------------------------------------------
+// dK / dV: P^T_j and dS^T_j never touch shared memory — they are written (bf16 pairs, tcgen05.st) over the S^T_j / dP^T_j
+// accumulators they were computed from and feed dV += P^T.dO, dK += dS^T.Q as TMEM A operands.
+constexpr int DKV_QD_STAGES = 4;
 template <bool PROF>
 __global__ void __launch_bounds__(384, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_constant__ CUtensorMap tm_q64,
@@ -737,14 +763,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
   constexpr bool prof_on = PROF;
   const long long t_start = prof_on ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t kv_full, qd_full[3], qd_empty[3], sp_full[2], sp_empty[2], ds_full[2], ds_empty[2], out_full;
+  __shared__ uint64_t kv_full, qd_full[DKV_QD_STAGES], qd_empty[DKV_QD_STAGES], sp_full[2], ds_full[2], ds_empty[2], out_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_lse[2][64], s_del[2][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // [K 32K][V 32K][3 x (Q 16K, dO 16K)][PT0 16K][dST0 16K][PT1 16K][dST1 16K] = 224 KB
-  const uint32_t sK = smem_base, sV = sK + TILE_BYTES, sQD = sV + TILE_BYTES, sPD = sQD + 6 * HALF_TILE;
+  // [K 32K][V 32K][DKV_QD_STAGES x (Q 16K, dO 16K)] = 192 KB
+  const uint32_t sK = smem_base, sV = sK + TILE_BYTES, sQD = sV + TILE_BYTES;
   KBlock d;
   if (p.kblocks) {
     d = p.kblocks[blockIdx.x];
@@ -768,13 +794,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
   if (threadIdx.x == 0) {
     mbar_init(&kv_full, 1);
     mbar_init(&out_full, 1);
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < DKV_QD_STAGES; ++s) {
       mbar_init(&qd_full[s], 1);
       mbar_init(&qd_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&sp_full[s], 1);
-      mbar_init(&sp_empty[s], 256);
+      mbar_init(&sp_full[s], 2);
       mbar_init(&ds_full[s], 256);
       mbar_init(&ds_empty[s], 1);
     }
@@ -790,6 +815,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
   const uint32_t tmem_base = tmem_base_smem;
   pdl_enter();
   // TMEM columns: S^T0 [0,64) S^T1 [64,128) dP^T0 [128,192) dP^T1 [192,256) dK [256,384) dV [384,512)
+  // P^T_j / dS^T_j (bf16 pairs) overwrite S^T_j / dP^T_j: queries 32c..32c+31 -> columns [32c, 32c+16) of the stage
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -800,10 +826,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
     tma_load_rows(smem_gen + TILE_BYTES, &tm_kv128, &kv_full, vcol, d.k_row0);
     tma_load_rows(smem_gen + TILE_BYTES + TILE_BYTES / 2, &tm_kv128, &kv_full, vcol + 64, d.k_row0);
     for (int it = 0; it < n_it; ++it) {
-      const int st = it % 3;
+      const int st = it % DKV_QD_STAGES;
       const int h = g * group + it / nqb;
       const int qrow = d.q_row0 + (qb0 + it % nqb) * 64;
-      mbar_wait(&qd_empty[st], ((it / 3) & 1) ^ 1u);
+      mbar_wait(&qd_empty[st], ((it / DKV_QD_STAGES) & 1) ^ 1u);
       uint8_t* qd = smem_gen + 2 * TILE_BYTES + st * 2 * HALF_TILE;
       uint8_t* dd = qd + HALF_TILE;
       mbar_arrive_expect_tx(&qd_full[st], 2 * HALF_TILE);
@@ -812,65 +838,60 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       tma_load_rows(dd, &tm_do64, &qd_full[st], h * HD, qrow);
       tma_load_rows(dd + HALF_TILE / 2, &tm_do64, &qd_full[st], h * HD + 64, qrow);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer 1: S^T = K.Q^T and dP^T = V.dO^T (see the dQ kernel: two issuing threads) ==========
+  } else if ((warp == 1 || warp == 2) && lane == 0) {
+    // ===================== MMA issuers 1 / 2: S^T = K.Q^T (warp 1), dP^T = V.dO^T (warp 2); see the dQ kernel ==========
     constexpr uint32_t id_s = idesc_n(64, false);    // [128 keys] x [64 queries], K-major over d
+    const bool is_dp = warp == 2;
+    const uint32_t a_lo = desc_lo_sw128(is_dp ? sV : sK, 16);
+    const uint32_t d_col = tmem_base + (is_dp ? 128u : 0u);
     mbar_wait(&kv_full, 0);
     long long m_k = 0, m_s = 0;
     const long long m_t0 = prof_on ? clock64() : 0;
     for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1, q3 = it % 3;
+      const int st = it & 1, q3 = it % DKV_QD_STAGES;
       PROF_T(b0);
-      mbar_wait(&qd_full[q3], (it / 3) & 1);
+      mbar_wait(&qd_full[q3], (it / DKV_QD_STAGES) & 1);
       PROF_T(b1);
-      mbar_wait(&sp_empty[st], ((it >> 1) & 1) ^ 1u);
+      mbar_wait(&ds_empty[st], ((it >> 1) & 1) ^ 1u);   // the gradient MMAs of block it-2 have consumed P^T / dS^T of this stage
       if (prof_on) { m_k += b1 - b0; m_s += clock64() - b1; }
       tc_fence_after();
-      const uint32_t qt = sQD + q3 * 2 * HALF_TILE, dt = qt + HALF_TILE;
+      const uint32_t b_lo = desc_lo_sw128(sQD + q3 * 2 * HALF_TILE + (is_dp ? HALF_TILE : 0), 16);
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         const uint32_t aoff = (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32;
         const uint32_t boff = (kk >> 2) * (HALF_TILE / 2) + (kk & 3) * 32;
-        umma_bf16(tmem_base + st * 64, smem_desc_sw128(sK + aoff, 16, 1024), smem_desc_sw128(qt + boff, 16, 1024),
-                  id_s, kk > 0 ? 1u : 0u);
+        umma_bf16(d_col + st * 64, desc_at(a_lo, aoff), desc_at(b_lo, boff), id_s, kk > 0 ? 1u : 0u);
       }
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t aoff = (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32;
-        const uint32_t boff = (kk >> 2) * (HALF_TILE / 2) + (kk & 3) * 32;
-        umma_bf16(tmem_base + 128 + st * 64, smem_desc_sw128(sV + aoff, 16, 1024),
-                  smem_desc_sw128(dt + boff, 16, 1024), id_s, kk > 0 ? 1u : 0u);
-      }
-      umma_commit(&sp_full[st]);
+      umma_commit(&sp_full[st]);   // count 2: S^T and dP^T
     }
-    if (prof_on) {
+    if (prof_on && !is_dp) {
       atomicAdd(p.prof + PROF_M_KFULL, (unsigned long long)m_k);
       atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
       atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
     }
   } else if (warp == 3 && lane == 0) {
-    // ===================== MMA issuer 2: dV += P^T.dO and dK += dS^T.Q =====================
+    // ===================== MMA issuer 3: dV += P^T.dO and dK += dS^T.Q =====================
     constexpr uint32_t id_g = idesc_n(128, true);    // [128 keys] x [128 d], B = dO / Q MN-major (k = queries)
     long long m_d = 0;
     const long long m_t0 = prof_on ? clock64() : 0;
     for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1, q3 = it % 3;
+      const int st = it & 1, q3 = it % DKV_QD_STAGES;
       PROF_T(a0);
-      mbar_wait(&qd_full[q3], (it / 3) & 1);  // landed long ago (P^T was computed from it); orders this thread's reads
+      mbar_wait(&qd_full[q3], (it / DKV_QD_STAGES) & 1);  // landed long ago (P^T was computed from it); orders this thread's reads
       mbar_wait(&ds_full[st], (it >> 1) & 1);
       if (prof_on) m_d += clock64() - a0;
       tc_fence_after();
-      const uint32_t qt = sQD + q3 * 2 * HALF_TILE, dt = qt + HALF_TILE;
-      const uint32_t pt = sPD + st * 2 * HALF_TILE, dst = pt + HALF_TILE;
+      const uint32_t q_lo = desc_lo_sw128(sQD + q3 * 2 * HALF_TILE, HALF_TILE / 2);
+      const uint32_t d_lo = desc_lo_sw128(sQD + q3 * 2 * HALF_TILE + HALF_TILE, HALF_TILE / 2);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {  // 64 queries = 4 x K16
-        umma_bf16(tmem_base + 384, smem_desc_sw128(pt + kk * 32, 16, 1024),
-                  smem_desc_sw128(dt + kk * 2048, HALF_TILE / 2, 1024), id_g, (it > 0 || kk > 0) ? 1u : 0u);
+      for (int kk = 0; kk < 4; ++kk) {  // 64 queries = 4 x K16; queries 32c.. sit at columns 32c.. of the stage
+        const uint32_t a_col = st * 64 + (kk >> 1) * 32 + (kk & 1) * 8;
+        umma_bf16_ts(tmem_base + 384, tmem_base + a_col, desc_at(d_lo, kk * 2048), id_g, (it > 0 || kk > 0) ? 1u : 0u);
       }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        umma_bf16(tmem_base + 256, smem_desc_sw128(dst + kk * 32, 16, 1024),
-                  smem_desc_sw128(qt + kk * 2048, HALF_TILE / 2, 1024), id_g, (it > 0 || kk > 0) ? 1u : 0u);
+        const uint32_t a_col = 128 + st * 64 + (kk >> 1) * 32 + (kk & 1) * 8;
+        umma_bf16_ts(tmem_base + 256, tmem_base + a_col, desc_at(q_lo, kk * 2048), id_g, (it > 0 || kk > 0) ? 1u : 0u);
       }
       umma_commit(&qd_empty[q3]);
       umma_commit(&ds_empty[st]);
@@ -903,7 +924,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       }
     };
     if (n_it > 0) fetch_stats(0);
-    long long c_sw = 0, c_dw = 0, c_ld = 0, c_ma = 0, c_fa = 0, c_mk = 0;
+    long long c_sw = 0, c_ld = 0, c_ma = 0, c_fa = 0, c_mk = 0;
     const long long t_loop0 = prof_on ? clock64() : 0;
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
@@ -921,20 +942,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       PROF_T(e1);
       mbar_wait(&sp_full[st], (it >> 1) & 1);
       PROF_T(e2);
-      mbar_wait(&ds_empty[st], ((it >> 1) & 1) ^ 1u);
-      PROF_T(e3);
       tc_fence_after();
-      const uint32_t pt = sPD + st * 2 * HALF_TILE, dst = pt + HALF_TILE;
       {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tmem_base + st * 64 + lane_addr + c * 32, sv);
         tmem_ld_32x32(tmem_base + 128 + st * 64 + lane_addr + c * 32, dv);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&sp_empty[st]);
         PROF_T(e4);
-        c_mk += e1 - e0; c_sw += e2 - e1; c_dw += e3 - e2; c_ld += e4 - e3;
-        float fp[32], fs[32];
+        c_mk += e1 - e0; c_sw += e2 - e1; c_ld += e4 - e2;
+        uint32_t pk_p[16], pk_s[16];
         const float4* l4 = reinterpret_cast<const float4*>(&s_lse[st][c * 32]);
         const float4* d4 = reinterpret_cast<const float4*>(&s_del[st][c * 32]);
 #pragma unroll
@@ -942,20 +958,28 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
           const float4 lv = l4[v4], dl = d4[v4];
           const float ls[4] = {lv.x, lv.y, lv.z, lv.w}, ds4[4] = {dl.x, dl.y, dl.z, dl.w};
 #pragma unroll
+          float fp[4], fs[4];
+#pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = v4 * 4 + u;
             float pr = ex2_approx(__uint_as_float(sv[i]) * p.scale_log2 - ls[u]);
             if (!key_ok || (need_cmp && kl > qc0 + i)) pr = 0.f;  // select, never 0 * inf
-            fp[i] = pr;
-            fs[i] = p.scale * pr * (__uint_as_float(dv[i]) - ds4[u]);
+            fp[u] = pr;
+            fs[u] = p.scale * pr * (__uint_as_float(dv[i]) - ds4[u]);
           }
+          pk_p[2 * v4] = pack_bf16x2(fp[0], fp[1]);
+          pk_p[2 * v4 + 1] = pack_bf16x2(fp[2], fp[3]);
+          pk_s[2 * v4] = pack_bf16x2(fs[0], fs[1]);
+          pk_s[2 * v4 + 1] = pack_bf16x2(fs[2], fs[3]);
         }
-        store_row32_sw128(pt, r, c * 32, fp);
-        store_row32_sw128(dst, r, c * 32, fs);
+        // P^T / dS^T back into the columns this thread just read: A operands of dV += P^T.dO and dK += dS^T.Q
+        tmem_st_32x16(tmem_base + st * 64 + lane_addr + c * 32, pk_p);
+        tmem_st_32x16(tmem_base + 128 + st * 64 + lane_addr + c * 32, pk_s);
         if (prof_on) c_ma += clock64() - e4;
       }
       PROF_T(e5);
-      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(&ds_full[st]);
       if (prof_on) c_fa += clock64() - e5;
     }
@@ -993,7 +1017,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       atomicAdd(p.prof + PROF_S_WAIT, (unsigned long long)c_sw);
       atomicAdd(p.prof + PROF_S_LD, (unsigned long long)c_ld);
       atomicAdd(p.prof + PROF_MAX_XCHG, (unsigned long long)c_mk);
-      atomicAdd(p.prof + PROF_ABSORB_WAIT, (unsigned long long)c_dw);
       atomicAdd(p.prof + PROF_EXP_STORE, (unsigned long long)c_ma);
       atomicAdd(p.prof + PROF_FENCE_ARRIVE, (unsigned long long)c_fa);
       atomicAdd(p.prof + PROF_LOOP, (unsigned long long)(t_loop1 - t_loop0));
@@ -1066,8 +1089,8 @@ int make_rows_map(CUtensorMap* tm, const void* base, long long rows, long long c
 }
 
 constexpr int SMEM_FWD = 6 * TILE_BYTES + 1024;
-constexpr int SMEM_DQ = 2 * TILE_BYTES + 8 * HALF_TILE + 1024;
-constexpr int SMEM_DKV = 2 * TILE_BYTES + 10 * HALF_TILE + 1024;
+constexpr int SMEM_DQ = DQ_KV_STAGES * 2 * HALF_TILE + 1024;
+constexpr int SMEM_DKV = 2 * TILE_BYTES + DKV_QD_STAGES * 2 * HALF_TILE + 1024;
 
 int set_attrs() {
   static DeviceOnce once;   // kernel attributes are per device
@@ -1137,12 +1160,14 @@ int attn_bwd_tc_launch(const void* qkv, const int* key_mask, const void* dout, c
   AttnParams p = base_params(key_mask, nq, nkv, scale);
   p.lse2 = const_cast<float*>(lse);
   p.delta = delta;
+  p.qkv = (const bf16*)qkv;
+  p.dout = (const bf16*)dout;
   p.dqkv = (bf16*)dqkv;
   p.L = L;
   p.stat_h = L;
   {
     dim3 grid((L + BQ - 1) / BQ, nq, B);
-    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 1 ? attn_bwd_dq_tc_kernel<true> : attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DQ, stream, m.q128, m.d128, m.q64, p));
+    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 1 ? attn_bwd_dq_tc_kernel<true> : attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DQ, stream, m.q64, p));
     B200RL_LAUNCH_OK();
   }
   {
@@ -1181,6 +1206,8 @@ int attn_bwd_seg_launch(const void* qkv, const int* key_mask, const void* dout, 
   AttnParams p = base_params(key_mask, nq, nkv, scale);
   p.lse2 = const_cast<float*>(lse);
   p.delta = delta;
+  p.qkv = (const bf16*)qkv;
+  p.dout = (const bf16*)dout;
   p.dqkv = (bf16*)dqkv;
   p.kv_part = kv_part;
   p.qblocks = qblocks_dev;
@@ -1188,7 +1215,7 @@ int attn_bwd_seg_launch(const void* qkv, const int* key_mask, const void* dout, 
   p.stat_h = (int)rows;
   {
     dim3 grid(n_qblocks, nq, 1);
-    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 1 ? attn_bwd_dq_tc_kernel<true> : attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DQ, stream, m.q128, m.d128, m.q64, p));
+    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 1 ? attn_bwd_dq_tc_kernel<true> : attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DQ, stream, m.q64, p));
     B200RL_LAUNCH_OK();
   }
   {

@@ -234,7 +234,10 @@ inline int raster_group(long long a_bytes, int num_m_blocks) {
   // B stream and the C write-allocate traffic); balanced groups, never thinner than the square-ish 8
   const long long panel = a_bytes / num_m_blocks;
   const long long fit = panel > 0 ? (40ll << 20) / panel : num_m_blocks;
-  if (fit < 8) return 8;
+  // K-long operands (a 256-row A panel above ~5 MB: gate|up dX, down fwd, lm_head dX): nothing stays resident anyway, and
+  // n-fastest order (the tiles that share an A panel sit on neighbouring CTA pairs and start together) measured 10-17 %
+  // less DRAM traffic than groups of 8 on all three shapes (profiles/r2_run13_raster_sweep.txt)
+  if (fit < 8) return 1;
   const long long groups = (num_m_blocks + fit - 1) / fit;
   return (int)((num_m_blocks + groups - 1) / groups);
 }
