@@ -145,12 +145,20 @@ struct KeyIter {
 
 // PROF = true: debug instantiation with per-phase clock64 counters (scripts/prof_attn_phases.py); the production
 // instantiation carries none of it
+// Forward, built around TMEM (profiles/r2_run22: registers <- TMEM runs at 56 B/clk per SM, so every fp32 tile the softmax
+// warps read costs ~1170 cycles per 64 KB):
+//   * O stays in TMEM for the whole key loop: P_j.V_j accumulates into it (tcgen05.mma, accumulate flag); the softmax
+//     warps never read the partial products back.  The running maximum is LAZY: a row keeps its reference maximum until
+//     a block exceeds it by more than 2^8, only then O (TMEM) and l are rescaled — after the first blocks that is rare.
+//   * P_j (bf16 pairs) is written with tcgen05.st over the S_j accumulator it was computed from and is the TMEM A
+//     operand of P_j.V_j: no P tile in shared memory, no proxy fence.
+//   * two issuing threads (Q.K^T on warp 1, P.V on warp 2).
+constexpr float FWD_RESCALE_LOG2 = 8.f;
 template <bool PROF>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], o_full[2],
-      o_empty[2], p_full;
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_mx[2][2][BQ];       // [stage][warpgroup][row] partial row max
   __shared__ float s_l[2][BQ];           // [warpgroup][row] partial row sums (final combine)
@@ -160,8 +168,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   const long long t_start = prof_on ? clock64() : 0;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // [Q 32K][K0 32K][V0 32K][K1 32K][V1 32K][P 32K]
-  const uint32_t sQ = smem_base, sKV = smem_base + TILE_BYTES, sP = smem_base + 5 * TILE_BYTES;
+  // [Q 32K][K0 32K][V0 32K][K1 32K][V1 32K]
+  const uint32_t sQ = smem_base, sKV = smem_base + TILE_BYTES;
 
   const QBlock d = p.qblocks ? p.qblocks[blockIdx.x] : classic_qblock(p);
   const int h = blockIdx.y;
@@ -177,11 +185,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 256);
-      mbar_init(&o_full[s], 1);
-      mbar_init(&o_empty[s], 256);
+      mbar_init(&p_full[s], 256);
+      mbar_init(&pv_done[s], 1);
     }
-    mbar_init(&p_full, 256);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tm);
@@ -194,6 +200,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   pdl_enter();
+  // TMEM columns: S0 [0,128) S1 [128,256) O [256,384).  P_j (bf16 pairs) overwrites S_j: keys 64w..64w+63 -> columns
+  // [64w, 64w+32) of the stage (the columns warpgroup w read its scores from)
+  constexpr uint32_t COL_O = 256;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer: Q, then the K ring (a K slot is free as soon as QK_j retired) ====
@@ -225,108 +234,79 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       tma_load_rows(v_dst + TILE_BYTES / 2, &tm, &v_full[st], vcol + 64, row0);
     }
   } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer 1: S_j = Q.K_j^T =====================
     constexpr uint32_t idesc_qk = idesc_128x128(false);
-    constexpr uint32_t idesc_pv = idesc_128x128(true);
     mbar_wait(&q_full, 0);
-    long long m_k = 0, m_s = 0, m_p = 0, m_v = 0, m_o = 0;
+    const uint32_t q_lo = desc_lo_sw128(sQ, 16);
+    long long m_k = 0, m_s = 0;
     const long long m_t0 = prof_on ? clock64() : 0;
-    auto issue_pv = [&](int j) {
-      const int st = j & 1;
-      PROF_T(a0);
-      mbar_wait(&p_full, j & 1);
-      PROF_T(a1);
-      mbar_wait(&v_full[st], (j >> 1) & 1);
-      PROF_T(a2);
-      mbar_wait(&o_empty[st], ((j >> 1) & 1) ^ 1u);
-      PROF_T(a3);
-      m_p += a1 - a0; m_v += a2 - a1; m_o += a3 - a2;
-      tc_fence_after();
-      const uint32_t v = sKV + TILE_BYTES * (2 * st + 1);
-      const uint32_t tmem_o = tmem_base + 256 + st * 128;
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        // A = P: K-major over keys, two 64-key halves; B = V stored [d-half][128 keys][128 B]: MN-major,
-        // LBO = 16 KB between the two 64-wide d slabs, SBO = 1 KB between 8-key groups, 2 KB per K=16 step
-        const uint64_t da = smem_desc_sw128(sP + (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32, 16, 1024);
-        const uint64_t db = smem_desc_sw128(v + kk * 2048, TILE_BYTES / 2, 1024);
-        umma_bf16(tmem_o, da, db, idesc_pv, kk > 0 ? 1u : 0u);
-      }
-      umma_commit(&o_full[st]);
-      umma_commit(&v_empty[st]);
-    };
     for (int j = 0; j < n_kb; ++j) {
       const int st = j & 1;
       PROF_T(b0);
       mbar_wait(&k_full[st], (j >> 1) & 1);
       PROF_T(b1);
-      mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1u);
+      mbar_wait(&pv_done[st], ((j >> 1) & 1) ^ 1u);   // P_{j-2}.V_{j-2} has read P_{j-2}, which lives in S stage st
       PROF_T(b2);
       m_k += b1 - b0; m_s += b2 - b1;
       tc_fence_after();
-      const uint32_t k = sKV + TILE_BYTES * (2 * st);
-      const uint32_t tmem_s = tmem_base + st * 128;
+      const uint32_t k_lo = desc_lo_sw128(sKV + TILE_BYTES * (2 * st), 16);
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
-        const uint64_t da = smem_desc_sw128(sQ + (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32, 16, 1024);
-        const uint64_t db = smem_desc_sw128(k + (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32, 16, 1024);
-        umma_bf16(tmem_s, da, db, idesc_qk, kk > 0 ? 1u : 0u);
+        const uint32_t off = (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32;
+        umma_bf16(tmem_base + st * 128, desc_at(q_lo, off), desc_at(k_lo, off), idesc_qk, kk > 0 ? 1u : 0u);
       }
       umma_commit(&s_full[st]);
       umma_commit(&k_empty[st]);
-      if (j > 0) issue_pv(j - 1);
     }
-    issue_pv(n_kb - 1);
     if (prof_on) {
       atomicAdd(p.prof + PROF_M_KFULL, (unsigned long long)m_k);
       atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
+      atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
+    }
+  } else if (warp == 2 && lane == 0) {
+    // ===================== MMA issuer 2: O += P_j.V_j (A = P_j in TMEM) =====================
+    constexpr uint32_t idesc_pv = idesc_128x128(true);
+    long long m_p = 0, m_v = 0;
+    for (int j = 0; j < n_kb; ++j) {
+      const int st = j & 1;
+      PROF_T(a0);
+      mbar_wait(&p_full[st], (j >> 1) & 1);   // P_j written; O already rescaled if block j asked for it
+      PROF_T(a1);
+      mbar_wait(&v_full[st], (j >> 1) & 1);
+      PROF_T(a2);
+      m_p += a1 - a0; m_v += a2 - a1;
+      tc_fence_after();
+      // B = V stored [d-half][128 keys][128 B]: MN-major, LBO = 16 KB between the two 64-wide d slabs, SBO = 1 KB
+      // between 8-key groups, 2 KB per K=16 step
+      const uint32_t v_lo = desc_lo_sw128(sKV + TILE_BYTES * (2 * st + 1), TILE_BYTES / 2);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t a_col = st * 128 + (kk >> 2) * 64 + (kk & 3) * 8;
+        umma_bf16_ts(tmem_base + COL_O, tmem_base + a_col, desc_at(v_lo, kk * 2048), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+      }
+      umma_commit(&pv_done[st]);
+      umma_commit(&v_empty[st]);
+    }
+    if (prof_on) {
       atomicAdd(p.prof + PROF_M_PFULL, (unsigned long long)m_p);
       atomicAdd(p.prof + PROF_M_VFULL, (unsigned long long)m_v);
-      atomicAdd(p.prof + PROF_M_OEMPTY, (unsigned long long)m_o);
-      atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
     }
   } else if (warp >= 4) {
     // ===================== softmax / output =====================
-    // two warpgroups share every query row: warpgroup wg owns keys [64 wg, 64 wg + 64) of each block (one
-    // swizzle atom of the P tile) and output columns d in [64 wg, 64 wg + 64); TMEM lane = row for both
+    // two warpgroups share every query row: warpgroup wg owns keys [64 wg, 64 wg + 64) of each block and output
+    // columns d in [64 wg, 64 wg + 64); TMEM lane = row for both
     const int wg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const int ql = d.q_local0 + r;  // query index inside its segment
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+    float m_ref = -INFINITY, l_run = 0.f;   // reference maximum (log2 domain, scaled) and row sum relative to it
     long long c_sw = 0, c_ld = 0, c_mx = 0, c_aw = 0, c_ab = 0, c_ex = 0, c_fa = 0;
     const long long t_loop0 = prof_on ? clock64() : 0;
 
-    auto absorb = [&](int j, float corr) {  // O_reg = O_reg * corr + O_j   (own 64 columns)
-      const int st = j & 1;
-      PROF_T(w0);
-      mbar_wait(&o_full[st], (j >> 1) & 1);
-      PROF_T(w1);
-      c_aw += w1 - w0;
-      tc_fence_after();
-      uint32_t a0[32], a1[32];
-      const uint32_t to = tmem_base + 256 + st * 128 + lane_addr + wg * 64;
-      tmem_ld_32x32(to, a0);
-      tmem_ld_32x32(to + 32, a1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o[i] = o[i] * corr + __uint_as_float(a0[i]);
-        o[32 + i] = o[32 + i] * corr + __uint_as_float(a1[i]);
-      }
-      tc_fence_before();
-      mbar_arrive(&o_empty[st]);
-      if (prof_on) c_ab += clock64() - w1;
-    };
-
     // validity of this warpgroup's 64 keys of a block (inside the segment AND a real token): every warp builds the two
     // 32-bit words itself with two coalesced loads + ballots, and the loads for block j+1 are issued during block j — no
-    // shared-memory exchange, no named barrier, no global-load latency on the per-block critical path (the phase counters
-    // showed 2073 cycles per key block in "mask + max + exchange" before this, profiles/r2_run08_attn_fwd_phases_before.txt)
+    // shared-memory exchange, no named barrier, no global-load latency on the per-block critical path
     int mk0 = 0, mk1 = 0;
     auto fetch_mask = [&](int j) {
       int row0, valid, local0;
@@ -355,15 +335,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       tmem_ld_32x32(ts, v0);
       tmem_ld_32x32(ts + 32, v1);
       tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_empty[st]);  // scores are in registers: S[st] may be overwritten by QK_{j+2}
       PROF_T(e3);
       c_mx += e1 - e0; c_sw += e2 - e1; c_ld += e3 - e2;
       const int kbase = local0 + wg * 64;  // local index of this warpgroup's first key (own blocks)
       // ---- row max over the own 64 keys, then exchange with the other warpgroup ----
       // masked scores become -inf in place (UNSCALED: scale > 0 keeps -inf), so that the exp loop below is the same
-      // straight-line code for plain and masked blocks (a `plain ? a : b` inside it made the compiler issue both MUFUs
-      // under opposite predicates: 130 MUFU issue slots per warp and block instead of 64)
+      // straight-line code for plain and masked blocks
       const float sl2 = p.scale_log2;
       float mx = -INFINITY;
       if (!plain) {
@@ -384,63 +361,89 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       s_mx[st][wg][r] = mx;
       named_bar_sync(2, 256);
       mx = fmaxf(mx, s_mx[st][wg ^ 1][r]);
-      const float m_new = fmaxf(m_run, mx);
-      const float mu = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = ex2_approx(m_run - mu);
-      // fold the previous block's P.V into the register accumulator (also guarantees the previous P.V has
-      // finished reading the P tile before it is overwritten below)
       PROF_T(e4);
       c_mx += e4 - e3;
-      if (j > 0) absorb(j - 1, corr_prev);
+      // ---- lazy reference maximum: both warpgroups see the same mx and m_ref, so they take the same decision ----
+      const bool bump = mx > m_ref + FWD_RESCALE_LOG2 || (m_ref == -INFINITY && mx > -INFINITY);
+      if (__any_sync(0xffffffffu, bump)) {
+        const float m_new = bump ? mx : m_ref;
+        const float corr = (bump && m_ref > -INFINITY) ? ex2_approx(m_ref - m_new) : 1.f;
+        if (j > 0) {
+          // O holds sum_{i<j} P_i.V_i relative to m_ref: rescale this warp's 32 rows x own 64 columns in place once
+          // P_{j-1}.V_{j-1} (the last MMA that writes O) has retired
+          PROF_T(w0c);
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          PROF_T(w1c);
+          c_aw += w1c - w0c;
+          tc_fence_after();
+          const uint32_t to = tmem_base + COL_O + lane_addr + wg * 64;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t a[32];
+            tmem_ld_32x32(to + half * 32, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) * corr);
+            tmem_st_32x32(to + half * 32, a);
+          }
+          if (prof_on) c_ab += clock64() - w1c;
+        }
+        l_run *= corr;
+        m_ref = m_new;
+      }
+      const float mu = (m_ref == -INFINITY) ? 0.f : m_ref;
       PROF_T(e5);
-      // ---- p = exp2(s - m) -> bf16 into this warpgroup's 64-key atom of the P tile ----
+      // ---- p = exp2(s - m_ref) -> bf16 pairs over this warpgroup's score columns: A operand of P.V ----
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t prow = sP + wg * (TILE_BYTES / 2) + r * 128;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        float pf[32];
+        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = __uint_as_float(half == 0 ? v0[i] : v1[i]);
-          const float pv = ex2_approx(fmaf(sv, sl2, -mu));   // masked: -inf * scale - mu = -inf -> 2^-inf = 0
-          pf[i] = pv;
-          rs4[i & 3] += pv;
+        for (int i = 0; i < 16; ++i) {
+          const float s0 = __uint_as_float(half == 0 ? v0[2 * i] : v1[2 * i]);
+          const float s1 = __uint_as_float(half == 0 ? v0[2 * i + 1] : v1[2 * i + 1]);
+          const float p0 = ex2_approx(fmaf(s0, sl2, -mu));   // masked: -inf * scale - mu = -inf -> 2^-inf = 0
+          const float p1 = ex2_approx(fmaf(s1, sl2, -mu));
+          rs4[(2 * i) & 3] += p0;
+          rs4[(2 * i + 1) & 3] += p1;
+          pk[i] = pack_bf16x2(p0, p1);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int cc = half * 4 + u;  // 16-byte chunk 0..7 within the 128-byte row of the atom
-          const bf16x8 pk = pack8(&pf[u * 8]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((cc ^ (r & 7)) << 4)),
-                       "r"(pk.u.x), "r"(pk.u.y), "r"(pk.u.z), "r"(pk.u.w)
-                       : "memory");
-        }
+        tmem_st_32x16(ts + half * 16, pk);
       }
-      l_run = l_run * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-      m_run = m_new;
-      corr_prev = corr;
+      l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       PROF_T(e6);
-      fence_proxy_async_smem();  // P tile visible to the tensor core (async proxy)
-      mbar_arrive(&p_full);
+      tmem_st_wait();      // P_j and (if any) the rescaled O are in TMEM
+      tc_fence_before();
+      mbar_arrive(&p_full[st]);
       if (prof_on) { c_ex += e6 - e5; c_fa += clock64() - e6; }
     }
     const long long t_loop1 = prof_on ? clock64() : 0;
-    // corr bookkeeping: O_reg before absorbing block j is relative to m_{j-1}; corr_j = exp2(m_{j-1} - m_j) was
-    // computed when block j's scores were processed and O_j (from P_j) is relative to m_j.
-    absorb(n_kb - 1, corr_prev);
     s_l[wg][r] = l_run;
     named_bar_sync(3, 256);
     const float l_tot = l_run + s_l[wg ^ 1][r];
     const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-    if (r < d.q_rows) {
-      if (wg == 0)
-        p.lse2[(long long)d.stat0 + (long long)h * p.stat_h + r] = l_tot > 0.f ? m_run + log2f(l_tot) : INFINITY;
-      bf16* dst = p.out + (long long)(d.q_row0 + r) * p.nq * HD + h * HD + wg * 64;
+    if (n_kb > 0) mbar_wait(&pv_done[(n_kb - 1) & 1], ((n_kb - 1) >> 1) & 1);
+    tc_fence_after();
+    {
+      // the TMEM loads are .sync.aligned: every lane executes them, only the stores are predicated
+      const bool row_ok = r < d.q_rows;
+      if (row_ok && wg == 0)
+        p.lse2[(long long)d.stat0 + (long long)h * p.stat_h + r] = l_tot > 0.f ? m_ref + log2f(l_tot) : INFINITY;
+      bf16* dst = p.out + (long long)(d.q_row0 + (row_ok ? r : 0)) * p.nq * HD + h * HD + wg * 64;
 #pragma unroll
-      for (int i = 0; i < 64; i += 8) {
-        float f[8];
+      for (int half = 0; half < 2; ++half) {
+        uint32_t a[32];
+        tmem_ld_32x32(tmem_base + COL_O + lane_addr + wg * 64 + half * 32, a);
+        tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) f[u] = o[i + u] * inv;
-        *reinterpret_cast<bf16x8*>(dst + i) = pack8(f);
+          for (int i = 0; i < 32; i += 8) {
+            float f[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] = n_kb > 0 ? __uint_as_float(a[i + u]) * inv : 0.f;
+            *reinterpret_cast<bf16x8*>(dst + half * 32 + i) = pack8(f);
+          }
+        }
       }
     }
     if (prof_on && (threadIdx.x == 128 || threadIdx.x == 256)) {   // one thread of each softmax warpgroup
@@ -1088,7 +1091,7 @@ int make_rows_map(CUtensorMap* tm, const void* base, long long rows, long long c
   return 0;
 }
 
-constexpr int SMEM_FWD = 6 * TILE_BYTES + 1024;
+constexpr int SMEM_FWD = 5 * TILE_BYTES + 1024;
 constexpr int SMEM_DQ = DQ_KV_STAGES * 2 * HALF_TILE + 1024;
 constexpr int SMEM_DKV = 2 * TILE_BYTES + DKV_QD_STAGES * 2 * HALF_TILE + 1024;
 

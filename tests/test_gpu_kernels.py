@@ -590,6 +590,42 @@ def test_attention(cuda, attn_mode, B, L, nq, nkv, hd):
         assert err < 2e-2, f"{name} rel err {err}"
 
 
+@pytest.mark.parametrize("B,L,nq,nkv", [(2, 700, 4, 2), (1, 1024, 2, 1)])
+def test_attention_lazy_rescale(cuda, B, L, nq, nkv):
+    """The tcgen05 forward keeps O in TMEM against a LAZY reference maximum and rescales O in place only when a key block
+    exceeds it by more than 2^8.  Keys whose magnitude grows along the sequence make the row maximum climb by far more
+    than that, several times per row: output, lse (through the backward) and gradients must still match fp32."""
+    from distrl_llm_b200 import ops
+    hd = 128
+    qkv = _rand((B * L, (nq + 2 * nkv) * hd), cuda, seed=5).float()
+    ramp = (1.0 + 40.0 * torch.arange(L, device=cuda, dtype=torch.float32) / L).repeat(B).view(-1, 1)
+    qkv[:, nq * hd:(nq + nkv) * hd] *= ramp
+    qkv = qkv.to(torch.bfloat16)
+    key_mask = torch.ones(B, L, dtype=torch.int32, device=cuda)
+    key_mask[-1, L - 9:] = 0
+    out, lse = ops.attn_fwd(qkv, key_mask, B, L, nq, nkv, hd)
+    qr = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qr, key_mask, B, L, nq, nkv, hd)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse[lse < float("inf")]).all()
+    assert _rel_err(out, ref) < 8e-3
+    # the scores really do climb: the fp32 row maxima of the last queries are far above those of the first block
+    with torch.no_grad():
+        q = qr[:L, :hd]
+        k = qr[:L, nq * hd:nq * hd + hd]
+        sc = (q @ k.t()) * hd ** -0.5 * 1.4426950408889634
+        sc = sc.masked_fill(torch.triu(torch.ones(L, L, device=cuda, dtype=torch.bool), 1), float("-inf"))
+        first = sc[-1, :128].max()
+        assert sc[-1].max() - first > 16.0
+    dout = _rand((B * L, nq * hd), cuda, seed=6)
+    (ref * dout.float()).sum().backward()
+    dqkv = ops.attn_bwd(qkv, key_mask, out, dout, lse, B, L, nq, nkv, hd)
+    g = qr.grad
+    nqh = nq * hd
+    for name, sl in (("dq", slice(0, nqh)), ("dk", slice(nqh, nqh + nkv * hd)), ("dv", slice(nqh + nkv * hd, None))):
+        err = _rel_err(dqkv[:, sl], g[:, sl])
+        assert err < 2e-2, f"{name} rel err {err}"
+
+
 # ------------------------------------------------------------------------------------------------
 # packed "shared-prompt" attention (tcgen05, head_dim 128): each distinct prompt stored once
 # ------------------------------------------------------------------------------------------------
