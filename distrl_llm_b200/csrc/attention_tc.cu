@@ -83,8 +83,6 @@ __device__ __forceinline__ void store_row32_sw128(uint32_t tile, int r, int col0
 
 struct AttnParams {
   const int* key_mask;   // [rows] 1 = real token
-  const bf16* qkv;       // bwd (dQ): [rows, (nq+2nkv)*HD], read directly for the Q rows that go to TMEM
-  const bf16* dout;      // bwd (dQ): [rows, nq*HD]
   bf16* out;             // fwd: [rows, nq*HD]
   float* lse2;           // fwd out / bwd in
   const float* delta;    // bwd in
@@ -486,14 +484,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 // ---------------------------------------------------------------------------------------------------
 // dQ
 // ---------------------------------------------------------------------------------------------------
-// dQ: every MMA takes its A operand from TENSOR MEMORY (tcgen05.mma [d], [a], b-desc).  Q and dO of the query block
-// are written there once (tcgen05.st), and dS_j is written back over the S_j accumulator it was computed from, so
-// shared memory only carries the K / V stream (profiles/r2_run14: with all operands in shared memory the 128 B/clk
-// shared-memory port, not the tensor pipe, was the floor: 176 KB per 64-key block).
+// dQ: dS_j never touches shared memory — it is written (bf16 pairs, tcgen05.st) over the S_j accumulator it was computed
+// from and is the TMEM A operand of dQ += dS_j.K_j (tcgen05.mma [d], [a], b-desc).  (profiles/r2_run14: with dS staged
+// in shared memory the 128 B/clk shared-memory port carried 176 KB per 64-key block and was the floor.)
 constexpr int DQ_KV_STAGES = 4;
 template <bool PROF>
 __global__ void __launch_bounds__(384, 1)
-attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_kv64, const AttnParams p) {
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_do128,
+                      const __grid_constant__ CUtensorMap tm_kv64, const AttnParams p) {
   constexpr bool prof_on = PROF;
   const long long t_start = prof_on ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
@@ -502,8 +500,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_kv64, const AttnPar
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // [DQ_KV_STAGES x (K 16K, V 16K)]
-  const uint32_t sKV = smem_base;
+  // [Q 32K][dO 32K][DQ_KV_STAGES x (K 16K, V 16K)] = 192 KB
+  const uint32_t sQ = smem_base, sdO = sQ + TILE_BYTES, sKV = sdO + TILE_BYTES;
   const QBlock d = p.qblocks ? p.qblocks[blockIdx.x] : classic_qblock(p);
   const int h = blockIdx.y;
   const int g = h / (p.nq / p.nkv);
@@ -511,7 +509,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_kv64, const AttnPar
   const int n_kb = kit.n_tot;
 
   if (threadIdx.x == 0) {
-    mbar_init(&qdo_full, 256);
+    mbar_init(&qdo_full, 1);
     mbar_init(&dq_full, 1);
     for (int s = 0; s < DQ_KV_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -533,19 +531,27 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_kv64, const AttnPar
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   pdl_enter();
-  // TMEM columns: S0 [0,64) S1 [64,128) dP0 [128,192) dP1 [192,256) dQ [256,384) Q [384,448) dO [448,512)
-  // (Q / dO: bf16 pairs, column j = d 2j, 2j+1).  dS_j (bf16 pairs) overwrites S_j: keys 32c..32c+31 -> columns [32c, 32c+16)
-  constexpr uint32_t COL_DP = 128, COL_DQ = 256, COL_Q = 384, COL_DO = 448;
+  // TMEM columns: S0 [0,64) S1 [64,128) dP0 [128,192) dP1 [192,256) dQ [256,384)
+  // dS_j (bf16 pairs, column i = keys 2i, 2i+1) overwrites S_j: keys 32c..32c+31 -> columns [32c, 32c+16) of the stage.
+  // Q and dO stay in shared memory (TMA): with dS in TMEM the shared-memory port carries 144 KB per key block, below
+  // what the TMEM read port (56 B/clk, profiles/r2_run22) allows the dS warps anyway, and a Q / dO copy into TMEM
+  // through registers cost 5000 cycles of prologue per CTA (profiles/r2_run18).
+  constexpr uint32_t COL_DP = 128, COL_DQ = 256;
 
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer: K_j / V_j =====================
+    // ===================== TMA producer: Q, dO once, then K_j / V_j =====================
+    mbar_arrive_expect_tx(&qdo_full, 2 * TILE_BYTES);
+    tma_load_rows(smem_gen, &tm_q128, &qdo_full, h * HD, d.q_row0);
+    tma_load_rows(smem_gen + TILE_BYTES / 2, &tm_q128, &qdo_full, h * HD + 64, d.q_row0);
+    tma_load_rows(smem_gen + TILE_BYTES, &tm_do128, &qdo_full, h * HD, d.q_row0);
+    tma_load_rows(smem_gen + TILE_BYTES + TILE_BYTES / 2, &tm_do128, &qdo_full, h * HD + 64, d.q_row0);
     const int kcol = (p.nq + g) * HD, vcol = (p.nq + p.nkv + g) * HD;
     for (int j = 0; j < n_kb; ++j) {
       const int st = j % DQ_KV_STAGES;
       int row0, valid, local0;
       kit.get(d, j, row0, valid, local0);
       mbar_wait(&kv_empty[st], ((j / DQ_KV_STAGES) & 1) ^ 1u);
-      uint8_t* kd = smem_gen + st * 2 * HALF_TILE;
+      uint8_t* kd = smem_gen + 2 * TILE_BYTES + st * 2 * HALF_TILE;
       uint8_t* vd = kd + HALF_TILE;
       mbar_arrive_expect_tx(&kv_full[st], 2 * HALF_TILE);
       tma_load_rows(kd, &tm_kv64, &kv_full[st], kcol, row0);
@@ -560,7 +566,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_kv64, const AttnPar
     // tensor pipe runs the MMAs in arrival order; the order that matters is carried by the mbarriers.
     constexpr uint32_t id_s = idesc_n(64, false);    // [128 q] x [64 keys], B K-major over d
     const bool is_dp = warp == 2;
-    const uint32_t a_col = tmem_base + (is_dp ? COL_DO : COL_Q);
+    const uint32_t a_lo = desc_lo_sw128(is_dp ? sdO : sQ, 16);
     const uint32_t d_col = tmem_base + (is_dp ? COL_DP : 0u);
     mbar_wait(&qdo_full, 0);
     tc_fence_after();
@@ -577,8 +583,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_kv64, const AttnPar
       const uint32_t b_lo = desc_lo_sw128(sKV + k3 * 2 * HALF_TILE + (is_dp ? HALF_TILE : 0), 16);
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {  // d = 128 = 8 x K16, two d-halves
+        const uint32_t aoff = (kk >> 2) * (TILE_BYTES / 2) + (kk & 3) * 32;
         const uint32_t boff = (kk >> 2) * (HALF_TILE / 2) + (kk & 3) * 32;
-        umma_bf16_ts(d_col + st * 64, a_col + kk * 8, desc_at(b_lo, boff), id_s, kk > 0 ? 1u : 0u);
+        umma_bf16(d_col + st * 64, desc_at(a_lo, aoff), desc_at(b_lo, boff), id_s, kk > 0 ? 1u : 0u);
       }
       umma_commit(&sp_full[st]);   // count 2: S_j and dP_j
     }
@@ -622,25 +629,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_kv64, const AttnPar
     const int ql = d.q_local0 + r;
     const bool q_ok = r < d.q_rows;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    // ---- this thread's row of Q (warpgroup 0) / dO (warpgroup 1) -> TMEM, once per CTA ----
-    {
-      const bf16* src = wg == 0 ? p.qkv + (long long)(d.q_row0 + (q_ok ? r : 0)) * (long long)(p.nq + 2 * p.nkv) * HD + h * HD
-                                : p.dout + (long long)(d.q_row0 + (q_ok ? r : 0)) * (long long)p.nq * HD + h * HD;
-      const uint32_t col0 = wg == 0 ? COL_Q : COL_DO;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint4 x = q_ok ? __ldg(reinterpret_cast<const uint4*>(src + half * 64) + u) : make_uint4(0u, 0u, 0u, 0u);
-          v[4 * u] = x.x; v[4 * u + 1] = x.y; v[4 * u + 2] = x.z; v[4 * u + 3] = x.w;
-        }
-        tmem_st_32x32(tmem_base + col0 + half * 32 + lane_addr, v);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&qdo_full);
-    }
     const long long sidx = (long long)d.stat0 + (long long)h * p.stat_h + r;
     const float lse = q_ok ? p.lse2[sidx] : INFINITY;
     const float del = q_ok ? p.delta[sidx] : 0.f;
@@ -1092,7 +1080,7 @@ int make_rows_map(CUtensorMap* tm, const void* base, long long rows, long long c
 }
 
 constexpr int SMEM_FWD = 5 * TILE_BYTES + 1024;
-constexpr int SMEM_DQ = DQ_KV_STAGES * 2 * HALF_TILE + 1024;
+constexpr int SMEM_DQ = 2 * TILE_BYTES + DQ_KV_STAGES * 2 * HALF_TILE + 1024;
 constexpr int SMEM_DKV = 2 * TILE_BYTES + DKV_QD_STAGES * 2 * HALF_TILE + 1024;
 
 int set_attrs() {
@@ -1163,14 +1151,12 @@ int attn_bwd_tc_launch(const void* qkv, const int* key_mask, const void* dout, c
   AttnParams p = base_params(key_mask, nq, nkv, scale);
   p.lse2 = const_cast<float*>(lse);
   p.delta = delta;
-  p.qkv = (const bf16*)qkv;
-  p.dout = (const bf16*)dout;
   p.dqkv = (bf16*)dqkv;
   p.L = L;
   p.stat_h = L;
   {
     dim3 grid((L + BQ - 1) / BQ, nq, B);
-    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 1 ? attn_bwd_dq_tc_kernel<true> : attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DQ, stream, m.q64, p));
+    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 1 ? attn_bwd_dq_tc_kernel<true> : attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DQ, stream, m.q128, m.d128, m.q64, p));
     B200RL_LAUNCH_OK();
   }
   {
@@ -1209,8 +1195,6 @@ int attn_bwd_seg_launch(const void* qkv, const int* key_mask, const void* dout, 
   AttnParams p = base_params(key_mask, nq, nkv, scale);
   p.lse2 = const_cast<float*>(lse);
   p.delta = delta;
-  p.qkv = (const bf16*)qkv;
-  p.dout = (const bf16*)dout;
   p.dqkv = (bf16*)dqkv;
   p.kv_part = kv_part;
   p.qblocks = qblocks_dev;
@@ -1218,7 +1202,7 @@ int attn_bwd_seg_launch(const void* qkv, const int* key_mask, const void* dout, 
   p.stat_h = (int)rows;
   {
     dim3 grid(n_qblocks, nq, 1);
-    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 1 ? attn_bwd_dq_tc_kernel<true> : attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DQ, stream, m.q64, p));
+    B200RL_CUDA_OK(launch_pdl(p.prof && g_attn_prof_which == 1 ? attn_bwd_dq_tc_kernel<true> : attn_bwd_dq_tc_kernel<false>, dim3(grid), dim3(384), SMEM_DQ, stream, m.q128, m.d128, m.q64, p));
     B200RL_LAUNCH_OK();
   }
   {
