@@ -41,17 +41,17 @@ struct AdamArgs {
   const volatile int* status; // world > 1: the group's status word; non-zero (a barrier timed out) = do nothing
 };
 
+// Device-resident copy of "a barrier of this process gave up" (the host-mapped status word), refreshed by every barrier
+// kernel.  The reduce kernel used to read the host-mapped word itself, once per block: 1184 PCIe reads made a 424 MB
+// reduce take 935 us (453 GB/s; profiles/r2_run29_reduce_adam_alone.txt) — now it reads this word from L2.
+__device__ int g_p2p_gave_up = 0;
+
 // WORLD > 0: compile-time learner count, so that all WORLD peer loads of an element are in flight together (a remote
 // load is ~2 us of NVLink latency; issued one after the other they serialise).  WORLD == 0: generic loop.
 template <int WORLD>
 __global__ void __launch_bounds__(256) reduce_adam_kernel(const AdamArgs a) {
   const int world = WORLD > 0 ? WORLD : a.world;
-  if (world > 1 && a.status) {   // a peer never arrived at the barrier: leave every buffer untouched
-    __shared__ int gave_up;
-    if (threadIdx.x == 0) gave_up = *a.status;   // host-mapped word: one PCIe read per block
-    __syncthreads();
-    if (gave_up != 0) return;
-  }
+  if (world > 1 && a.status && g_p2p_gave_up != 0) return;   // a peer never arrived at the barrier: leave every buffer untouched
   const long long n4 = (a.hi - a.lo) / 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -141,6 +141,8 @@ __global__ void p2p_barrier_kernel(const BarrierArgs a) {
     }
     __threadfence_system();
   }
+  __syncthreads();
+  if (t == 0) g_p2p_gave_up = (a.status && *a.status != 0) ? 1 : 0;   // one PCIe read per barrier, for the kernels behind it
 }
 
 // fp32 master -> bf16 operand copies in the padded layouts the GEMM consumes.
