@@ -202,7 +202,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   // [64w, 64w+32) of the stage (the columns warpgroup w read its scores from)
   constexpr uint32_t COL_O = 256;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ===================== TMA producer: Q, then the K ring (a K slot is free as soon as QK_j retired) ====
     mbar_arrive_expect_tx(&q_full, TILE_BYTES);
     tma_load_rows(smem_gen, &tm, &q_full, h * HD, d.q_row0);
@@ -218,7 +218,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       tma_load_rows(k_dst, &tm, &k_full[st], kcol, row0);
       tma_load_rows(k_dst + TILE_BYTES / 2, &tm, &k_full[st], kcol + 64, row0);
     }
-  } else if (warp == 3 && lane == 0) {
+  } else if (warp == 3 && elect_one_sync()) {
     // ===================== TMA producer: V ring (a V slot is free when P.V_j retired) =====================
     const int vcol = (p.nq + p.nkv + g) * HD;
     for (int j = 0; j < n_kb; ++j) {
@@ -231,7 +231,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       tma_load_rows(v_dst, &tm, &v_full[st], vcol, row0);
       tma_load_rows(v_dst + TILE_BYTES / 2, &tm, &v_full[st], vcol + 64, row0);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one_sync()) {
     // ===================== MMA issuer 1: S_j = Q.K_j^T =====================
     constexpr uint32_t idesc_qk = idesc_128x128(false);
     mbar_wait(&q_full, 0);
@@ -261,7 +261,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
       atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
     }
-  } else if (warp == 2 && lane == 0) {
+  } else if (warp == 2 && elect_one_sync()) {
     // ===================== MMA issuer 2: O += P_j.V_j (A = P_j in TMEM) =====================
     constexpr uint32_t idesc_pv = idesc_128x128(true);
     long long m_p = 0, m_v = 0;
@@ -538,7 +538,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
   // through registers cost 5000 cycles of prologue per CTA (profiles/r2_run18).
   constexpr uint32_t COL_DP = 128, COL_DQ = 256;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ===================== TMA producer: Q, dO once, then K_j / V_j =====================
     mbar_arrive_expect_tx(&qdo_full, 2 * TILE_BYTES);
     tma_load_rows(smem_gen, &tm_q128, &qdo_full, h * HD, d.q_row0);
@@ -559,7 +559,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
       tma_load_rows(vd, &tm_kv64, &kv_full[st], vcol, row0);
       tma_load_rows(vd + HALF_TILE / 2, &tm_kv64, &kv_full[st], vcol + 64, row0);
     }
-  } else if ((warp == 1 || warp == 2) && lane == 0) {
+  } else if ((warp == 1 || warp == 2) && elect_one_sync()) {
     // ===================== MMA issuers 1 / 2: S_j = Q.K_j^T (warp 1), dP_j = dO.V_j^T (warp 2) =====================
     // Three issuing threads on three SM sub-partitions (profiles/r2_run11, r2_run17: one thread needs 80-100 cycles per
     // tcgen05.mma while an N = 64 MMA executes in < 50, so the issuer, not the tensor pipe, paced the kernel).  The
@@ -594,7 +594,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_
       atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
       atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
     }
-  } else if (warp == 3 && lane == 0) {
+  } else if (warp == 3 && elect_one_sync()) {
     // ===================== MMA issuer 3: dQ += dS_j.K_j =====================
     constexpr uint32_t id_dq = idesc_n(128, true);   // [128 q] x [128 d], B = K_j MN-major (k = keys)
     long long m_d = 0;
@@ -808,7 +808,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
   // TMEM columns: S^T0 [0,64) S^T1 [64,128) dP^T0 [128,192) dP^T1 [192,256) dK [256,384) dV [384,512)
   // P^T_j / dS^T_j (bf16 pairs) overwrite S^T_j / dP^T_j: queries 32c..32c+31 -> columns [32c, 32c+16) of the stage
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ===================== TMA producer =====================
     const int kcol = (p.nq + g) * HD, vcol = (p.nq + p.nkv + g) * HD;
     mbar_arrive_expect_tx(&kv_full, 2 * TILE_BYTES);
@@ -829,7 +829,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       tma_load_rows(dd, &tm_do64, &qd_full[st], h * HD, qrow);
       tma_load_rows(dd + HALF_TILE / 2, &tm_do64, &qd_full[st], h * HD + 64, qrow);
     }
-  } else if ((warp == 1 || warp == 2) && lane == 0) {
+  } else if ((warp == 1 || warp == 2) && elect_one_sync()) {
     // ===================== MMA issuers 1 / 2: S^T = K.Q^T (warp 1), dP^T = V.dO^T (warp 2); see the dQ kernel ==========
     constexpr uint32_t id_s = idesc_n(64, false);    // [128 keys] x [64 queries], K-major over d
     const bool is_dp = warp == 2;
@@ -860,7 +860,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __gri
       atomicAdd(p.prof + PROF_M_SEMPTY, (unsigned long long)m_s);
       atomicAdd(p.prof + PROF_M_TOTAL, (unsigned long long)(clock64() - m_t0));
     }
-  } else if (warp == 3 && lane == 0) {
+  } else if (warp == 3 && elect_one_sync()) {
     // ===================== MMA issuer 3: dV += P^T.dO and dK += dS^T.Q =====================
     constexpr uint32_t id_g = idesc_n(128, true);    // [128 keys] x [128 d], B = dO / Q MN-major (k = queries)
     long long m_d = 0;

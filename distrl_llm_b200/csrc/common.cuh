@@ -130,6 +130,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// one lane of the (converged) warp, chosen by the hardware: the compiler knows the region below it runs on a single
+// elected lane, which keeps the tcgen05.mma operands in uniform registers (with `lane == 0` it re-elects and re-broadcasts
+// them around every MMA)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

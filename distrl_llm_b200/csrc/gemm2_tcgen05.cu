@@ -233,7 +233,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   // bytes one CTA stages per k-block of an ext unit: its 128 rows of A + its half of the ext operand
   const uint32_t ext_b_bytes = B_MN ? ((p.ext_n / 2 + 63) / 64) * 8192u : (uint32_t)(p.ext_n / 2) * BK * 2;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -314,7 +314,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
+  } else if (warp == 1 && leader && elect_one_sync()) {
     // ===================== MMA issuer (leader CTA only) =====================
     // instruction M = 256 (both CTAs), N = BN
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((B_MN ? 1u : 0u) << 16) |
@@ -336,14 +336,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + A_TILE_BYTES;
+          const uint32_t a_lo = smem_desc_lo(sa, 16);
+          const uint32_t b_lo = smem_desc_lo(sa + A_TILE_BYTES, B_MN ? 8192 : 16);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
-                                     : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16_pair(tmem_d, da, db, idesc_ext, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_pair(tmem_d, smem_desc_at(a_lo, k * 32), smem_desc_at(b_lo, B_MN ? k * 2048 : k * 32), idesc_ext,
+                           (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit_pair(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
@@ -368,6 +366,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t a_lo = smem_desc_lo(sa, 16);   // descriptors: built once per k-block, an offset added per MMA
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           if (NT == 2 && kb == kb_begin) {   // sub-tile t may start as soon as the epilogue drained ITS accumulator
@@ -375,14 +374,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             tc_fence_after();
           }
           const uint32_t tmem_d = tmem_base + (acc0 + t) * C::ACC_STRIDE;
-          const uint32_t sb = sa + A_TILE_BYTES + t * C::B_TILE_BYTES;
+          const uint32_t b_lo = smem_desc_lo(sa + A_TILE_BYTES + t * C::B_TILE_BYTES, B_MN ? 8192 : 16);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
-                                     : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16_pair(tmem_d, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_pair(tmem_d, smem_desc_at(a_lo, k * 32), smem_desc_at(b_lo, B_MN ? k * 2048 : k * 32), idesc,
+                           (kb > kb_begin || k > 0) ? 1u : 0u);
         }
         umma_commit_pair(&empty_bar[stage]);
         if (++stage == STAGES) {

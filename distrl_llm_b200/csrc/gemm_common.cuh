@@ -69,6 +69,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
+// The same descriptor in two halves, for the MMA-issuing thread: every instruction it spends per MMA is serial latency
+// (one thread issues all MMAs of a CTA pair; profiles/r2_run11, r2_run12: ~100 cycles per MMA with the descriptor rebuilt
+// each time vs 128 cycles of execution for a 256 x 256 x 16 pair MMA).  The low word is built once per k-block and a byte
+// offset is ADDED per MMA (the address field holds addr >> 4 in bits 0-13; shared memory is < 256 KB: no carry leaves it).
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+constexpr uint32_t SMEM_DESC_HI_SBO1024 = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t smem_desc_at(uint32_t lo, uint32_t byte_off) {
+  return ((uint64_t)SMEM_DESC_HI_SBO1024 << 32) | (uint64_t)(lo + (byte_off >> 4));
+}
 // Instruction descriptor (InstrDescriptor): c_format[4,6)=F32(1), a_format[7,10)=BF16(1),
 // b_format[10,13)=BF16(1), a_major bit15, b_major bit16 (0 = K-major, 1 = MN-major),
 // n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.

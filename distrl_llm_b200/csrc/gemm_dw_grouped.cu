@@ -75,7 +75,7 @@ dw_grouped_kernel(const __grid_constant__ DwMaps maps, const DwParams p) {
   pdl_enter();
 
   const int num_units = p.unit0[p.nprob];
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -101,7 +101,7 @@ dw_grouped_kernel(const __grid_constant__ DwMaps maps, const DwParams p) {
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one_sync()) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(DW_BN, true, true);
     int stage = 0;

@@ -81,7 +81,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
   const int kb_total = p.kb1 + p.kb2;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -123,7 +123,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one_sync()) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
     int stage = 0;
