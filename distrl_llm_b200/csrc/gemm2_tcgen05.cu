@@ -1035,7 +1035,13 @@ bool gemm_pair_wide_enabled() { return wide_mode() != 0; }
 bool gemm_pair_wide_for(int M, int n_cols, int k_total) {
   const int mode = wide_mode();
   if (mode == 0 || n_cols < 512) return false;
-  if (mode == 2 && (k_total + BK - 1) / BK < 256) return false;
+  static int min_kb = -1;   // B200RL_GEMM_WIDE_MIN_KB: k-blocks from which a GEMM counts as K-long (A/B knob)
+  if (min_kb < 0) {
+    const char* e = getenv("B200RL_GEMM_WIDE_MIN_KB");
+    min_kb = e ? atoi(e) : 256;
+    if (min_kb <= 0) min_kb = 256;
+  }
+  if (mode == 2 && (k_total + BK - 1) / BK < min_kb) return false;
   const long long mb = (M + 2 * BM - 1) / (2 * BM);
   return mb * ((n_cols + 511) / 512) >= num_sms() / 2;
 }
