@@ -11,12 +11,17 @@
 //             same attention inputs per query.  Descriptors come from arrays built on the host.
 //
 // Forward (one CTA per <=128-query block and q head):
-//   warp 0 / 3 : TMA producers (Q + K ring / V ring)       warp 1 : MMA issuer      warp 2 : TMEM allocator
+//   warp 0 / 3 : TMA producers (Q + K ring / V ring)    warp 1 : issues S_j = Q.K_j^T    warp 2 : TMEM allocator, issues
+//   O += P_j.V_j    (every single-lane role is entered through elect.sync, see common.cuh)
 //   warps 4-11 : two softmax warpgroups; thread = query row (TMEM lane); warpgroup wg owns keys [64wg,64wg+64) of
-//                each 128-key block and output columns [64wg, 64wg+64); O_reg = O_reg*corr + P_j.V_j (from TMEM)
+//                each 128-key block and output columns [64wg, 64wg+64).  O lives in TMEM for the whole key loop (lazy
+//                reference maximum); P_j is written with tcgen05.st over S_j and is the TMEM A operand of P_j.V_j.
 // Backward: dQ kernel per query block (64-key inner blocks, dQ accumulates in TMEM); dK/dV kernel per key block and
 // per query segment that sees it (64-query inner blocks over all q heads of the GQA group, dK/dV accumulate in TMEM;
-// in the packed layout the per-(key block, query segment) partials are fp32 slabs summed in fixed order).
+// in the packed layout the per-(key block, query segment) partials are fp32 slabs summed in fixed order).  dS / P^T / dS^T
+// are TMEM A operands as well; three MMA-issuing threads per CTA (scores, dP, gradients).
+// The design follows three measurements: ~100 cycles per MMA for one issuing thread, the 128 B/clk
+// shared-memory port, and the 56 B/clk TMEM read port.
 #include "common.cuh"
 #include "b200rl.h"
 #include <string.h>
@@ -474,10 +479,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 // BACKWARD on tcgen05.  Deterministic two-kernel split like the mma.sync version:
 //   dQ  kernel: CTA = (128-query block, q head, sequence), inner loop over 64-key blocks j up to the diagonal:
 //       S_j = Q.K_j^T, dP_j = dO.V_j^T (TMEM, double buffered)  ->  softmax warps: P = exp2(S*c - lse2),
-//       dS = scale * P * (dP - delta) as a bf16 smem tile  ->  dQ += dS_j.K_j (TMEM accumulator).
+//       dS = scale * P * (dP - delta) written (bf16) over S_j in TMEM  ->  dQ += dS_j.K_j (TMEM accumulator).
 //   dKV kernel: CTA = (128-key block, kv head, sequence), inner loop over (q head of the GQA group, 64-query
-//       block at or after the key block): S^T = K.Q^T, dP^T = V.dO^T (TMEM, double buffered) -> P^T, dS^T tiles
-//       -> dV += P^T.dO, dK += dS^T.Q (TMEM accumulators, summed over the whole group: no atomics).
+//       block at or after the key block): S^T = K.Q^T, dP^T = V.dO^T (TMEM, double buffered) -> P^T, dS^T written
+//       over them -> dV += P^T.dO, dK += dS^T.Q (TMEM accumulators, summed over the whole group: no atomics).
 // The 64-row streamed tiles are stored [d-half][64 rows][128 B]; the SAME smem tile is read K-major (rows = N)
 // by the score MMAs and MN-major (rows = K) by the gradient MMAs.
 // ==================================================================================================
